@@ -1,0 +1,165 @@
+/* showo_b200.h -- C ABI of libshowo_b200.so, the sm_100a engine behind the Show-o hot path.
+ *
+ * The reference (showlab/Show-o) is pure Python and has no FFI: its seam is the method surface of
+ * `models.Showo` / `models.MAGVITv2`.  Every entry point below names the reference method
+ * it stands behind; the Python shim in show-o_b200/ (classes Showo, MAGVITv2 with the reference signatures) is
+ * the binding a maintainer would add -- see INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C types only; all `*_dev` pointers are device pointers owned by the caller (torch tensors);
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises unless stated;
+ *   - every function returns 0 on success, non-zero on failure; showo_last_error() describes the failure
+ *     (thread-local, valid until the next call on the same thread).  Nothing throws across the ABI;
+ *   - an engine handle is re-entrant across handles but not thread-safe per handle;
+ *   - there is no CPU fallback: on a box without an sm_100 device every compute entry point fails loudly.
+ */
+#ifndef SHOWO_B200_H_
+#define SHOWO_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SHOWO_B200_ABI_VERSION 1
+#if defined(__GNUC__)
+#define SHOWO_API __attribute__((visibility("default")))
+#else
+#define SHOWO_API
+#endif
+
+/* Per-sequence closed form of the omni attention mask (training/omni_attention.py:48-96 mask_mods; equals the dense
+ * builders training/prompting_utils.py:466-511,591-624 on every non-pad query row).  Query q may attend key k iff
+ *   ( k <= q  ||  full_begin <= q < full_end  ||  win_begin <= k < win_end )  &&  !( k < pad_end && q >= pad_end )
+ * t2i row : pad_end = #left pads, full = [soi, eoi], win = empty.   lm row : all zero (pure causal).
+ * mmu row : win = [0, eoi_pos+1).   mmu_vit row : win = [1+sys+1, 1+sys+1+576). */
+typedef struct {
+    int32_t pad_end;
+    int32_t full_begin, full_end;
+    int32_t win_begin, win_end;
+} showo_seq_mask_t;
+
+/* Backbone geometry (PhiConfig as instantiated by models/modeling_showo.py:38-47) + Show-o vocabulary layout
+ * (configs/showo_demo.yaml:19-24). head_dim = hidden / n_heads must be 64, rotary_dim 32. */
+typedef struct {
+    int32_t vocab_size;              /* 58498 */
+    int32_t hidden;                  /* 2048  */
+    int32_t n_layers;                /* 24    */
+    int32_t n_heads;                 /* 32    */
+    int32_t ffn;                     /* 8192  */
+    int32_t rotary_dim;              /* 32    */
+    int32_t max_pos;                 /* 2048  */
+    float   ln_eps;                  /* 1e-5  */
+    float   rope_theta;              /* 10000 */
+    int32_t llm_vocab_size;          /* 50295 */
+    int32_t num_new_special_tokens;  /* 10    */
+    int32_t codebook_size;           /* 8192  */
+} showo_config_t;
+
+typedef struct showo_engine showo_engine_t;
+
+SHOWO_API const char* showo_last_error(void);
+SHOWO_API int showo_abi_version(void);
+/* number of CUDA devices with compute capability 10.x visible to the library (0 on a CPU box) */
+SHOWO_API int showo_device_count(void);
+
+/* models/modeling_showo.py:27-54  Showo.__init__ */
+SHOWO_API int showo_engine_create(const showo_config_t* cfg, int device, showo_engine_t** out);
+SHOWO_API int showo_engine_destroy(showo_engine_t* e);
+
+/* Showo.from_pretrained / load_state_dict: hand one fp32 tensor of the reference state_dict (key names of
+ * SURVEY.md section 8b, e.g. "showo.model.layers.3.mlp.fc1.weight") to the engine.  `data` may be a host or a device
+ * pointer (is_device).  The engine converts to bf16 and copies into its fused layout (q|k|v|fc1 rows, dense|fc2
+ * columns); it does not keep a reference to `data`.  Synchronous. */
+SHOWO_API int showo_load_weight(showo_engine_t* e, const char* name, const float* data, int64_t numel, int is_device);
+/* returns 0 when every tensor of the model has been loaded, else sets last_error to the first missing key */
+SHOWO_API int showo_weights_complete(showo_engine_t* e);
+
+/* models/modeling_showo.py:59-79  Showo.forward (labels=None): logits fp32 [B, L, vocab].
+ * Exactly one of ids_dev [B,L] (int64) / embeds_dev [B,L,hidden] (fp32) is non-NULL.  masks_host: B descriptors. */
+SHOWO_API int showo_forward(showo_engine_t* e, const int64_t* ids_dev, const float* embeds_dev, int B, int L,
+                  const showo_seq_mask_t* masks_host, float* logits_out_dev, void* stream);
+
+/* One denoise-step forward of t2i_generate (modeling_showo.py:136-147) WITHOUT sampling, for parity tests:
+ * runs the text prefix [0, prefix_len) once and the image rows, returns the sliced logits
+ * [n_branch*B, N, codebook] fp32 (cond rows first, then uncond rows if uncond_ids_dev != NULL).
+ * ids rows are [prefix (prefix_len) | soi | N image ids | eoi], L = prefix_len + N + 2. */
+SHOWO_API int showo_t2i_logits(showo_engine_t* e, const int64_t* ids_dev, const int64_t* uncond_ids_dev, int B, int L, int N,
+                     int prefix_len, const showo_seq_mask_t* masks_host, float* logits_out_dev, void* stream);
+
+/* models/modeling_showo.py:104-181  Showo.t2i_generate.  ids_dev [B,L] int64 is updated IN PLACE like the reference.
+ * The host evaluates the schedule (the reference takes an arbitrary Python callable): mask_len_floor[s] =
+ * floor(N * noise_schedule((s+1)/T)), temperature[s] = the compounded temperature handed to mask_by_random_topk.
+ * noise_expo_dev [T, B*N, C] / noise_unif_dev [T, B, N]: optional host-drawn noise for parity runs (the order
+ * torch.multinomial / gumbel_noise consume it); NULL -> counter-based Philox keyed by (seed, step, row, col).
+ * sampled_out_dev [B,N] int64 receives the last step's sampled codes (the function's return value).
+ * masks_host: B descriptors (guidance == 0 or uncond NULL) or 2B (cond rows then uncond rows). */
+SHOWO_API int showo_t2i_generate(showo_engine_t* e, int64_t* ids_dev, const int64_t* uncond_ids_dev, int B, int L, int N,
+                       int prefix_len, const showo_seq_mask_t* masks_host, int timesteps, float guidance_scale,
+                       const int32_t* mask_len_floor, const float* temperature, const float* noise_expo_dev,
+                       const float* noise_unif_dev, uint64_t seed, int64_t* sampled_out_dev, void* stream);
+
+/* models/modeling_showo.py:149-179 + models/sampling.py:31-36: the fused sampler step on caller-supplied logits
+ * [B, N, C] fp32 (cond, optional uncond).  ids_dev [B, ids_stride]: image ids at [ids_pos0, ids_pos0+N), updated in
+ * place; sampled_out_dev [B,N] int64; masking_out_dev optional [B,N] uint8. */
+SHOWO_API int showo_sampler_step(const float* logits_cond_dev, const float* logits_uncond_dev, int B, int N, int C,
+                       float guidance_scale, int64_t* ids_dev, int64_t ids_stride, int ids_pos0, int image_offset,
+                       int mask_token_id, int mask_len_floor, float temperature, const float* noise_expo_dev,
+                       const float* noise_unif_dev, uint64_t seed, uint32_t step, int64_t* sampled_out_dev,
+                       uint8_t* masking_out_dev, void* stream);
+
+/* models/modeling_showo.py:183-240  Showo.mmu_generate, batched with a KV cache: row b is exactly what the
+ * reference returns for a B=1 call on row b (greedy when top_k == 1).  ids_dev [B, L0] int64 (or embeds_dev
+ * [B, L0, hidden] fp32).  out_tokens_dev [B, max_new_tokens] int64, out_lengths_dev [B] int32 (tokens produced
+ * up to and including eot; eot_token < 0 disables early stop).  Only top_k == 1 (the reference script's
+ * setting, inference_mmu.py:81) is supported. */
+SHOWO_API int showo_mmu_generate(showo_engine_t* e, const int64_t* ids_dev, const float* embeds_dev, int B, int L0,
+                       const showo_seq_mask_t* masks_host, int max_new_tokens, int top_k, float temperature,
+                       int64_t eot_token, int64_t* out_tokens_dev, int32_t* out_lengths_dev, void* stream);
+
+/* model.showo.model.embed_tokens(ids) as called from outside (inference_mmu.py:134-136): out fp32 [n, hidden] */
+SHOWO_API int showo_embed_tokens(showo_engine_t* e, const int64_t* ids_dev, int64_t n, float* out_dev, void* stream);
+
+/* seconds spent / kernels launched by the last generate call (for bench.py's gpu_launches) */
+SHOWO_API int64_t showo_kernel_launches(showo_engine_t* e);
+
+/* ---------------------------------------------------------------- MAGVIT-v2 (models/modeling_magvitv2.py:402-433) */
+typedef struct magvit_engine magvit_engine_t;
+SHOWO_API int magvit_engine_create(int device, magvit_engine_t** out);
+SHOWO_API int magvit_engine_destroy(magvit_engine_t* m);
+/* one fp32 tensor of MAGVITv2.state_dict() ("decoder.up.2.block.1.conv1.weight", ...) */
+SHOWO_API int magvit_load_weight(magvit_engine_t* m, const char* name, const float* data, int64_t numel, int is_device);
+SHOWO_API int magvit_weights_complete(magvit_engine_t* m);
+/* MAGVITv2.decode_code(ids, shape=(h,w)): ids_dev [B, h*w] int64 -> pixels_out_dev [B,3,16h,16w] fp32 (NCHW) */
+SHOWO_API int magvit_decode_code(magvit_engine_t* m, const int64_t* ids_dev, int B, int h, int w, float* pixels_out_dev,
+                       void* stream);
+/* decode + the caller's post-processing (inference_t2i.py:338-341): clamp((x+1)/2,0,1)*255 -> uint8 NHWC [B,16h,16w,3] */
+SHOWO_API int magvit_decode_code_u8(magvit_engine_t* m, const int64_t* ids_dev, int B, int h, int w, uint8_t* images_out_dev,
+                          void* stream);
+/* MAGVITv2.get_code(pixel_values): pixels_dev [B,3,R,R] fp32 NCHW -> ids_out_dev [B,(R/16)^2] int64 */
+SHOWO_API int magvit_get_code(magvit_engine_t* m, const float* pixels_dev, int B, int R, int64_t* ids_out_dev, void* stream);
+SHOWO_API int64_t magvit_kernel_launches(magvit_engine_t* m);
+
+/* ---------------------------------------------------------------- raw kernels, exported for the parity tests */
+/* C[M,N] (+epilogue) = A[M,K] bf16 * B[N,K]^T bf16 on tcgen05; epi 0: bf16 out = acc+bias (gelu_new on cols >=
+ * gelu_from), 1: f32 out = resid + acc + bias, 2: f32 out = acc + bias.  block_n 0 = auto. */
+SHOWO_API int showo_gemm_bf16(const void* A_dev, int64_t lda, const void* B_dev, int64_t ldb, int M, int N, int K, void* out_dev,
+                    int64_t ldc, const float* bias_dev, const float* resid_dev, int64_t ldr, int gelu_from, int epi,
+                    int block_n, void* stream);
+/* omni-mask attention over a [n_seq*rows, ld] bf16 buffer holding k|v|q column blocks (test entry: runs q/k layernorm
+ * + rotary + cache scatter, then attention; output overwrites the q block). */
+SHOWO_API int showo_attention_test(void* qkv_dev, int64_t ld, int n_seq, int rows_per_seq, int pos0, int H,
+                         const float* qg, const float* qb, const float* kg, const float* kb, float eps,
+                         float rope_theta, int rotary_dim, void* kcache_dev, void* vtcache_dev, int Lmax, int n_keys,
+                         const showo_seq_mask_t* masks_host, void* stream);
+SHOWO_API int showo_layernorm_test(const float* x_dev, const float* gamma_dev, const float* beta_dev, float eps, void* out_bf16_dev,
+                         int rows, int D, void* stream);
+/* NHWC bf16 3x3 (taps=9) or 1x1 (taps=1) convolution, stride 1, same padding; w [cout_pad, taps*cin] bf16 */
+SHOWO_API int showo_conv_test(const void* x_dev, const void* w_dev, const float* bias_dev, const void* resid_dev, void* out_dev,
+                    int NB, int H, int W, int cin, int cout, int taps, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHOWO_B200_H_ */

@@ -1,0 +1,288 @@
+// Omni-mask attention (causal over text, bidirectional inside image spans, always-visible windows, left-pad removal).
+//
+// The mask is never materialised: each (query, key) pair evaluates the closed-form predicate of showo_seq_mask_t in
+// registers, and whole 64-key tiles that the predicate rules out for the CTA's query range are skipped.
+//
+// Prefill / denoise-step kernel: flash-style, one CTA = 64 query rows of one (sequence, head); K tiles [64 keys][64]
+// and V^T tiles [64 dims][64 keys] stream through a double-buffered cp.async pipeline; QK^T and PV run on the tensor
+// cores (mma.sync m16n8k16 bf16, fp32 accumulate), softmax in fp32 with exp2.  head_dim is fixed at 64.
+// Attention is ~3 % of the step FLOPs at L=387, the tcgen05 GEMMs carry the rest.
+//
+// Decode kernel: one query per sequence against the KV cache (mmu_generate), HBM-bound, CUDA cores.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace showo {
+
+__device__ __forceinline__ bool omni_allowed(const showo_seq_mask_t& m, int q, int k) {
+    const bool ok = (k <= q) | ((q >= m.full_begin) & (q < m.full_end)) | ((k >= m.win_begin) & (k < m.win_end));
+    return ok & !((k < m.pad_end) & (q >= m.pad_end));
+}
+// conservative: can ANY (q in [q_lo,q_hi], k in [k_lo,k_hi)) pair be allowed?
+__device__ __forceinline__ bool omni_tile_possible(const showo_seq_mask_t& m, int q_lo, int q_hi, int k_lo, int k_hi) {
+    if (k_hi <= m.pad_end && q_lo >= m.pad_end) return false;
+    const bool causal = k_lo <= q_hi;
+    const bool full = (q_hi >= m.full_begin) && (q_lo < m.full_end);
+    const bool win = (k_lo < m.win_end) && (k_hi > m.win_begin);
+    return causal || full || win;
+}
+
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+constexpr int kTileK = 64;     // keys per smem tile
+constexpr int kPad = 72;       // padded smem row (elements) -> conflict-free 32-bit fragment loads
+constexpr float kNegBig = -1.0e30f;
+
+__global__ void __launch_bounds__(128) omni_attention_kernel(AttnArgs a) {
+    __shared__ __align__(16) bf16 Ks[2][kTileK][kPad];
+    __shared__ __align__(16) bf16 Vs[2][64][kPad];
+
+    const int seq = blockIdx.z, h = blockIdx.y;
+    const int q0 = blockIdx.x * 64;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    const showo_seq_mask_t msk = a.masks[seq];
+
+    // ---- Q fragments (rows r0 = q0 + warp*16 + g and r0 + 8), straight from global
+    const int r0 = q0 + warp * 16 + g;
+    const int r1 = r0 + 8;
+    const bool r0_ok = r0 < a.rows_per_seq, r1_ok = r1 < a.rows_per_seq;
+    bf16* qrow0 = a.q + ((int64_t)seq * a.rows_per_seq + r0) * a.ld + h * 64;
+    bf16* qrow1 = a.q + ((int64_t)seq * a.rows_per_seq + r1) * a.ld + h * 64;
+    uint32_t qf[4][4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        const int c = kk * 16 + t4 * 2;
+        qf[kk][0] = r0_ok ? *reinterpret_cast<const uint32_t*>(qrow0 + c) : 0u;
+        qf[kk][1] = r1_ok ? *reinterpret_cast<const uint32_t*>(qrow1 + c) : 0u;
+        qf[kk][2] = r0_ok ? *reinterpret_cast<const uint32_t*>(qrow0 + c + 8) : 0u;
+        qf[kk][3] = r1_ok ? *reinterpret_cast<const uint32_t*>(qrow1 + c + 8) : 0u;
+    }
+    const int qpos0 = a.pos0 + r0, qpos1 = a.pos0 + r1;
+    const int cta_q_lo = a.pos0 + q0;
+    const int cta_q_hi = a.pos0 + min(q0 + 63, a.rows_per_seq - 1);
+
+    const bf16* kbase = a.kcache + ((int64_t)seq * a.H + h) * (int64_t)a.Lmax * 64;
+    const bf16* vbase = a.vtcache + ((int64_t)seq * a.H + h) * 64 * (int64_t)a.Lmax;
+    const int n_tiles = (a.n_keys + kTileK - 1) / kTileK;
+
+    auto next_tile = [&](int kt) {
+        while (kt < n_tiles &&
+               !omni_tile_possible(msk, cta_q_lo, cta_q_hi, kt * kTileK, min((kt + 1) * kTileK, a.n_keys)))
+            ++kt;
+        return kt;
+    };
+    auto load_tile = [&](int kt, int buf) {
+        const int k0 = kt * kTileK;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = threadIdx.x + i * 128;   // 0..511
+            const int row = idx >> 3, ch = idx & 7;
+            cp_async16(&Ks[buf][row][ch * 8], kbase + (int64_t)(k0 + row) * 64 + ch * 8, 16);
+            cp_async16(&Vs[buf][row][ch * 8], vbase + (int64_t)row * a.Lmax + k0 + ch * 8, 16);
+        }
+        cp_async_commit();
+    };
+
+    float o[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+    float m0 = kNegBig, m1 = kNegBig, l0 = 0.f, l1 = 0.f;
+    const float sc = a.scale * 1.4426950408889634f;
+
+    int kt = next_tile(0);
+    int buf = 0;
+    if (kt < n_tiles) load_tile(kt, 0);
+    while (kt < n_tiles) {
+        const int kt_next = next_tile(kt + 1);
+        if (kt_next < n_tiles) {
+            load_tile(kt_next, buf ^ 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+
+        // ---- S = Q K^T
+        float s[8][4];
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) { s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f; }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb) {
+                const bf16* kr = &Ks[buf][nb * 8 + g][kk * 16 + t4 * 2];
+                const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kr);
+                const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kr + 8);
+                mma_bf16_16816(s[nb], qf[kk], b0, b1);
+            }
+        }
+        // ---- scale + mask + online softmax
+        const int k0 = kt * kTileK;
+        float tm0 = kNegBig, tm1 = kNegBig;
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int col = k0 + nb * 8 + t4 * 2 + (e & 1);
+                const int qp = (e < 2) ? qpos0 : qpos1;
+                const bool ok = (col < a.n_keys) && omni_allowed(msk, qp, col);
+                const float v = ok ? s[nb][e] * sc : kNegBig;
+                s[nb][e] = v;
+                if (e < 2) tm0 = fmaxf(tm0, v); else tm1 = fmaxf(tm1, v);
+            }
+        }
+        tm0 = fmaxf(tm0, __shfl_xor_sync(0xffffffffu, tm0, 1));
+        tm0 = fmaxf(tm0, __shfl_xor_sync(0xffffffffu, tm0, 2));
+        tm1 = fmaxf(tm1, __shfl_xor_sync(0xffffffffu, tm1, 1));
+        tm1 = fmaxf(tm1, __shfl_xor_sync(0xffffffffu, tm1, 2));
+        const float mn0 = fmaxf(m0, tm0), mn1 = fmaxf(m1, tm1);
+        const float al0 = exp2f(m0 - mn0), al1 = exp2f(m1 - mn1);
+        m0 = mn0; m1 = mn1;
+        l0 *= al0; l1 *= al1;
+#pragma unroll
+        for (int nd = 0; nd < 8; ++nd) { o[nd][0] *= al0; o[nd][1] *= al0; o[nd][2] *= al1; o[nd][3] *= al1; }
+        uint32_t pf[4][4];
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) {
+            const float p0 = exp2f(s[nb][0] - m0), p1 = exp2f(s[nb][1] - m0);
+            const float p2 = exp2f(s[nb][2] - m1), p3 = exp2f(s[nb][3] - m1);
+            l0 += p0 + p1; l1 += p2 + p3;
+            const int kk = nb >> 1;
+            if ((nb & 1) == 0) { pf[kk][0] = pack_bf16(p0, p1); pf[kk][1] = pack_bf16(p2, p3); }
+            else               { pf[kk][2] = pack_bf16(p0, p1); pf[kk][3] = pack_bf16(p2, p3); }
+        }
+        // ---- O += P V   (B operand = V^T tile: [dim][key], keys contiguous)
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+            for (int nd = 0; nd < 8; ++nd) {
+                const bf16* vr = &Vs[buf][nd * 8 + g][kk * 16 + t4 * 2];
+                const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vr);
+                const uint32_t b1 = *reinterpret_cast<const uint32_t*>(vr + 8);
+                mma_bf16_16816(o[nd], pf[kk], b0, b1);
+            }
+        }
+        __syncthreads();
+        buf ^= 1;
+        kt = kt_next;
+    }
+
+    // ---- finalise: row sums across the quad, normalise, write over q
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;
+#pragma unroll
+    for (int nd = 0; nd < 8; ++nd) {
+        const int c = nd * 8 + t4 * 2;
+        if (r0_ok) *reinterpret_cast<uint32_t*>(qrow0 + c) = pack_bf16(o[nd][0] * i0, o[nd][1] * i0);
+        if (r1_ok) *reinterpret_cast<uint32_t*>(qrow1 + c) = pack_bf16(o[nd][2] * i1, o[nd][3] * i1);
+    }
+}
+
+int omni_attention(const AttnArgs& a, cudaStream_t st) {
+    if (a.n_seq == 0 || a.rows_per_seq == 0) return 0;
+    SHOWO_CHECK(a.Lmax % 64 == 0, "attention: Lmax must be a multiple of 64");
+    SHOWO_CHECK(a.n_keys <= a.Lmax, "attention: n_keys exceeds the cache length");
+    dim3 grid(cdiv(a.rows_per_seq, 64), a.H, a.n_seq);
+    omni_attention_kernel<<<grid, 128, 0, st>>>(a);
+    note_launch();
+    SHOWO_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ decode (1 query / seq)
+__global__ void __launch_bounds__(128) omni_attention_decode_kernel(AttnArgs a) {
+    extern __shared__ float sc_s[];             // [n_keys]
+    __shared__ float red[8];
+    const int h = blockIdx.x, seq = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const showo_seq_mask_t msk = a.masks[seq];
+    const int qpos = a.pos0;
+    bf16* qrow = a.q + (int64_t)seq * a.rows_per_seq * a.ld + h * 64;
+    float q[64];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint4 u = *reinterpret_cast<const uint4*>(qrow + i * 8);
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = __bfloat1622float2(h2[j]);
+            q[i * 8 + 2 * j] = f.x; q[i * 8 + 2 * j + 1] = f.y;
+        }
+    }
+    const bf16* kbase = a.kcache + ((int64_t)seq * a.H + h) * (int64_t)a.Lmax * 64;
+    const bf16* vbase = a.vtcache + ((int64_t)seq * a.H + h) * 64 * (int64_t)a.Lmax;
+    const float sc = a.scale * 1.4426950408889634f;
+    float mx = kNegBig;
+    for (int k = tid; k < a.n_keys; k += 128) {
+        float s = kNegBig;
+        if (omni_allowed(msk, qpos, k)) {
+            float acc = 0.f;
+            const uint4* kr = reinterpret_cast<const uint4*>(kbase + (int64_t)k * 64);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint4 u = __ldg(kr + i);
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = __bfloat1622float2(h2[j]);
+                    acc += q[i * 8 + 2 * j] * f.x + q[i * 8 + 2 * j + 1] * f.y;
+                }
+            }
+            s = acc * sc;
+        }
+        sc_s[k] = s;
+        mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    float sum = 0.f;
+    for (int k = tid; k < a.n_keys; k += 128) {
+        const float p = exp2f(sc_s[k] - mx);
+        sc_s[k] = p;
+        sum += p;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) red[4 + warp] = sum;
+    __syncthreads();
+    sum = red[4] + red[5] + red[6] + red[7];
+    // o[d] = sum_k p[k] V^T[d][k]; two threads per d split the keys
+    const int d = tid >> 1, half = tid & 1;
+    const bf16* vr = vbase + (int64_t)d * a.Lmax;
+    float acc = 0.f;
+    const int n8 = a.n_keys >> 3;
+    for (int c = half; c < n8; c += 2) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(vr) + c);
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = __bfloat1622float2(h2[j]);
+            acc += sc_s[c * 8 + 2 * j] * f.x + sc_s[c * 8 + 2 * j + 1] * f.y;
+        }
+    }
+    if (half == 0)
+        for (int k = n8 * 8; k < a.n_keys; ++k) acc += sc_s[k] * __bfloat162float(vr[k]);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    __syncthreads();   // everyone has read q before it is overwritten
+    if (half == 0) qrow[d] = __float2bfloat16(acc / sum);
+}
+
+int omni_attention_decode(const AttnArgs& a, cudaStream_t st) {
+    if (a.n_seq == 0) return 0;
+    SHOWO_CHECK(a.n_keys <= a.Lmax && a.n_keys * 4 <= 48 * 1024, "attention decode: n_keys too large");
+    dim3 grid(a.H, a.n_seq);
+    omni_attention_decode_kernel<<<grid, 128, a.n_keys * sizeof(float), st>>>(a);
+    note_launch();
+    SHOWO_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace showo

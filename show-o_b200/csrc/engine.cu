@@ -1,0 +1,618 @@
+// Host orchestration of the Show-o backbone behind the C ABI (include/showo_b200.h): weight packing, workspaces,
+// the per-layer kernel sequence, the t2i denoise loop with text-prefix reuse, KV-cached batched MMU decoding.
+//
+// Per layer (PhiDecoderLayer, phi.py:774-790: y = Attn(LN x) + MLP(LN x) + x with ONE shared pre-LN) the engine runs
+//   1. layernorm_bf16        x(f32) -> xh(bf16)
+//   2. gemm  [M,D] x W1^T    W1 = [Wk; Wv; Wq; Wfc1]  ([3D+F, D])  -> buf [M, 3D+F] bf16 = k | v | q | gelu_new(fc1)
+//   3. qk_norm_rope_scatter  q/k LayerNorm(64) + partial rotary; K -> cache, V -> cache (transposed); q in place
+//   4. omni_attention        softmax(q K^T / 8 + mask) V  -> overwrites the q block (so buf = k | v | attn | act)
+//   5. gemm  [M,D+F] x W2^T  W2 = [Wdense | Wfc2] ([D, D+F]), A = buf[:, 2D:], epilogue x += acc + (b_dense + b_fc2)
+// i.e. two GEMMs per layer instead of six, and the attention/MLP outputs never round-trip HBM separately.
+#include <atomic>
+#include <map>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace showo {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+static std::atomic<int64_t> g_launches{0};
+void note_launch(int n) { g_launches += n; }
+int64_t launches_total() { return g_launches.load(); }
+const char* last_error_cstr() { return g_last_error.c_str(); }
+
+__global__ void vec_add_kernel(const float* a, const float* b, float* o, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) o[i] = a[i] + b[i];
+}
+__global__ void mmu_lengths_kernel(const int64_t* toks, int max_new, int64_t eot, int32_t* lens) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    int n = max_new;
+    if (eot >= 0)
+        for (int i = 0; i < max_new; ++i)
+            if (toks[(int64_t)b * max_new + i] == eot) { n = i + 1; break; }
+    lens[b] = n;
+}
+
+template <class T>
+static int dev_alloc(T** p, size_t n) {
+    *p = nullptr;
+    if (n == 0) return 0;
+    SHOWO_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
+    return 0;
+}
+template <class T>
+static void dev_free(T*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+}  // namespace showo
+
+using namespace showo;
+
+struct LayerW {
+    bf16* w1 = nullptr;   // [3D+F, D]
+    float* b1 = nullptr;  // [3D+F]
+    bf16* w2 = nullptr;   // [D, D+F]
+    float* b2 = nullptr;  // [D]  (= dense.bias + fc2.bias)
+    float* b_dense = nullptr; float* b_fc2 = nullptr;
+    float* ln_g = nullptr; float* ln_b = nullptr;
+    float* qg = nullptr; float* qb = nullptr; float* kg = nullptr; float* kb = nullptr;
+};
+
+struct showo_engine {
+    showo_config_t cfg{};
+    int device = 0;
+    int D = 0, H = 0, F = 0, NL = 0, V = 0, W1N = 0, W2K = 0;
+    bf16* embed = nullptr;
+    bf16* head_w = nullptr; float* head_b = nullptr;
+    float* fln_g = nullptr; float* fln_b = nullptr;
+    std::vector<LayerW> layers;
+    float* cos_tab = nullptr; float* sin_tab = nullptr;
+    std::set<std::string> loaded;
+    bool finalized = false;
+    float* stage = nullptr; size_t stage_cap = 0;       // fp32 staging for weight uploads
+    // workspaces
+    int cap_rows = 0, cap_seq = 0, cap_L = 0; int64_t cap_logit_elems = 0;
+    float* x = nullptr; bf16* xh = nullptr; bf16* buf = nullptr;
+    bf16* kcache = nullptr; bf16* vtcache = nullptr;     // [NL][cap_seq][H][cap_L][64] each
+    showo_seq_mask_t* d_masks = nullptr;
+    float* logits_ws = nullptr; float* conf_ws = nullptr; int* sampled_ws = nullptr;
+    int64_t* tok_ws = nullptr; int64_t tok_ws_cap = 0;
+    int64_t launches_last = 0;
+};
+
+static int engine_set_device(showo_engine* e) {
+    SHOWO_CUDA_OK(cudaSetDevice(e->device));
+    return 0;
+}
+
+static int ensure_ws(showo_engine* e, int rows, int n_seq, int L, int64_t logit_elems, cudaStream_t st) {
+    const int Lr = cdiv(L, 64) * 64;
+    if (rows > e->cap_rows) {
+        SHOWO_CUDA_OK(cudaStreamSynchronize(st));
+        dev_free(e->x); dev_free(e->xh); dev_free(e->buf);
+        SHOWO_TRY(dev_alloc(&e->x, (size_t)rows * e->D));
+        SHOWO_TRY(dev_alloc(&e->xh, (size_t)rows * e->D));
+        SHOWO_TRY(dev_alloc(&e->buf, (size_t)rows * e->W1N));
+        e->cap_rows = rows;
+    }
+    if (n_seq > e->cap_seq || Lr > e->cap_L) {
+        SHOWO_CUDA_OK(cudaStreamSynchronize(st));
+        const int ns = n_seq > e->cap_seq ? n_seq : e->cap_seq;
+        const int nl = Lr > e->cap_L ? Lr : e->cap_L;
+        dev_free(e->kcache); dev_free(e->vtcache); dev_free(e->d_masks);
+        const size_t n = (size_t)e->NL * ns * e->H * nl * 64;
+        SHOWO_TRY(dev_alloc(&e->kcache, n));
+        SHOWO_TRY(dev_alloc(&e->vtcache, n));
+        SHOWO_CUDA_OK(cudaMemset(e->kcache, 0, n * sizeof(bf16)));
+        SHOWO_CUDA_OK(cudaMemset(e->vtcache, 0, n * sizeof(bf16)));
+        SHOWO_TRY(dev_alloc(&e->d_masks, (size_t)ns));
+        e->cap_seq = ns; e->cap_L = nl;
+    }
+    if (logit_elems > e->cap_logit_elems) {
+        SHOWO_CUDA_OK(cudaStreamSynchronize(st));
+        dev_free(e->logits_ws);
+        SHOWO_TRY(dev_alloc(&e->logits_ws, (size_t)logit_elems));
+        e->cap_logit_elems = logit_elems;
+    }
+    if (!e->conf_ws) {
+        SHOWO_TRY(dev_alloc(&e->conf_ws, (size_t)1 << 20));
+        SHOWO_TRY(dev_alloc(&e->sampled_ws, (size_t)1 << 20));
+    }
+    return 0;
+}
+
+static size_t layer_cache_stride(const showo_engine* e) { return (size_t)e->cap_seq * e->H * e->cap_L * 64; }
+
+// One pass of all layers over rows laid out as [n_seq][rows_per_seq] in e->x (fp32 residual stream).
+static int run_layers(showo_engine* e, int n_seq, int rows_per_seq, int pos0, int n_keys, bool decode, cudaStream_t st) {
+    const int M = n_seq * rows_per_seq;
+    const int D = e->D, F = e->F;
+    for (int l = 0; l < e->NL; ++l) {
+        const LayerW& w = e->layers[l];
+        SHOWO_TRY(layernorm_bf16(e->x, w.ln_g, w.ln_b, e->cfg.ln_eps, e->xh, M, D, M, M, 0, st));
+        GemmArgs g1{};
+        g1.A = e->xh; g1.lda = D; g1.B = w.w1; g1.ldb = D; g1.M = M; g1.N = e->W1N; g1.K = D;
+        g1.out = e->buf; g1.ldc = e->W1N; g1.bias = w.b1; g1.gelu_from = 3 * D;
+        SHOWO_TRY(gemm_bf16(g1, GEMM_BIAS_BF16, st));
+        bf16* kc = e->kcache + (size_t)l * layer_cache_stride(e);
+        bf16* vc = e->vtcache + (size_t)l * layer_cache_stride(e);
+        QkRopeArgs r{};
+        r.qkv = e->buf; r.ld = e->W1N; r.n_rows = M; r.rows_per_seq = rows_per_seq; r.pos0 = pos0; r.H = e->H; r.D = D;
+        r.q_gamma = w.qg; r.q_beta = w.qb; r.k_gamma = w.kg; r.k_beta = w.kb; r.eps = e->cfg.ln_eps;
+        r.cos_tab = e->cos_tab; r.sin_tab = e->sin_tab; r.kcache = kc; r.vtcache = vc; r.Lmax = e->cap_L;
+        SHOWO_TRY(qk_norm_rope_scatter(r, st));
+        AttnArgs a{};
+        a.q = e->buf + 2 * D; a.ld = e->W1N; a.n_seq = n_seq; a.H = e->H; a.rows_per_seq = rows_per_seq; a.pos0 = pos0;
+        a.kcache = kc; a.vtcache = vc; a.Lmax = e->cap_L; a.n_keys = n_keys; a.masks = e->d_masks; a.scale = 0.125f;
+        if (decode) SHOWO_TRY(omni_attention_decode(a, st));
+        else SHOWO_TRY(omni_attention(a, st));
+        GemmArgs g2{};
+        g2.A = e->buf + 2 * D; g2.lda = e->W1N; g2.B = w.w2; g2.ldb = e->W2K; g2.M = M; g2.N = D; g2.K = D + F;
+        g2.out = e->x; g2.ldc = D; g2.bias = w.b2; g2.resid = e->x; g2.ldr = D;
+        SHOWO_TRY(gemm_bf16(g2, GEMM_RESID_F32, st));
+    }
+    return 0;
+}
+
+static int upload_masks(showo_engine* e, const showo_seq_mask_t* masks_host, int n, cudaStream_t st) {
+    SHOWO_CUDA_OK(cudaMemcpyAsync(e->d_masks, masks_host, (size_t)n * sizeof(showo_seq_mask_t), cudaMemcpyHostToDevice, st));
+    return 0;
+}
+
+static int check_ready(showo_engine* e) {
+    SHOWO_CHECK(e != nullptr, "null engine");
+    SHOWO_TRY(engine_set_device(e));
+    if (!e->finalized) SHOWO_TRY(showo_weights_complete(e));
+    return 0;
+}
+
+extern "C" {
+
+const char* showo_last_error(void) { return last_error_cstr(); }
+int showo_abi_version(void) { return SHOWO_B200_ABI_VERSION; }
+int showo_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int i = 0; i < n; ++i) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i) == cudaSuccess && major == 10) ++ok;
+    }
+    return ok;
+}
+
+int showo_engine_create(const showo_config_t* cfg, int device, showo_engine_t** out) {
+    SHOWO_CHECK(cfg && out, "null argument");
+    SHOWO_CHECK(cfg->hidden % 128 == 0 && cfg->hidden <= 2048, "hidden must be a multiple of 128 and <= 2048");
+    SHOWO_CHECK(cfg->hidden / cfg->n_heads == 64 && cfg->hidden % cfg->n_heads == 0, "head_dim must be 64");
+    SHOWO_CHECK(cfg->rotary_dim == 32, "rotary_dim must be 32");
+    SHOWO_CHECK(cfg->ffn % 64 == 0, "ffn must be a multiple of 64");
+    SHOWO_CHECK(showo_device_count() > 0, "no sm_100 CUDA device visible: libshowo_b200 has no CPU fallback");
+    SHOWO_CUDA_OK(cudaSetDevice(device));
+    showo_engine* e = new showo_engine();
+    e->cfg = *cfg; e->device = device;
+    e->D = cfg->hidden; e->H = cfg->n_heads; e->F = cfg->ffn; e->NL = cfg->n_layers; e->V = cfg->vocab_size;
+    e->W1N = 3 * e->D + e->F; e->W2K = e->D + e->F;
+    const int D = e->D, F = e->F, V = e->V;
+    SHOWO_TRY(dev_alloc(&e->embed, (size_t)V * D));
+    SHOWO_TRY(dev_alloc(&e->head_w, (size_t)V * D));
+    SHOWO_TRY(dev_alloc(&e->head_b, (size_t)V));
+    SHOWO_TRY(dev_alloc(&e->fln_g, (size_t)D));
+    SHOWO_TRY(dev_alloc(&e->fln_b, (size_t)D));
+    e->layers.resize(e->NL);
+    for (auto& w : e->layers) {
+        SHOWO_TRY(dev_alloc(&w.w1, (size_t)e->W1N * D));
+        SHOWO_TRY(dev_alloc(&w.b1, (size_t)e->W1N));
+        SHOWO_TRY(dev_alloc(&w.w2, (size_t)D * e->W2K));
+        SHOWO_TRY(dev_alloc(&w.b2, (size_t)D));
+        SHOWO_TRY(dev_alloc(&w.b_dense, (size_t)D));
+        SHOWO_TRY(dev_alloc(&w.b_fc2, (size_t)D));
+        SHOWO_TRY(dev_alloc(&w.ln_g, (size_t)D));
+        SHOWO_TRY(dev_alloc(&w.ln_b, (size_t)D));
+        SHOWO_TRY(dev_alloc(&w.qg, 64)); SHOWO_TRY(dev_alloc(&w.qb, 64));
+        SHOWO_TRY(dev_alloc(&w.kg, 64)); SHOWO_TRY(dev_alloc(&w.kb, 64));
+    }
+    // rotary tables (phi.py:79-112): inv_freq_i = theta^(-2i/32), emb = cat(freqs, freqs)
+    {
+        const int P = cfg->max_pos;
+        std::vector<float> c((size_t)P * 32), s((size_t)P * 32);
+        for (int p = 0; p < P; ++p)
+            for (int i = 0; i < 16; ++i) {
+                const float inv = 1.0f / powf(cfg->rope_theta, (float)(2 * i) / 32.0f);
+                const float f = (float)p * inv;
+                c[(size_t)p * 32 + i] = c[(size_t)p * 32 + 16 + i] = cosf(f);
+                s[(size_t)p * 32 + i] = s[(size_t)p * 32 + 16 + i] = sinf(f);
+            }
+        SHOWO_TRY(dev_alloc(&e->cos_tab, c.size()));
+        SHOWO_TRY(dev_alloc(&e->sin_tab, s.size()));
+        SHOWO_CUDA_OK(cudaMemcpy(e->cos_tab, c.data(), c.size() * 4, cudaMemcpyHostToDevice));
+        SHOWO_CUDA_OK(cudaMemcpy(e->sin_tab, s.data(), s.size() * 4, cudaMemcpyHostToDevice));
+    }
+    *out = e;
+    return 0;
+}
+
+int showo_engine_destroy(showo_engine_t* e) {
+    if (!e) return 0;
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    dev_free(e->embed); dev_free(e->head_w); dev_free(e->head_b); dev_free(e->fln_g); dev_free(e->fln_b);
+    for (auto& w : e->layers) {
+        dev_free(w.w1); dev_free(w.b1); dev_free(w.w2); dev_free(w.b2); dev_free(w.b_dense); dev_free(w.b_fc2);
+        dev_free(w.ln_g); dev_free(w.ln_b); dev_free(w.qg); dev_free(w.qb); dev_free(w.kg); dev_free(w.kb);
+    }
+    dev_free(e->cos_tab); dev_free(e->sin_tab); dev_free(e->stage);
+    dev_free(e->x); dev_free(e->xh); dev_free(e->buf); dev_free(e->kcache); dev_free(e->vtcache); dev_free(e->d_masks);
+    dev_free(e->logits_ws); dev_free(e->conf_ws); dev_free(e->sampled_ws); dev_free(e->tok_ws);
+    delete e;
+    return 0;
+}
+
+int showo_load_weight(showo_engine_t* e, const char* name_c, const float* data, int64_t numel, int is_device) {
+    SHOWO_CHECK(e && name_c && data, "null argument");
+    SHOWO_TRY(engine_set_device(e));
+    const std::string name(name_c);
+    const int D = e->D, F = e->F, V = e->V;
+    // stage on the device as fp32
+    const float* src = data;
+    if (!is_device) {
+        if ((size_t)numel > e->stage_cap) {
+            dev_free(e->stage);
+            SHOWO_TRY(dev_alloc(&e->stage, (size_t)numel));
+            e->stage_cap = (size_t)numel;
+        }
+        SHOWO_CUDA_OK(cudaMemcpy(e->stage, data, (size_t)numel * 4, cudaMemcpyHostToDevice));
+        src = e->stage;
+    }
+    cudaStream_t st = 0;
+    auto expect = [&](int64_t n) -> int {
+        SHOWO_CHECK(numel == n, "weight " + name + ": expected " + std::to_string(n) + " elements, got " + std::to_string(numel));
+        return 0;
+    };
+    auto copy_f32 = [&](float* dst, int64_t n) -> int {
+        SHOWO_TRY(expect(n));
+        SHOWO_CUDA_OK(cudaMemcpyAsync(dst, src, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+        return 0;
+    };
+    int rc = -2;
+    const std::string lp = "showo.model.layers.";
+    if (name == "showo.model.embed_tokens.weight") {
+        rc = expect((int64_t)V * D); if (!rc) rc = f32_to_bf16(src, e->embed, numel, st);
+    } else if (name == "showo.lm_head.weight") {
+        rc = expect((int64_t)V * D); if (!rc) rc = f32_to_bf16(src, e->head_w, numel, st);
+    } else if (name == "showo.lm_head.bias") {
+        rc = copy_f32(e->head_b, V);
+    } else if (name == "showo.model.final_layernorm.weight") {
+        rc = copy_f32(e->fln_g, D);
+    } else if (name == "showo.model.final_layernorm.bias") {
+        rc = copy_f32(e->fln_b, D);
+    } else if (name.compare(0, lp.size(), lp) == 0) {
+        const size_t dot = name.find('.', lp.size());
+        SHOWO_CHECK(dot != std::string::npos, "bad weight name " + name);
+        const int l = atoi(name.substr(lp.size(), dot - lp.size()).c_str());
+        SHOWO_CHECK(l >= 0 && l < e->NL, "layer index out of range in " + name);
+        LayerW& w = e->layers[l];
+        const std::string k = name.substr(dot + 1);
+        // W1 rows: k | v | q | fc1 ; W2 columns: dense | fc2
+        if (k == "self_attn.k_proj.weight") { rc = expect((int64_t)D * D); if (!rc) rc = pack_block_bf16(src, D, w.w1, D, D, D, st); }
+        else if (k == "self_attn.v_proj.weight") { rc = expect((int64_t)D * D); if (!rc) rc = pack_block_bf16(src, D, w.w1 + (size_t)D * D, D, D, D, st); }
+        else if (k == "self_attn.q_proj.weight") { rc = expect((int64_t)D * D); if (!rc) rc = pack_block_bf16(src, D, w.w1 + (size_t)2 * D * D, D, D, D, st); }
+        else if (k == "mlp.fc1.weight") { rc = expect((int64_t)F * D); if (!rc) rc = pack_block_bf16(src, D, w.w1 + (size_t)3 * D * D, D, F, D, st); }
+        else if (k == "self_attn.k_proj.bias") rc = copy_f32(w.b1, D);
+        else if (k == "self_attn.v_proj.bias") rc = copy_f32(w.b1 + D, D);
+        else if (k == "self_attn.q_proj.bias") rc = copy_f32(w.b1 + 2 * D, D);
+        else if (k == "mlp.fc1.bias") rc = copy_f32(w.b1 + 3 * D, F);
+        else if (k == "self_attn.dense.weight") { rc = expect((int64_t)D * D); if (!rc) rc = pack_block_bf16(src, D, w.w2, e->W2K, D, D, st); }
+        else if (k == "mlp.fc2.weight") { rc = expect((int64_t)D * F); if (!rc) rc = pack_block_bf16(src, F, w.w2 + D, e->W2K, D, F, st); }
+        else if (k == "self_attn.dense.bias") rc = copy_f32(w.b_dense, D);
+        else if (k == "mlp.fc2.bias") rc = copy_f32(w.b_fc2, D);
+        else if (k == "input_layernorm.weight") rc = copy_f32(w.ln_g, D);
+        else if (k == "input_layernorm.bias") rc = copy_f32(w.ln_b, D);
+        else if (k == "self_attn.q_layernorm.weight") rc = copy_f32(w.qg, 64);
+        else if (k == "self_attn.q_layernorm.bias") rc = copy_f32(w.qb, 64);
+        else if (k == "self_attn.k_layernorm.weight") rc = copy_f32(w.kg, 64);
+        else if (k == "self_attn.k_layernorm.bias") rc = copy_f32(w.kb, 64);
+        else { set_last_error("unknown weight name " + name); rc = -2; }
+    } else {
+        set_last_error("unknown weight name " + name);
+        rc = -2;
+    }
+    if (rc) return rc;
+    SHOWO_CUDA_OK(cudaStreamSynchronize(st));
+    e->loaded.insert(name);
+    e->finalized = false;
+    return 0;
+}
+
+int showo_weights_complete(showo_engine_t* e) {
+    SHOWO_CHECK(e, "null engine");
+    SHOWO_TRY(engine_set_device(e));
+    std::vector<std::string> need = {"showo.model.embed_tokens.weight", "showo.lm_head.weight", "showo.lm_head.bias",
+                                     "showo.model.final_layernorm.weight", "showo.model.final_layernorm.bias"};
+    const char* per_layer[] = {"self_attn.q_proj.weight", "self_attn.q_proj.bias", "self_attn.k_proj.weight",
+                               "self_attn.k_proj.bias", "self_attn.v_proj.weight", "self_attn.v_proj.bias",
+                               "self_attn.dense.weight", "self_attn.dense.bias", "mlp.fc1.weight", "mlp.fc1.bias",
+                               "mlp.fc2.weight", "mlp.fc2.bias", "input_layernorm.weight", "input_layernorm.bias",
+                               "self_attn.q_layernorm.weight", "self_attn.q_layernorm.bias",
+                               "self_attn.k_layernorm.weight", "self_attn.k_layernorm.bias"};
+    for (int l = 0; l < e->NL; ++l)
+        for (const char* k : per_layer) need.push_back("showo.model.layers." + std::to_string(l) + "." + k);
+    for (const auto& n : need) SHOWO_CHECK(e->loaded.count(n) == 1, "weight not loaded: " + n);
+    for (auto& w : e->layers) {
+        vec_add_kernel<<<cdiv(e->D, 256), 256>>>(w.b_dense, w.b_fc2, w.b2, e->D);
+        SHOWO_CUDA_OK(cudaGetLastError());
+    }
+    SHOWO_CUDA_OK(cudaDeviceSynchronize());
+    e->finalized = true;
+    return 0;
+}
+
+int showo_embed_tokens(showo_engine_t* e, const int64_t* ids_dev, int64_t n, float* out_dev, void* stream) {
+    SHOWO_TRY(check_ready(e));
+    return embed_gather(ids_dev, 0, 0, e->embed, out_dev, (int)n, (int)n, e->D, e->V, (cudaStream_t)stream);
+}
+
+int showo_forward(showo_engine_t* e, const int64_t* ids_dev, const float* embeds_dev, int B, int L,
+                  const showo_seq_mask_t* masks_host, float* logits_out_dev, void* stream) {
+    SHOWO_TRY(check_ready(e));
+    SHOWO_CHECK((ids_dev != nullptr) != (embeds_dev != nullptr), "forward: exactly one of ids / embeds");
+    SHOWO_CHECK(B > 0 && L > 0 && L <= e->cfg.max_pos && masks_host && logits_out_dev, "forward: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t l0 = launches_total();
+    const int M = B * L;
+    SHOWO_TRY(ensure_ws(e, M, B, L, 0, st));
+    SHOWO_TRY(upload_masks(e, masks_host, B, st));
+    if (ids_dev) SHOWO_TRY(embed_gather(ids_dev, L, 0, e->embed, e->x, M, L, e->D, e->V, st));
+    else SHOWO_CUDA_OK(cudaMemcpyAsync(e->x, embeds_dev, (size_t)M * e->D * 4, cudaMemcpyDeviceToDevice, st));
+    SHOWO_TRY(run_layers(e, B, L, 0, L, false, st));
+    SHOWO_TRY(layernorm_bf16(e->x, e->fln_g, e->fln_b, e->cfg.ln_eps, e->xh, M, e->D, M, M, 0, st));
+    GemmArgs g{};
+    g.A = e->xh; g.lda = e->D; g.B = e->head_w; g.ldb = e->D; g.M = M; g.N = e->V; g.K = e->D;
+    g.out = logits_out_dev; g.ldc = e->V; g.bias = e->head_b;
+    SHOWO_TRY(gemm_bf16(g, GEMM_BIAS_F32, st));
+    e->launches_last = launches_total() - l0;
+    return 0;
+}
+
+// text prefix [0,P): computed once per generate call; K/V land in the cache, hidden states are dropped.
+static int t2i_prefix(showo_engine* e, const int64_t* ids, const int64_t* uncond, int B, int L, int P, int nb,
+                      cudaStream_t st) {
+    if (P == 0) return 0;
+    SHOWO_TRY(embed_gather(ids, L, 0, e->embed, e->x, B * P, P, e->D, e->V, st));
+    if (nb == 2) SHOWO_TRY(embed_gather(uncond, L, 0, e->embed, e->x + (size_t)B * P * e->D, B * P, P, e->D, e->V, st));
+    return run_layers(e, nb * B, P, 0, P, false, st);
+}
+// image rows [P, L): every step.  Leaves sliced logits [nb*B*N, C] in e->logits_ws.
+static int t2i_step_logits(showo_engine* e, const int64_t* ids, int B, int L, int N, int P, int nb, cudaStream_t st) {
+    const int R = L - P;
+    const int C = e->cfg.codebook_size;
+    const int off = e->cfg.llm_vocab_size + e->cfg.num_new_special_tokens;
+    // both branches share the image part of the cond ids (modeling_showo.py:137-138)
+    SHOWO_TRY(embed_gather(ids, L, P, e->embed, e->x, B * R, R, e->D, e->V, st));
+    if (nb == 2) SHOWO_TRY(embed_gather(ids, L, P, e->embed, e->x + (size_t)B * R * e->D, B * R, R, e->D, e->V, st));
+    SHOWO_TRY(run_layers(e, nb * B, R, P, L, false, st));
+    // final LN on the N image positions only, then the image-vocab slice of the head (modeling_showo.py:144)
+    SHOWO_TRY(layernorm_bf16(e->x, e->fln_g, e->fln_b, e->cfg.ln_eps, e->xh, nb * B * N, e->D, N, R, R - N - 1, st));
+    GemmArgs g{};
+    g.A = e->xh; g.lda = e->D; g.B = e->head_w + (size_t)off * e->D; g.ldb = e->D; g.M = nb * B * N; g.N = C; g.K = e->D;
+    g.out = e->logits_ws; g.ldc = C; g.bias = e->head_b + off;
+    return gemm_bf16(g, GEMM_BIAS_F32, st);
+}
+
+static int t2i_check(showo_engine* e, int B, int L, int N, int P) {
+    SHOWO_CHECK(B > 0 && N > 0 && P >= 0, "t2i: bad sizes");
+    SHOWO_CHECK((P > 0 && L == P + N + 2) || (P == 0 && L >= N + 2), "t2i: need L == prefix_len + N + 2");
+    SHOWO_CHECK(L <= e->cfg.max_pos, "t2i: sequence longer than max_pos");
+    SHOWO_CHECK(e->cfg.codebook_size % 4 == 0, "t2i: codebook size must be a multiple of 4");
+    return 0;
+}
+
+int showo_t2i_logits(showo_engine_t* e, const int64_t* ids_dev, const int64_t* uncond_ids_dev, int B, int L, int N,
+                     int prefix_len, const showo_seq_mask_t* masks_host, float* logits_out_dev, void* stream) {
+    SHOWO_TRY(check_ready(e));
+    SHOWO_CHECK(ids_dev && masks_host && logits_out_dev, "t2i_logits: null argument");
+    SHOWO_TRY(t2i_check(e, B, L, N, prefix_len));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nb = uncond_ids_dev ? 2 : 1;
+    const int C = e->cfg.codebook_size;
+    const int P = prefix_len, R = L - P;
+    const int rows = nb * B * (R > P ? R : P);
+    SHOWO_TRY(ensure_ws(e, rows, nb * B, L, (int64_t)nb * B * N * C, st));
+    SHOWO_TRY(upload_masks(e, masks_host, nb * B, st));
+    SHOWO_TRY(t2i_prefix(e, ids_dev, uncond_ids_dev, B, L, P, nb, st));
+    SHOWO_TRY(t2i_step_logits(e, ids_dev, B, L, N, P, nb, st));
+    SHOWO_CUDA_OK(cudaMemcpyAsync(logits_out_dev, e->logits_ws, (size_t)nb * B * N * C * 4, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+int showo_t2i_generate(showo_engine_t* e, int64_t* ids_dev, const int64_t* uncond_ids_dev, int B, int L, int N,
+                       int prefix_len, const showo_seq_mask_t* masks_host, int timesteps, float guidance_scale,
+                       const int32_t* mask_len_floor, const float* temperature, const float* noise_expo_dev,
+                       const float* noise_unif_dev, uint64_t seed, int64_t* sampled_out_dev, void* stream) {
+    SHOWO_TRY(check_ready(e));
+    SHOWO_CHECK(ids_dev && masks_host && mask_len_floor && temperature && sampled_out_dev, "t2i_generate: null argument");
+    SHOWO_CHECK(timesteps > 0, "t2i_generate: timesteps must be positive");
+    SHOWO_TRY(t2i_check(e, B, L, N, prefix_len));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t l0 = launches_total();
+    const bool cfg_on = uncond_ids_dev != nullptr && guidance_scale > 0.f;     // modeling_showo.py:136
+    const int nb = cfg_on ? 2 : 1;
+    const int C = e->cfg.codebook_size;
+    const int P = prefix_len, R = L - P;
+    const int rows = nb * B * (R > P ? R : P);
+    SHOWO_CHECK((int64_t)B * N <= (1 << 20), "t2i_generate: B*N too large");
+    SHOWO_TRY(ensure_ws(e, rows, nb * B, L, (int64_t)nb * B * N * C, st));
+    SHOWO_TRY(upload_masks(e, masks_host, nb * B, st));
+    SHOWO_TRY(t2i_prefix(e, ids_dev, uncond_ids_dev, B, L, P, nb, st));
+    for (int s = 0; s < timesteps; ++s) {
+        SHOWO_TRY(t2i_step_logits(e, ids_dev, B, L, N, P, nb, st));
+        SamplerArgs sa{};
+        sa.logits_cond = e->logits_ws;
+        sa.logits_uncond = cfg_on ? e->logits_ws + (size_t)B * N * C : nullptr;
+        sa.ld = C; sa.rows_per_seq = N; sa.B = B; sa.N = N; sa.C = C; sa.guidance = guidance_scale;
+        sa.ids = ids_dev; sa.ids_stride = L; sa.ids_pos0 = L - N - 1; sa.ids2 = nullptr; sa.ids2_stride = 0;
+        sa.sampled_out = sampled_out_dev;
+        sa.image_offset = e->cfg.llm_vocab_size + e->cfg.num_new_special_tokens;
+        sa.mask_token_id = e->V - 1;
+        sa.mask_len_floor = mask_len_floor[s]; sa.temperature = temperature[s];
+        sa.noise_expo = noise_expo_dev ? noise_expo_dev + (size_t)s * B * N * C : nullptr;
+        sa.noise_unif = noise_unif_dev ? noise_unif_dev + (size_t)s * B * N : nullptr;
+        sa.seed = seed; sa.step = (uint32_t)s;
+        sa.conf_ws = e->conf_ws; sa.sampled_ws = e->sampled_ws; sa.masking_out = nullptr;
+        SHOWO_TRY(t2i_sampler_step(sa, st));
+    }
+    e->launches_last = launches_total() - l0;
+    return 0;
+}
+
+int showo_sampler_step(const float* logits_cond_dev, const float* logits_uncond_dev, int B, int N, int C,
+                       float guidance_scale, int64_t* ids_dev, int64_t ids_stride, int ids_pos0, int image_offset,
+                       int mask_token_id, int mask_len_floor, float temperature, const float* noise_expo_dev,
+                       const float* noise_unif_dev, uint64_t seed, uint32_t step, int64_t* sampled_out_dev,
+                       uint8_t* masking_out_dev, void* stream) {
+    SHOWO_CHECK(logits_cond_dev && ids_dev && sampled_out_dev, "sampler_step: null argument");
+    SHOWO_CHECK(showo_device_count() > 0, "no sm_100 CUDA device visible: libshowo_b200 has no CPU fallback");
+    cudaStream_t st = (cudaStream_t)stream;
+    float* conf = nullptr; int* samp = nullptr;
+    SHOWO_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&conf), (size_t)B * N * 4, st));
+    SHOWO_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&samp), (size_t)B * N * 4, st));
+    SamplerArgs sa{};
+    sa.logits_cond = logits_cond_dev; sa.logits_uncond = logits_uncond_dev; sa.ld = C; sa.rows_per_seq = N;
+    sa.B = B; sa.N = N; sa.C = C; sa.guidance = guidance_scale;
+    sa.ids = ids_dev; sa.ids_stride = ids_stride; sa.ids_pos0 = ids_pos0; sa.sampled_out = sampled_out_dev;
+    sa.image_offset = image_offset; sa.mask_token_id = mask_token_id; sa.mask_len_floor = mask_len_floor;
+    sa.temperature = temperature; sa.noise_expo = noise_expo_dev; sa.noise_unif = noise_unif_dev;
+    sa.seed = seed; sa.step = step; sa.conf_ws = conf; sa.sampled_ws = samp; sa.masking_out = masking_out_dev;
+    int rc = t2i_sampler_step(sa, st);
+    cudaFreeAsync(conf, st);
+    cudaFreeAsync(samp, st);
+    return rc;
+}
+
+int showo_mmu_generate(showo_engine_t* e, const int64_t* ids_dev, const float* embeds_dev, int B, int L0,
+                       const showo_seq_mask_t* masks_host, int max_new_tokens, int top_k, float temperature,
+                       int64_t eot_token, int64_t* out_tokens_dev, int32_t* out_lengths_dev, void* stream) {
+    SHOWO_TRY(check_ready(e));
+    SHOWO_CHECK((ids_dev != nullptr) != (embeds_dev != nullptr), "mmu_generate: exactly one of ids / embeds");
+    SHOWO_CHECK(B > 0 && L0 > 0 && max_new_tokens > 0 && masks_host && out_tokens_dev, "mmu_generate: bad arguments");
+    SHOWO_CHECK(top_k == 1, "mmu_generate: only top_k == 1 (greedy, inference_mmu.py:81) is implemented");
+    SHOWO_CHECK(temperature > 0.f, "mmu_generate: temperature must be positive");
+    SHOWO_CHECK(L0 + max_new_tokens <= e->cfg.max_pos, "mmu_generate: sequence would exceed max_pos");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t l0 = launches_total();
+    const int D = e->D, V = e->V;
+    const int Ltot = L0 + max_new_tokens;
+    SHOWO_TRY(ensure_ws(e, B * L0, B, Ltot, (int64_t)B * V, st));
+    SHOWO_TRY(upload_masks(e, masks_host, B, st));
+    // ---- prefill
+    if (ids_dev) SHOWO_TRY(embed_gather(ids_dev, L0, 0, e->embed, e->x, B * L0, L0, D, V, st));
+    else SHOWO_CUDA_OK(cudaMemcpyAsync(e->x, embeds_dev, (size_t)B * L0 * D * 4, cudaMemcpyDeviceToDevice, st));
+    SHOWO_TRY(run_layers(e, B, L0, 0, L0, false, st));
+    SHOWO_TRY(layernorm_bf16(e->x, e->fln_g, e->fln_b, e->cfg.ln_eps, e->xh, B, D, 1, L0, L0 - 1, st));
+    GemmArgs g{};
+    g.A = e->xh; g.lda = D; g.B = e->head_w; g.ldb = D; g.M = B; g.N = V; g.K = D;
+    g.out = e->logits_ws; g.ldc = V; g.bias = e->head_b;
+    SHOWO_TRY(gemm_bf16(g, GEMM_BIAS_F32, st));
+    // token t of row b lives at out_tokens[b*max_new + t]; argmax writes a [B] vector -> strided copy via tok_ws
+    if (e->tok_ws_cap < B) {
+        dev_free(e->tok_ws);
+        SHOWO_TRY(dev_alloc(&e->tok_ws, (size_t)B));
+        e->tok_ws_cap = B;
+    }
+    for (int t = 0; t < max_new_tokens; ++t) {
+        SHOWO_TRY(argmax_rows(e->logits_ws, V, B, V, e->tok_ws, st));
+        SHOWO_CUDA_OK(cudaMemcpy2DAsync(out_tokens_dev + t, (size_t)max_new_tokens * 8, e->tok_ws, 8, 8, B,
+                                        cudaMemcpyDeviceToDevice, st));
+        if (t == max_new_tokens - 1) break;
+        // ---- decode one token per row at position L0 + t
+        SHOWO_TRY(embed_gather(e->tok_ws, 1, 0, e->embed, e->x, B, 1, D, V, st));
+        SHOWO_TRY(run_layers(e, B, 1, L0 + t, L0 + t + 1, true, st));
+        SHOWO_TRY(layernorm_bf16(e->x, e->fln_g, e->fln_b, e->cfg.ln_eps, e->xh, B, D, B, B, 0, st));
+        SHOWO_TRY(gemm_bf16(g, GEMM_BIAS_F32, st));
+    }
+    if (out_lengths_dev) {
+        mmu_lengths_kernel<<<1, B, 0, st>>>(out_tokens_dev, max_new_tokens, eot_token, out_lengths_dev);
+        SHOWO_CUDA_OK(cudaGetLastError());
+        note_launch();
+    }
+    e->launches_last = launches_total() - l0;
+    return 0;
+}
+
+int64_t showo_kernel_launches(showo_engine_t* e) { return e ? e->launches_last : 0; }
+
+// ------------------------------------------------------------------------------------------------ raw kernel test entries
+int showo_gemm_bf16(const void* A_dev, int64_t lda, const void* B_dev, int64_t ldb, int M, int N, int K, void* out_dev,
+                    int64_t ldc, const float* bias_dev, const float* resid_dev, int64_t ldr, int gelu_from, int epi,
+                    int block_n, void* stream) {
+    SHOWO_CHECK(showo_device_count() > 0, "no sm_100 CUDA device visible: libshowo_b200 has no CPU fallback");
+    GemmArgs g{};
+    g.A = (const bf16*)A_dev; g.lda = lda; g.B = (const bf16*)B_dev; g.ldb = ldb; g.M = M; g.N = N; g.K = K;
+    g.out = out_dev; g.ldc = ldc; g.bias = bias_dev; g.resid = resid_dev; g.ldr = ldr; g.gelu_from = gelu_from;
+    g.block_n = block_n;
+    SHOWO_CHECK(epi >= 0 && epi <= 2, "gemm: epi must be 0, 1 or 2");
+    return gemm_bf16(g, (GemmEpi)epi, (cudaStream_t)stream);
+}
+
+int showo_layernorm_test(const float* x_dev, const float* gamma_dev, const float* beta_dev, float eps, void* out_bf16_dev,
+                         int rows, int D, void* stream) {
+    SHOWO_CHECK(showo_device_count() > 0, "no sm_100 CUDA device visible: libshowo_b200 has no CPU fallback");
+    return layernorm_bf16(x_dev, gamma_dev, beta_dev, eps, (bf16*)out_bf16_dev, rows, D, rows, rows, 0, (cudaStream_t)stream);
+}
+
+int showo_attention_test(void* qkv_dev, int64_t ld, int n_seq, int rows_per_seq, int pos0, int H,
+                         const float* qg, const float* qb, const float* kg, const float* kb, float eps,
+                         float rope_theta, int rotary_dim, void* kcache_dev, void* vtcache_dev, int Lmax, int n_keys,
+                         const showo_seq_mask_t* masks_host, void* stream) {
+    SHOWO_CHECK(showo_device_count() > 0, "no sm_100 CUDA device visible: libshowo_b200 has no CPU fallback");
+    SHOWO_CHECK(rotary_dim == 32, "rotary_dim must be 32");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int D = H * 64;
+    std::vector<float> c((size_t)Lmax * 32), s((size_t)Lmax * 32);
+    for (int p = 0; p < Lmax; ++p)
+        for (int i = 0; i < 16; ++i) {
+            const float inv = 1.0f / powf(rope_theta, (float)(2 * i) / 32.0f);
+            const float f = (float)p * inv;
+            c[(size_t)p * 32 + i] = c[(size_t)p * 32 + 16 + i] = cosf(f);
+            s[(size_t)p * 32 + i] = s[(size_t)p * 32 + 16 + i] = sinf(f);
+        }
+    float *dc = nullptr, *ds = nullptr; showo_seq_mask_t* dm = nullptr;
+    SHOWO_TRY(dev_alloc(&dc, c.size())); SHOWO_TRY(dev_alloc(&ds, s.size())); SHOWO_TRY(dev_alloc(&dm, (size_t)n_seq));
+    SHOWO_CUDA_OK(cudaMemcpyAsync(dc, c.data(), c.size() * 4, cudaMemcpyHostToDevice, st));
+    SHOWO_CUDA_OK(cudaMemcpyAsync(ds, s.data(), s.size() * 4, cudaMemcpyHostToDevice, st));
+    SHOWO_CUDA_OK(cudaMemcpyAsync(dm, masks_host, (size_t)n_seq * sizeof(showo_seq_mask_t), cudaMemcpyHostToDevice, st));
+    QkRopeArgs r{};
+    r.qkv = (bf16*)qkv_dev; r.ld = ld; r.n_rows = n_seq * rows_per_seq; r.rows_per_seq = rows_per_seq; r.pos0 = pos0;
+    r.H = H; r.D = D; r.q_gamma = qg; r.q_beta = qb; r.k_gamma = kg; r.k_beta = kb; r.eps = eps;
+    r.cos_tab = dc; r.sin_tab = ds; r.kcache = (bf16*)kcache_dev; r.vtcache = (bf16*)vtcache_dev; r.Lmax = Lmax;
+    int rc = qk_norm_rope_scatter(r, st);
+    if (!rc) {
+        AttnArgs a{};
+        a.q = (bf16*)qkv_dev + 2 * D; a.ld = ld; a.n_seq = n_seq; a.H = H; a.rows_per_seq = rows_per_seq; a.pos0 = pos0;
+        a.kcache = (const bf16*)kcache_dev; a.vtcache = (const bf16*)vtcache_dev; a.Lmax = Lmax; a.n_keys = n_keys;
+        a.masks = dm; a.scale = 0.125f;
+        rc = (rows_per_seq == 1 && pos0 == n_keys - 1 && n_keys > 1) ? omni_attention_decode(a, st) : omni_attention(a, st);
+    }
+    cudaStreamSynchronize(st);
+    cudaFree(dc); cudaFree(ds); cudaFree(dm);
+    return rc;
+}
+
+int showo_conv_test(const void* x_dev, const void* w_dev, const float* bias_dev, const void* resid_dev, void* out_dev,
+                    int NB, int H, int W, int cin, int cout, int taps, void* stream) {
+    SHOWO_CHECK(showo_device_count() > 0, "no sm_100 CUDA device visible: libshowo_b200 has no CPU fallback");
+    ConvArgs a{};
+    a.x = (const bf16*)x_dev; a.w = (const bf16*)w_dev; a.bias = bias_dev; a.resid = (const bf16*)resid_dev; a.ldr = cout;
+    a.out = (bf16*)out_dev; a.ldc = cout; a.NB = NB; a.H = H; a.W = W; a.cin = cin; a.cout = cout; a.taps = taps;
+    return conv_nhwc_bf16(a, (cudaStream_t)stream);
+}
+
+}  // extern "C"

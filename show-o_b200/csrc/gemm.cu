@@ -1,0 +1,176 @@
+// Host launchers for the tcgen05 GEMM / implicit-GEMM convolution (gemm_tcgen05.cuh).
+#include <cudaTypedefs.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "gemm_tcgen05.cuh"
+#include "kernels.h"
+
+namespace showo {
+
+// cuTensorMapEncodeTiled is fetched through the runtime so the library has no link-time dependency on libcuda.so
+// (it must dlopen on a CPU-only box for the symbol-export test).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+struct MapKey {
+    const void* ptr; uint64_t d0, d1, d2, d3, s1, s2, s3; uint32_t b0, b1, b2, b3, rank;
+    bool operator==(const MapKey& o) const {
+        return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && d3 == o.d3 && s1 == o.s1 && s2 == o.s2 &&
+               s3 == o.s3 && b0 == o.b0 && b1 == o.b1 && b2 == o.b2 && b3 == o.b3 && rank == o.rank;
+    }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        uint64_t h = reinterpret_cast<uint64_t>(k.ptr);
+        auto mix = [&h](uint64_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+        mix(k.d0); mix(k.d1); mix(k.d2); mix(k.d3); mix(k.s1); mix(k.s2); mix(k.s3);
+        mix(k.b0); mix(k.b1); mix(k.b2); mix(k.b3); mix(k.rank);
+        return (size_t)h;
+    }
+};
+static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+static std::mutex g_maps_mu;
+
+// bf16 tensor map, 128B swizzle, zero OOB fill.  dims/strides innermost first; strides in bytes for dims 1..rank-1.
+static int make_map(CUtensorMap* out, const void* ptr, uint32_t rank, const uint64_t* dims, const uint64_t* strides,
+                    const uint32_t* box) {
+    MapKey key{ptr, dims[0], rank > 1 ? dims[1] : 0, rank > 2 ? dims[2] : 0, rank > 3 ? dims[3] : 0,
+               rank > 1 ? strides[0] : 0, rank > 2 ? strides[1] : 0, rank > 3 ? strides[2] : 0,
+               box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0, rank};
+    {
+        std::lock_guard<std::mutex> lk(g_maps_mu);
+        auto it = g_maps.find(key);
+        if (it != g_maps.end()) { *out = it->second; return 0; }
+    }
+    EncodeTiledFn fn = get_encode_fn();
+    SHOWO_CHECK(fn != nullptr, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    cuuint64_t gd[4], gs[3];
+    cuuint32_t bx[4];
+    for (uint32_t i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; }
+    for (uint32_t i = 0; i + 1 < rank; ++i) gs[i] = strides[i];
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gd, gs, bx, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_last_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r) + " rank " +
+                       std::to_string(rank) + " dims " + std::to_string(dims[0]) + "," +
+                       std::to_string(rank > 1 ? dims[1] : 0) + " stride " + std::to_string(rank > 1 ? strides[0] : 0));
+        return -3;
+    }
+    std::lock_guard<std::mutex> lk(g_maps_mu);
+    if (g_maps.size() > 8192) g_maps.clear();
+    g_maps[key] = *out;
+    return 0;
+}
+
+int gemm_num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return n;
+}
+
+template <int BN, int EPI, int AMODE>
+static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int num_tiles, cudaStream_t st) {
+    using Cfg = GemmCfg<BN>;
+    static bool attr_set = false;
+    auto kern = gemm_tcgen05_kernel<BN, EPI, AMODE>;
+    if (!attr_set) {
+        SHOWO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        attr_set = true;
+    }
+    int grid = num_tiles < gemm_num_sms() ? num_tiles : gemm_num_sms();
+    kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(ma, mb, p);
+    note_launch();
+    SHOWO_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template <int BN>
+static int gemm_bn(const GemmArgs& a, GemmEpi epi, cudaStream_t st) {
+    CUtensorMap ma, mb;
+    uint64_t da[2] = {(uint64_t)a.K, (uint64_t)a.M}, sa[1] = {(uint64_t)a.lda * 2};
+    uint32_t ba[2] = {64, 128};
+    SHOWO_TRY(make_map(&ma, a.A, 2, da, sa, ba));
+    uint64_t db[2] = {(uint64_t)a.K, (uint64_t)a.N}, sb[1] = {(uint64_t)a.ldb * 2};
+    uint32_t bb[2] = {64, (uint32_t)BN};
+    SHOWO_TRY(make_map(&mb, a.B, 2, db, sb, bb));
+    GemmParams p{};
+    p.M = a.M; p.N = a.N; p.K = a.K;
+    p.out = a.out; p.ldc = a.ldc; p.bias = a.bias; p.resid = a.resid; p.ldr = a.ldr; p.gelu_from = a.gelu_from;
+    const int tiles = cdiv(a.M, 128) * cdiv(a.N, BN);
+    switch (epi) {
+        case GEMM_BIAS_BF16: return launch<BN, EPI_BIAS_BF16, A_PLAIN>(ma, mb, p, tiles, st);
+        case GEMM_RESID_F32: return launch<BN, EPI_RESID_F32, A_PLAIN>(ma, mb, p, tiles, st);
+        case GEMM_BIAS_F32: return launch<BN, EPI_BIAS_F32, A_PLAIN>(ma, mb, p, tiles, st);
+    }
+    SHOWO_CHECK(false, "bad epilogue");
+}
+
+int gemm_bf16(const GemmArgs& a, GemmEpi epi, cudaStream_t st) {
+    SHOWO_CHECK(a.M > 0 && a.N > 0 && a.K > 0, "gemm: empty problem");
+    SHOWO_CHECK((a.lda % 8) == 0 && (a.ldb % 8) == 0, "gemm: lda/ldb must be multiples of 8 elements (16 B)");
+    SHOWO_CHECK((reinterpret_cast<uintptr_t>(a.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.B) & 15) == 0,
+                "gemm: A/B must be 16-byte aligned");
+    int bn = a.block_n;
+    if (bn == 0) {
+        if (a.M <= 256) bn = 64;              // decode / tiny batches: more CTAs streaming the weights
+        else if (a.N >= 2048) bn = 256;
+        else if (a.N >= 128) bn = 128;
+        else bn = 64;
+    }
+    if (bn == 256) return gemm_bn<256>(a, epi, st);
+    if (bn == 128) return gemm_bn<128>(a, epi, st);
+    if (bn == 64) return gemm_bn<64>(a, epi, st);
+    SHOWO_CHECK(false, "gemm: block_n must be 64, 128 or 256");
+}
+
+int conv_nhwc_bf16(const ConvArgs& a, cudaStream_t st) {
+    SHOWO_CHECK(a.cin % 64 == 0, "conv: cin must be a multiple of 64 (pad the activation)");
+    SHOWO_CHECK(a.taps == 9 || a.taps == 1 || a.taps == 4, "conv: taps must be 9 (3x3), 4 (2x2 forward) or 1 (1x1)");
+    // spatial patch of 128 output pixels
+    int TW = a.W >= 16 ? 16 : a.W;
+    int TH = 128 / TW;
+    SHOWO_CHECK(TW * TH == 128, "conv: W must be >= 16 or a power of two dividing 128");
+    CUtensorMap ma, mb;
+    uint64_t da[4] = {(uint64_t)a.cin, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.NB};
+    uint64_t sa[3] = {(uint64_t)a.cin * 2, (uint64_t)a.W * a.cin * 2, (uint64_t)a.H * a.W * a.cin * 2};
+    uint32_t ba[4] = {64, (uint32_t)TW, (uint32_t)TH, 1};
+    SHOWO_TRY(make_map(&ma, a.x, 4, da, sa, ba));
+    const int cout_pad = cdiv(a.cout, 64) * 64;
+    const int BN = (a.cout >= 256) ? 256 : (a.cout >= 128 ? 128 : 64);
+    const int K = a.taps * a.cin;
+    uint64_t db[2] = {(uint64_t)K, (uint64_t)cout_pad}, sb[1] = {(uint64_t)K * 2};
+    uint32_t bb[2] = {64, (uint32_t)BN};
+    SHOWO_TRY(make_map(&mb, a.w, 2, db, sb, bb));
+    GemmParams p{};
+    p.M = a.NB * a.H * a.W; p.N = a.cout; p.K = K;
+    p.out = a.out; p.ldc = a.ldc; p.bias = a.bias; p.resid = a.resid; p.ldr = a.ldr; p.gelu_from = a.cout;
+    p.conv_H = a.H; p.conv_W = a.W; p.conv_TH = TH; p.conv_TW = TW; p.conv_taps = a.taps; p.conv_cin = a.cin;
+    p.conv_pad = a.taps == 9 ? 1 : 0;
+    const int tiles = a.NB * cdiv(a.H, TH) * cdiv(a.W, TW) * cdiv(a.cout, BN);
+    if (BN == 256) return launch<256, EPI_CONV_BF16, A_CONV3>(ma, mb, p, tiles, st);
+    if (BN == 128) return launch<128, EPI_CONV_BF16, A_CONV3>(ma, mb, p, tiles, st);
+    return launch<64, EPI_CONV_BF16, A_CONV3>(ma, mb, p, tiles, st);
+}
+
+}  // namespace showo

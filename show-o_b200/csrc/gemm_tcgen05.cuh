@@ -1,0 +1,324 @@
+// Persistent warp-specialised tcgen05 GEMM for sm_100a:  C[M,N] = A[M,K] * B[N,K]^T  (+ fused epilogue)
+//
+//   A, B : bf16, K-contiguous ("K-major"); loaded by TMA into 128B-swizzled smem tiles (BLOCK_K = 64 elements).
+//   acc  : fp32 in TMEM, two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   roles: warp 0 = TMA producer (one elected lane), warp 1 = MMA issuer (one elected lane; also owns TMEM
+//          alloc/dealloc), warps 2..5 = epilogue (TMEM -> registers -> global, one output row per thread).
+//   grid : persistent, min(#tiles, #SMs) CTAs, 1 CTA / SM; tiles are walked m-fastest so concurrently running
+//          CTAs share the same B (weight) columns in L2.
+//
+// A-operand modes:
+//   A_PLAIN : 2-D tensor map over [M, K] (row stride lda).
+//   A_CONV3 : implicit-GEMM 3x3 / 1x1 convolution over an NHWC activation: a 4-D tensor map [C, W, H, N]; an M tile is
+//             a TH x TW patch of output pixels of one image, the K loop runs over (tap, channel-chunk) and each tap is
+//             the same box shifted by (dy, dx) -- out-of-bounds rows/cols are zero-filled by TMA (= zero padding).
+//
+// Epilogues (fused, applied on the fp32 accumulator):
+//   EPI_BIAS_BF16  : out_bf16 = acc + bias[n], gelu_new on columns >= gelu_from
+//   EPI_RESID_F32  : out_f32  = resid[m,n] + acc + bias[n]                    (in place allowed)
+//   EPI_BIAS_F32   : out_f32  = acc + bias[n]                                 (logits)
+//   EPI_CONV_BF16  : out_bf16 = acc + bias[n] (+ resid_bf16[m,n]); rows are NHWC pixels of the conv tile
+#pragma once
+#include "common.cuh"
+
+namespace showo {
+
+enum { EPI_BIAS_BF16 = 0, EPI_RESID_F32 = 1, EPI_BIAS_F32 = 2, EPI_CONV_BF16 = 3 };
+enum { A_PLAIN = 0, A_CONV3 = 1 };
+
+struct GemmParams {
+    int M, N, K;
+    // outputs
+    void* out;              // bf16 or f32, row-major, leading dimension ldc (elements)
+    int64_t ldc;
+    const float* bias;      // [N] or nullptr
+    const void* resid;      // EPI_RESID_F32: f32 [M, ldr]; EPI_CONV_BF16: bf16 [M, ldr] or nullptr
+    int64_t ldr;
+    int gelu_from;          // EPI_BIAS_BF16: columns >= gelu_from get gelu_new; pass N for none
+    // conv mode
+    int conv_H, conv_W;     // output spatial size (== input spatial size; stride-1, 'same' padding)
+    int conv_TH, conv_TW;   // patch: TH*TW == 128
+    int conv_taps;          // 9 (3x3) or 1 (1x1)
+    int conv_cin;           // channels per tap; K == taps * cin
+    int conv_pad;           // 1 for 3x3 same-padding, 0 for 1x1
+};
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int BM = 128;
+    static constexpr int BK = 64;
+    static constexpr int kAB = BM * BK * 2;                 // 16 KB
+    static constexpr int kBB = BN * BK * 2;
+    static constexpr int kStageBytes = kAB + kBB;
+    static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int kTmemCols = 2 * BN;                // 2 accumulator stages (power of two for BN in {64,128,256})
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kThreads = 192;
+};
+
+template <int BN, int EPI, int AMODE>
+__global__ void __launch_bounds__(192, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const GemmParams p) {
+    using Cfg = GemmCfg<BN>;
+    constexpr int BM = Cfg::BM, BK = Cfg::BK, kStages = Cfg::kStages;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + kStages * Cfg::kAB;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+    uint64_t* full_bar = bars;                       // [kStages]
+    uint64_t* empty_bar = bars + kStages;            // [kStages]
+    uint64_t* tmem_full = bars + 2 * kStages;        // [2]
+    uint64_t* tmem_empty = bars + 2 * kStages + 2;   // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    int tiles_m;
+    if constexpr (AMODE == A_CONV3) {
+        tiles_m = (p.M / (p.conv_H * p.conv_W)) * cdiv_dev(p.conv_H, p.conv_TH) * cdiv_dev(p.conv_W, p.conv_TW);
+    } else {
+        tiles_m = (p.M + BM - 1) / BM;
+    }
+    const int tiles_n = (p.N + BN - 1) / BN;
+    const int num_tiles = tiles_m * tiles_n;
+    const int num_kb = (AMODE == A_CONV3) ? p.conv_taps * ((p.conv_cin + BK - 1) / BK) : (p.K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < kStages; ++s) {
+                mbar_init(&full_bar[s], 1);
+                mbar_init(&empty_bar[s], 1);
+            }
+            for (int a = 0; a < 2; ++a) {
+                mbar_init(&tmem_full[a], 1);
+                mbar_init(&tmem_empty[a], 128);
+            }
+            mbar_fence_init();
+        }
+        __syncwarp();
+        tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================================================== TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int tm = tile % tiles_m, tn = tile / tiles_m;
+                int img = 0, y0 = 0, x0 = 0;
+                if constexpr (AMODE == A_CONV3) {
+                    const int tw = cdiv_dev(p.conv_W, p.conv_TW), th = cdiv_dev(p.conv_H, p.conv_TH);
+                    img = tm / (tw * th);
+                    const int r = tm % (tw * th);
+                    y0 = (r / tw) * p.conv_TH;
+                    x0 = (r % tw) * p.conv_TW;
+                }
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                    if constexpr (AMODE == A_CONV3) {
+                        const int cchunks = (p.conv_cin + BK - 1) / BK;
+                        const int tap = kb / cchunks, cc = kb % cchunks;
+                        // 9 taps: 3x3 'same' (shift -1..1); 4 taps: 2x2 forward window (shift 0..1, the
+                        // space-to-depth form of the stride-2 Downsample); 1 tap: 1x1
+                        const int dy = (p.conv_taps == 9) ? tap / 3 - 1 : (p.conv_taps == 4 ? tap >> 1 : 0);
+                        const int dx = (p.conv_taps == 9) ? tap % 3 - 1 : (p.conv_taps == 4 ? tap & 1 : 0);
+                        tma_load_4d(smem_a + stage * Cfg::kAB, &tmap_a, &full_bar[stage], cc * BK, x0 + dx, y0 + dy, img);
+                        tma_load_2d(smem_b + stage * Cfg::kBB, &tmap_b, &full_bar[stage], tap * p.conv_cin + cc * BK,
+                                    tn * BN);
+                    } else {
+                        tma_load_2d(smem_a + stage * Cfg::kAB, &tmap_a, &full_bar[stage], kb * BK, tm * BM);
+                        tma_load_2d(smem_b + stage * Cfg::kBB, &tmap_b, &full_bar[stage], kb * BK, tn * BN);
+                    }
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer
+        constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BN;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::kAB);
+                    const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::kBB);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t da = umma_desc_k128(a_addr + k * 32);
+                        const uint64_t db = umma_desc_k128(b_addr + k * 32);
+                        umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
+                    }
+                    umma_commit(&empty_bar[stage]);                 // frees the smem slot when these MMAs retire
+                    if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
+                }
+                __syncwarp();
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================================================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1)
+        const int quarter = warp & 3;
+        const int row_in_tile = quarter * 32 + lane;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int tm = tile % tiles_m, tn = tile / tiles_m;
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            // output row of this thread
+            int64_t m;
+            bool row_ok;
+            if constexpr (AMODE == A_CONV3) {
+                const int tw = cdiv_dev(p.conv_W, p.conv_TW), th = cdiv_dev(p.conv_H, p.conv_TH);
+                const int img = tm / (tw * th);
+                const int r = tm % (tw * th);
+                const int y = (r / tw) * p.conv_TH + row_in_tile / p.conv_TW;
+                const int x = (r % tw) * p.conv_TW + row_in_tile % p.conv_TW;
+                row_ok = (y < p.conv_H) && (x < p.conv_W);
+                m = ((int64_t)img * p.conv_H + y) * p.conv_W + x;
+            } else {
+                m = (int64_t)tm * BM + row_in_tile;
+                row_ok = m < p.M;
+            }
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr0 = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 32) {
+                uint32_t v[32];
+                __syncwarp();
+                tmem_ld32(taddr0 + c, v);
+                tmem_ld_wait();
+                const int n0 = tn * BN + c;
+                if (row_ok && n0 < p.N) {
+                const bool full = (n0 + 32 <= p.N);
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                if (p.bias != nullptr) {
+                    if (full) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+                            f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (n0 + j < p.N) f[j] += __ldg(p.bias + n0 + j);
+                    }
+                }
+                if constexpr (EPI == EPI_BIAS_BF16) {
+                    if (n0 >= p.gelu_from) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = gelu_new_f(f[j]);
+                    }
+                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.ldc + n0;
+                    if (full) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            uint4 pk;
+                            pk.x = pack_bf16(f[j], f[j + 1]); pk.y = pack_bf16(f[j + 2], f[j + 3]);
+                            pk.z = pack_bf16(f[j + 4], f[j + 5]); pk.w = pack_bf16(f[j + 6], f[j + 7]);
+                            *reinterpret_cast<uint4*>(o + j) = pk;
+                        }
+                    } else {
+                        for (int j = 0; j < 32; ++j)
+                            if (n0 + j < p.N) o[j] = __float2bfloat16(f[j]);
+                    }
+                } else if constexpr (EPI == EPI_CONV_BF16) {
+                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.ldc + n0;
+                    const __nv_bfloat16* r = p.resid ? reinterpret_cast<const __nv_bfloat16*>(p.resid) + m * p.ldr + n0
+                                                     : nullptr;
+                    if (full) {
+                        if (r) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8) {
+                                const uint4 rr = *reinterpret_cast<const uint4*>(r + j);
+                                const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr);
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const float2 t = __bfloat1622float2(r2[q]);
+                                    f[j + 2 * q] += t.x; f[j + 2 * q + 1] += t.y;
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            uint4 pk;
+                            pk.x = pack_bf16(f[j], f[j + 1]); pk.y = pack_bf16(f[j + 2], f[j + 3]);
+                            pk.z = pack_bf16(f[j + 4], f[j + 5]); pk.w = pack_bf16(f[j + 6], f[j + 7]);
+                            *reinterpret_cast<uint4*>(o + j) = pk;
+                        }
+                    } else {
+                        for (int j = 0; j < 32; ++j)
+                            if (n0 + j < p.N) {
+                                float t = f[j];
+                                if (r) t += __bfloat162float(r[j]);
+                                o[j] = __float2bfloat16(t);
+                            }
+                    }
+                } else if constexpr (EPI == EPI_RESID_F32) {
+                    float* o = reinterpret_cast<float*>(p.out) + m * p.ldc + n0;
+                    const float* r = reinterpret_cast<const float*>(p.resid) + m * p.ldr + n0;
+                    if (full) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 r4 = *reinterpret_cast<const float4*>(r + j);
+                            float4 o4 = make_float4(f[j] + r4.x, f[j + 1] + r4.y, f[j + 2] + r4.z, f[j + 3] + r4.w);
+                            *reinterpret_cast<float4*>(o + j) = o4;
+                        }
+                    } else {
+                        for (int j = 0; j < 32; ++j)
+                            if (n0 + j < p.N) o[j] = f[j] + r[j];
+                    }
+                } else {  // EPI_BIAS_F32
+                    float* o = reinterpret_cast<float*>(p.out) + m * p.ldc + n0;
+                    if (full && ((p.ldc & 3) == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                    } else {
+                        for (int j = 0; j < 32; ++j)
+                            if (n0 + j < p.N) o[j] = f[j];
+                    }
+                }
+                }  // row_ok
+            }
+            __syncwarp();
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    }
+}
+
+}  // namespace showo

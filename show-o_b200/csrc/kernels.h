@@ -1,0 +1,104 @@
+// Internal launcher interface between the engine (host orchestration) and the .cu kernels.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/showo_b200.h"
+
+namespace showo {
+
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------------ GEMM (gemm.cu)
+enum GemmEpi { GEMM_BIAS_BF16 = 0, GEMM_RESID_F32 = 1, GEMM_BIAS_F32 = 2 };
+struct GemmArgs {
+    const bf16* A; int64_t lda;       // [M,K] bf16, row stride lda (elements, multiple of 8)
+    const bf16* B; int64_t ldb;       // [N,K] bf16 (weights, K-contiguous)
+    int M, N, K;
+    void* out; int64_t ldc;
+    const float* bias;
+    const float* resid; int64_t ldr;  // GEMM_RESID_F32
+    int gelu_from;                    // GEMM_BIAS_BF16: gelu_new on columns >= gelu_from (N = none)
+    int block_n;                      // 0 = auto, else 64 / 128 / 256
+};
+int gemm_bf16(const GemmArgs& a, GemmEpi epi, cudaStream_t st);
+
+// implicit-GEMM convolution on NHWC bf16 (3x3 pad 1, or 1x1), stride 1.  cin multiple of 64, weights [Cout_pad, taps*cin].
+struct ConvArgs {
+    const bf16* x;          // [NB, H, W, cin]
+    const bf16* w;          // [cout_pad(>=cout, multiple of 64), taps*cin]
+    const float* bias;      // [cout]
+    const bf16* resid;      // optional [NB*H*W, ldr]
+    int64_t ldr;
+    bf16* out;              // [NB*H*W, ldc]
+    int64_t ldc;
+    int NB, H, W, cin, cout, taps;
+};
+int conv_nhwc_bf16(const ConvArgs& a, cudaStream_t st);
+int gemm_num_sms();
+
+// ------------------------------------------------------------------ elementwise / norm (elementwise.cu)
+// out[r, :] = bf16(LN(x[map(r), :]))   with map(r) = (r / rows_out) * rows_in + row_off + r % rows_out
+int layernorm_bf16(const float* x, const float* gamma, const float* beta, float eps, bf16* out, int n_rows_out,
+                   int D, int rows_out_per_seq, int rows_in_per_seq, int row_off, cudaStream_t st);
+// x[r, :] = float(table[ids[seq(r) * ids_stride + pos0 + r % rows_per_seq], :])
+int embed_gather(const int64_t* ids, int64_t ids_stride, int pos0, const bf16* table, float* x, int n_rows,
+                 int rows_per_seq, int D, int vocab, cudaStream_t st);
+int f32_to_bf16(const float* src, bf16* dst, int64_t n, cudaStream_t st);
+int copy_f32_to_f32_rows(const float* src, int64_t src_ld, float* dst, int64_t dst_ld, int rows, int cols, cudaStream_t st);
+// dst[r, c0 + c] = bf16(src[r, c])  -- packs weight blocks into the fused weight matrices
+int pack_block_bf16(const float* src, int64_t src_ld, bf16* dst, int64_t dst_ld, int rows, int cols, cudaStream_t st);
+
+// q/k LayerNorm(head_dim) + partial rotary + KV-cache scatter.   (phi.py:665-694)
+//   qkv: [n_rows, ld] bf16 with k at col 0, v at col D, q at col 2D (per head h: cols h*64 .. h*64+63)
+//   row r belongs to sequence r / rows_per_seq at position pos0 + r % rows_per_seq
+//   K cache  [seq][H][Lmax][64], V^T cache [seq][H][64][Lmax]
+struct QkRopeArgs {
+    bf16* qkv; int64_t ld; int n_rows, rows_per_seq, pos0;
+    int H, D;
+    const float* q_gamma; const float* q_beta; const float* k_gamma; const float* k_beta; float eps;
+    const float* cos_tab; const float* sin_tab;   // [max_pos, 32]  (emb = cat(freqs, freqs); we store the 16 freqs twice)
+    bf16* kcache; bf16* vtcache; int Lmax;
+};
+int qk_norm_rope_scatter(const QkRopeArgs& a, cudaStream_t st);
+
+// ------------------------------------------------------------------ attention (attention.cu)
+struct AttnArgs {
+    bf16* q;            // points at the q column block of the qkv buffer; output overwrites q in place
+    int64_t ld;         // row stride (elements)
+    int n_seq, H, rows_per_seq, pos0;    // query row r of seq s sits at position pos0 + r
+    const bf16* kcache; const bf16* vtcache; int Lmax;
+    int n_keys;                          // keys [0, n_keys) are valid in the cache
+    const showo_seq_mask_t* masks;       // device array [n_seq]
+    float scale;                         // 1/sqrt(head_dim)
+};
+int omni_attention(const AttnArgs& a, cudaStream_t st);
+// single-query (decode) variant: one query row per sequence at position n_keys-1
+int omni_attention_decode(const AttnArgs& a, cudaStream_t st);
+
+// ------------------------------------------------------------------ sampler (sampler.cu)
+struct SamplerArgs {
+    const float* logits_cond;    // [B * rows_per_seq, ld] fp32, image row n of seq b at row b*rows_per_seq + n
+    const float* logits_uncond;  // same layout or nullptr
+    int64_t ld; int rows_per_seq;
+    int B, N, C;                 // C = codebook size (8192)
+    float guidance;              // w; logits = (1+w) cond - w uncond when uncond != nullptr
+    int64_t* ids; int64_t ids_stride; int ids_pos0;   // input_ids [B, L]: image part at [pos0, pos0+N)
+    int64_t* ids2; int64_t ids2_stride;                // optional mirror (uncond rows) or nullptr
+    int64_t* sampled_out;        // [B, N] int64 codes (the function's return value)
+    int image_offset; int mask_token_id;
+    int mask_len_floor;          // floor(N * mask_ratio) for this step (host-evaluated schedule)
+    float temperature;           // compounded temperature for this step
+    const float* noise_expo;     // [B*N, C] Exp(1) or nullptr -> Philox
+    const float* noise_unif;     // [B, N] U(0,1) or nullptr -> Philox
+    uint64_t seed; uint32_t step;
+    float* conf_ws;              // [B, N] workspace
+    int* sampled_ws;             // [B, N] workspace
+    uint8_t* masking_out;        // optional [B, N] (debug / parity), or nullptr
+};
+int t2i_sampler_step(const SamplerArgs& a, cudaStream_t st);
+// greedy / top-k=1 next-token pick for MMU decode: out[b] = argmax_v logits[b, v]; appended to ids at position pos
+int argmax_rows(const float* logits, int64_t ld, int B, int V, int64_t* out, cudaStream_t st);
+
+}  // namespace showo

@@ -1,0 +1,360 @@
+"""`Showo`: drop-in for the reference's models.Showo (models/modeling_showo.py:23-240) on top of libshowo_b200.so.
+
+Same constructor arguments, state_dict key names, `forward` / `t2i_generate` / `mmu_generate` signatures and return
+conventions, so inference_t2i.py / inference_mmu.py can import it unchanged.  The torch modules below
+are parameter containers only (they give `state_dict()`, `named_parameters()`, `.to()`, and the
+`model.showo.model.embed_tokens(ids)` call the scripts make from outside); all arithmetic of the hot path runs in the
+CUDA library through the C ABI.  No CPU fallback: calling a compute method without a B200 raises ShowoError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from types import SimpleNamespace
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib, masks
+from .schedules import cosine_schedule, step_schedule
+
+
+class _Cfg(dict):
+    """Minimal stand-in for diffusers' FrozenDict config (`model.config.mask_token_id`, ...)."""
+    __getattr__ = dict.get
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+class _Attn(nn.Module):
+    def __init__(self, d, dh, eps):
+        super().__init__()
+        self.q_proj, self.k_proj, self.v_proj, self.dense = (nn.Linear(d, d) for _ in range(4))
+        self.q_layernorm = nn.LayerNorm(dh, eps=eps)
+        self.k_layernorm = nn.LayerNorm(dh, eps=eps)
+
+
+class _Mlp(nn.Module):
+    def __init__(self, d, f):
+        super().__init__()
+        self.fc1 = nn.Linear(d, f)
+        self.fc2 = nn.Linear(f, d)
+
+
+class _Layer(nn.Module):
+    def __init__(self, d, f, dh, eps):
+        super().__init__()
+        self.self_attn = _Attn(d, dh, eps)
+        self.mlp = _Mlp(d, f)
+        self.input_layernorm = nn.LayerNorm(d, eps=eps)
+
+
+class _PhiModel(nn.Module):
+    def __init__(self, v, d, f, nl, dh, eps):
+        super().__init__()
+        self.embed_tokens = nn.Embedding(v, d)
+        self.layers = nn.ModuleList([_Layer(d, f, dh, eps) for _ in range(nl)])
+        self.final_layernorm = nn.LayerNorm(d, eps=eps)
+
+
+class _PhiForCausalLM(nn.Module):
+    def __init__(self, v, d, f, nl, dh, eps):
+        super().__init__()
+        self.model = _PhiModel(v, d, f, nl, dh, eps)
+        self.lm_head = nn.Linear(d, v)
+
+    def resize_token_embeddings(self, new_v: int):
+        """train.py:195 calls this; rows are copied, new rows N(0, 0.02) (phi.py:833-842)."""
+        old_e, old_h = self.model.embed_tokens, self.lm_head
+        d = old_e.embedding_dim
+        if new_v == old_e.num_embeddings:
+            return old_e
+        e = nn.Embedding(new_v, d).to(old_e.weight.device, old_e.weight.dtype)
+        h = nn.Linear(d, new_v).to(old_h.weight.device, old_h.weight.dtype)
+        with torch.no_grad():
+            e.weight.normal_(0, 0.02)
+            h.weight.normal_(0, 0.02)
+            h.bias.zero_()
+            n = min(new_v, old_e.num_embeddings)
+            e.weight[:n] = old_e.weight[:n]
+            h.weight[:n] = old_h.weight[:n]
+            h.bias[:n] = old_h.bias[:n]
+        self.model.embed_tokens, self.lm_head = e, h
+        return e
+
+
+class Showo(nn.Module):
+    """Reference signature: Showo(w_clip_vit, vocab_size, llm_vocab_size, llm_model_path='', codebook_size=8192,
+    num_vq_tokens=256, load_from_showo=True, **kwargs)   (modeling_showo.py:27-37).
+
+    Extra keyword-only arguments select a non-default backbone geometry for tests (`phi_dims=dict(hidden=..,
+    n_layers=.., n_heads=.., ffn=..)`) and `materialize=False` skips allocating the fp32 torch parameters when
+    the weights will be streamed straight into the engine with `load_weights`."""
+
+    def __init__(self, w_clip_vit, vocab_size, llm_vocab_size, llm_model_path="", codebook_size=8192,
+                 num_vq_tokens=256, load_from_showo=True, *, phi_dims: Optional[dict] = None,
+                 materialize: bool = True, num_new_special_tokens: int = 10, **kwargs):
+        super().__init__()
+        dims = dict(hidden=2048, n_layers=24, n_heads=32, ffn=8192, rotary_dim=32, max_pos=2048, ln_eps=1e-5,
+                    rope_theta=10000.0)
+        dims.update(phi_dims or {})
+        self._dims = SimpleNamespace(**dims)
+        self.vocab_size = vocab_size
+        self.output_size = vocab_size
+        self.w_clip_vit = w_clip_vit
+        self.config = _Cfg(w_clip_vit=w_clip_vit, vocab_size=vocab_size, llm_vocab_size=llm_vocab_size,
+                           llm_model_path=llm_model_path, codebook_size=codebook_size, num_vq_tokens=num_vq_tokens,
+                           load_from_showo=load_from_showo, mask_token_id=vocab_size - 1)
+        self._num_new_special_tokens = num_new_special_tokens
+        d = self._dims
+        if materialize:
+            self.showo = _PhiForCausalLM(vocab_size, d.hidden, d.ffn, d.n_layers, d.hidden // d.n_heads, d.ln_eps)
+            self.showo.apply(self._init_weights)
+        else:
+            self.showo = None
+        if w_clip_vit:
+            self.mm_projector = nn.Sequential(nn.Linear(1024, 2048), nn.GELU(), nn.Linear(2048, 2048))
+        self._engine = None
+        self._engine_versions = None
+        self._engine_device = None
+        self._streamed = False
+
+    @staticmethod
+    def _init_weights(m):
+        if isinstance(m, (nn.Linear, nn.Embedding)):
+            m.weight.data.normal_(mean=0.0, std=0.02)
+            if isinstance(m, nn.Linear) and m.bias is not None:
+                m.bias.data.zero_()
+
+    @classmethod
+    def from_pretrained(cls, path, **kwargs):
+        """Load `config.json` + `pytorch_model.bin` / safetensors written by the reference's save_pretrained."""
+        import json
+        import os
+        cfg = json.load(open(os.path.join(path, "config.json")))
+        model = cls(**{k: v for k, v in cfg.items() if not k.startswith("_")}, **kwargs)
+        binp = os.path.join(path, "pytorch_model.bin")
+        if os.path.exists(binp):
+            sd = torch.load(binp, map_location="cpu")
+        else:
+            from safetensors.torch import load_file
+            sd = load_file(os.path.join(path, "diffusion_pytorch_model.safetensors"))
+        model.load_state_dict(sd, strict=False)
+        return model
+
+    # ------------------------------------------------------------------ engine plumbing
+    @property
+    def device(self):
+        if self.showo is not None:
+            return self.showo.lm_head.weight.device
+        return self._engine_device or torch.device("cuda", torch.cuda.current_device())
+
+    def _make_engine(self, device: torch.device):
+        lib = _lib.require_gpu()
+        d = self._dims
+        cfg = _lib.Config(self.vocab_size, d.hidden, d.n_layers, d.n_heads, d.ffn, d.rotary_dim, d.max_pos, d.ln_eps,
+                          d.rope_theta, self.config.llm_vocab_size, self._num_new_special_tokens,
+                          self.config.codebook_size)
+        h = C.c_void_p()
+        _lib.check(lib.showo_engine_create(C.byref(cfg), device.index or 0, C.byref(h)), "showo_engine_create")
+        self._engine, self._engine_device = h, device
+        return h
+
+    def load_weights(self, weights: Dict[str, torch.Tensor], device=None):
+        """Stream a reference-format state_dict (fp32, host or device tensors) straight into the engine."""
+        device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        lib = _lib.require_gpu()
+        if self._engine is None:
+            self._make_engine(device)
+        for name, t in weights.items():
+            if not name.startswith("showo."):
+                continue
+            if "rotary_emb" in name:
+                continue
+            t = t.detach()
+            if t.dtype != torch.float32:
+                t = t.float()
+            t = t.contiguous()
+            _lib.check(lib.showo_load_weight(self._engine, name.encode(), _lib.ptr(t), t.numel(), int(t.is_cuda)),
+                       f"showo_load_weight({name})")
+        _lib.check(lib.showo_weights_complete(self._engine), "showo_weights_complete")
+        self._streamed = True
+        return self
+
+    def _sync_engine(self):
+        """(Re)load the engine's bf16 copy when the torch parameters changed (load_state_dict, optimizer step)."""
+        if self.showo is None:
+            if not self._streamed:
+                raise _lib.ShowoError("no weights: call load_weights() or construct with materialize=True")
+            return self._engine
+        dev = self.showo.lm_head.weight.device
+        if dev.type != "cuda":
+            raise _lib.ShowoError("Showo must live on a CUDA (B200) device: show-o_b200 has no CPU fallback")
+        versions = tuple(p._version for p in self.showo.parameters())
+        if self._engine is not None and self._engine_versions == versions and self._engine_device == dev:
+            return self._engine
+        sd = {"showo." + k: v for k, v in self.showo.state_dict().items()}
+        with torch.cuda.device(dev):
+            self.load_weights(sd, device=dev)
+        self._engine_versions = versions
+        return self._engine
+
+    def __del__(self):
+        try:
+            if self._engine is not None:
+                _lib.load().showo_engine_destroy(self._engine)
+        except Exception:
+            pass
+
+    def kernel_launches(self) -> int:
+        return int(_lib.load().showo_kernel_launches(self._engine)) if self._engine is not None else 0
+
+    def _mask_descs(self, attention_mask, n_seq: int):
+        if attention_mask is None:
+            return masks.descriptors_causal(n_seq)
+        if isinstance(attention_mask, (list, tuple)):       # already descriptors
+            return list(attention_mask)
+        return masks.descriptors_from_dense(attention_mask)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, input_ids, input_embeddings=None, attention_mask=None, labels=None, label_smoothing=0.0,
+                batch_size_t2i=0, batch_size_lm=0, batch_size_mmu=0, max_seq_length=128, labels_mask_text=None,
+                labels_mask_image=None, **kwargs):
+        """modeling_showo.py:59-102.  Returns logits fp32 [B,L,V] (and the three CE losses when labels are given).
+        Inference-only in this round: the logits carry no autograd graph."""
+        lib = _lib.require_gpu()
+        eng = self._sync_engine()
+        if input_embeddings is None:
+            B, L = input_ids.shape
+            ids = input_ids.contiguous()
+            emb = None
+            dev = ids.device
+        else:
+            B, L, _ = input_embeddings.shape
+            ids = None
+            emb = input_embeddings.float().contiguous()
+            dev = emb.device
+        descs = self._mask_descs(attention_mask, B)
+        logits = torch.empty(B, L, self.vocab_size, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.showo_forward(eng, _lib.ptr(ids), _lib.ptr(emb), B, L, _lib.masks_array(descs),
+                                         _lib.ptr(logits), _lib.current_stream_ptr()), "showo_forward")
+        if labels is not None:
+            import torch.nn.functional as F
+            V = self.output_size
+            loss_t2i = F.cross_entropy(logits[:batch_size_t2i, max_seq_length + 1:].reshape(-1, V),
+                                       labels[:batch_size_t2i, max_seq_length + 1:].reshape(-1), ignore_index=-100)
+            sl = slice(batch_size_t2i, batch_size_t2i + batch_size_lm)
+            loss_lm = F.cross_entropy(logits[sl, :-1].reshape(-1, V), labels[sl, 1:].reshape(-1), ignore_index=-100)
+            loss_mmu = F.cross_entropy(logits[-batch_size_mmu:, :-1].reshape(-1, V),
+                                       labels[-batch_size_mmu:, 1:].reshape(-1), ignore_index=-100)
+            return logits, loss_t2i, loss_lm, loss_mmu
+        return logits
+
+    # ------------------------------------------------------------------ t2i
+    def _t2i_layout(self, input_ids, uncond_input_ids, attention_mask, guidance_scale, config):
+        N = config.model.showo.num_vq_tokens
+        P = config.dataset.preprocessing.max_seq_length + 1
+        B, L = input_ids.shape
+        cfg_on = uncond_input_ids is not None and guidance_scale > 0
+        n_seq = 2 * B if cfg_on else B
+        if isinstance(attention_mask, (list, tuple)):
+            descs = list(attention_mask)
+        else:
+            am = attention_mask
+            if am is not None and am.shape[0] != n_seq:
+                am = am[:n_seq]
+            descs = self._mask_descs(am, n_seq)
+        assert len(descs) >= n_seq, "attention_mask must cover cond (and uncond) rows"
+        descs = descs[:n_seq]
+        # the text prefix is step-invariant iff its rows are purely causal and nothing later is visible to them
+        reusable = (L == P + N + 2) and all((d[2] <= d[1] or d[1] >= P) and d[4] <= d[3] for d in descs)
+        return N, (P if reusable else 0), B, L, cfg_on, descs
+
+    @torch.no_grad()
+    def t2i_generate(self, input_ids: torch.LongTensor = None, uncond_input_ids: torch.LongTensor = None,
+                     attention_mask=None, temperature=1.0, timesteps=18, guidance_scale=0,
+                     noise_schedule=cosine_schedule, generator: torch.Generator = None, config=None, **kwargs):
+        """modeling_showo.py:104-181.  `input_ids` is updated in place; returns LongTensor[B, N] of codes.
+
+        With `generator` given the categorical / gumbel noise is drawn by torch from it in the reference's order
+        ([B*N,C] exponentials then [B,N] uniforms per step) and handed to the kernel, so a run is reproducible
+        against the reference on identical logits; with generator=None the kernel uses its own Philox stream."""
+        lib = _lib.require_gpu()
+        eng = self._sync_engine()
+        N, P, B, L, cfg_on, descs = self._t2i_layout(input_ids, uncond_input_ids, attention_mask, guidance_scale, config)
+        dev = input_ids.device
+        C_ = self.config.codebook_size
+        assert input_ids.is_contiguous() and input_ids.dtype == torch.int64
+        floors, temps = step_schedule(noise_schedule, timesteps, N, float(temperature))
+        floors_a = (C.c_int32 * timesteps)(*floors)
+        temps_a = (C.c_float * timesteps)(*temps)
+        expo = unif = None
+        if generator is not None:
+            expo = torch.empty(timesteps, B * N, C_, dtype=torch.float32, device=dev)
+            unif = torch.empty(timesteps, B, N, dtype=torch.float32, device=dev)
+            for s in range(timesteps):
+                expo[s].exponential_(1, generator=generator)
+                unif[s].uniform_(0, 1, generator=generator)
+            seed = 0
+        else:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        unc = uncond_input_ids.contiguous() if cfg_on else None
+        out = torch.empty(B, N, dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.showo_t2i_generate(eng, _lib.ptr(input_ids), _lib.ptr(unc), B, L, N, P,
+                                              _lib.masks_array(descs), timesteps, float(guidance_scale), floors_a,
+                                              temps_a, _lib.ptr(expo), _lib.ptr(unif), seed, _lib.ptr(out),
+                                              _lib.current_stream_ptr()), "showo_t2i_generate")
+        return out
+
+    @torch.no_grad()
+    def t2i_step_logits(self, input_ids, uncond_input_ids=None, attention_mask=None, guidance_scale=0, config=None):
+        """Parity helper: sliced logits [n_branch*B, N, C] of ONE denoise-step forward (cond rows, then uncond)."""
+        lib = _lib.require_gpu()
+        eng = self._sync_engine()
+        N, P, B, L, cfg_on, descs = self._t2i_layout(input_ids, uncond_input_ids, attention_mask, guidance_scale, config)
+        nb = 2 if cfg_on else 1
+        out = torch.empty(nb * B, N, self.config.codebook_size, dtype=torch.float32, device=input_ids.device)
+        unc = uncond_input_ids.contiguous() if cfg_on else None
+        with torch.cuda.device(input_ids.device):
+            _lib.check(lib.showo_t2i_logits(eng, _lib.ptr(input_ids.contiguous()), _lib.ptr(unc), B, L, N, P,
+                                            _lib.masks_array(descs), _lib.ptr(out), _lib.current_stream_ptr()),
+                       "showo_t2i_logits")
+        return out
+
+    # ------------------------------------------------------------------ mmu
+    @torch.no_grad()
+    def mmu_generate_batched(self, idx=None, input_embeddings=None, attention_mask=None, max_new_tokens=100,
+                             temperature=1.0, top_k=None, eot_token=None):
+        """Batched KV-cached decode: returns (tokens [B, max_new_tokens] int64, lengths [B] int32)."""
+        lib = _lib.require_gpu()
+        eng = self._sync_engine()
+        if top_k != 1:
+            raise NotImplementedError("mmu_generate: only top_k=1 (greedy, as inference_mmu.py:81) is implemented")
+        if input_embeddings is None:
+            B, L0 = idx.shape
+            ids, emb, dev = idx.contiguous(), None, idx.device
+        else:
+            B, L0, _ = input_embeddings.shape
+            ids, emb, dev = None, input_embeddings.float().contiguous(), input_embeddings.device
+        descs = self._mask_descs(attention_mask, B)
+        toks = torch.zeros(B, max_new_tokens, dtype=torch.int64, device=dev)
+        lens = torch.zeros(B, dtype=torch.int32, device=dev)
+        eot = -1 if eot_token is None else int(eot_token)
+        with torch.cuda.device(dev):
+            _lib.check(lib.showo_mmu_generate(eng, _lib.ptr(ids), _lib.ptr(emb), B, L0, _lib.masks_array(descs),
+                                              max_new_tokens, 1, float(temperature), eot, _lib.ptr(toks),
+                                              _lib.ptr(lens), _lib.current_stream_ptr()), "showo_mmu_generate")
+        return toks, lens
+
+    @torch.no_grad()
+    def mmu_generate(self, idx=None, input_embeddings=None, attention_mask=None, max_new_tokens=100, temperature=1.0,
+                     top_k=None, eot_token=None):
+        """modeling_showo.py:183-240: list of 0-d LongTensors for batch row 0, cut after eot_token.  (The reference
+        only works for B == 1; for B > 1 use mmu_generate_batched.)"""
+        toks, lens = self.mmu_generate_batched(idx, input_embeddings, attention_mask, max_new_tokens, temperature,
+                                               top_k, eot_token)
+        n = int(lens[0].item())
+        return [toks[0, i] for i in range(n)]
