@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the Show-o hot path on B200 (contract: see the task brief / DESIGN.md section 6).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...          (N > 1: one rank per GPU, NCCL)
+
+A "step" = one batch of the configs[1] workload of BASELINE.json on every rank: showo_demo.yaml t2i 256x256,
+18 denoise steps, CFG 5, batch 8 per GPU (weak scaling) -> t2i_generate + MAGVIT decode_code + uint8 conversion
+(SURVEY.md section 8d, config 2), then (N > 1) an NCCL all-gather of the uint8 images.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+from types import SimpleNamespace as NS
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "t2i_256x256_images_per_sec_18steps_cfg5"
+UNIT = "images/s"
+B_PER_GPU, N_TOK, T_STEPS, CFG_W, L_SEQ, P_TXT, CODEBOOK = 8, 256, 18, 5.0, 387, 129, 8192
+D, NL, H, F, V = 2048, 24, 32, 8192, 58498
+# algorithmic FLOPs: per-token 24-layer GEMM, attention per (q,k) pair, head per position
+G_TOK = 2 * NL * (4 * D * D + 2 * D * F)
+A_PAIR = 4 * D * NL
+F_IMG = T_STEPS * 2 * ((N_TOK + 2) * (G_TOK + A_PAIR * L_SEQ) + N_TOK * 2 * D * CODEBOOK) + 2 * P_TXT * (G_TOK + A_PAIR * P_TXT / 2)
+F_DEC = 300.9e9           # MAGVIT-v2 decode, per 256x256 image (probed)
+
+
+def t2i_config():
+    return NS(model=NS(showo=NS(num_vq_tokens=N_TOK, num_new_special_tokens=10, llm_vocab_size=50295)),
+              dataset=NS(preprocessing=NS(max_seq_length=P_TXT - 1)))
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(bf16_burst=d.get("bf16_tflops", 1590.0), bf16_sustained=d.get("bf16_tflops_sustained", 1400.0),
+                    hbm=d.get("hbm_gbs", 6650.0), source="measured (MEASURED_PEAKS.json)")
+    return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi style clock / throttle-reason sampling during the timed region (pynvml)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, n in names.items():
+                    if r & bit:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def synth_prompts(torch, batch, seed):
+    """Synthetic t2i_gen rows (prompting_utils.py:92-123): left-padded [t2i][bos] text [eos] + [soi] 256 x mask [eoi]."""
+    g = torch.Generator().manual_seed(seed)
+    PAD, SOI, EOI, T2I, BOS = 50295, 50296, 50297, 50300, 50256
+    cond = torch.full((batch, L_SEQ), PAD, dtype=torch.int64)
+    unc = torch.full((batch, L_SEQ), PAD, dtype=torch.int64)
+    descs_c, descs_u = [], []
+    for b in range(batch):
+        n = int(torch.randint(8, 65, (1,), generator=g))
+        text = torch.randint(0, 50257, (n,), generator=g)
+        row = torch.cat([torch.tensor([T2I, BOS]), text, torch.tensor([BOS])])
+        cond[b, P_TXT - row.numel():P_TXT] = row
+        unc[b, P_TXT - 3:P_TXT] = torch.tensor([T2I, BOS, BOS])
+        for r in (cond, unc):
+            r[b, P_TXT] = SOI
+            r[b, P_TXT + 1:P_TXT + 1 + N_TOK] = V - 1
+            r[b, P_TXT + 1 + N_TOK] = EOI
+        descs_c.append((P_TXT - row.numel(), P_TXT, L_SEQ, 0, 0))
+        descs_u.append((P_TXT - 3, P_TXT, L_SEQ, 0, 0))
+    return cond, unc, descs_c + descs_u
+
+
+def gpu_random_weights(torch, dev, seed=0):
+    """Random-init Phi-1.5-sized state_dict generated on the device (N(0,0.02) matrices, zero biases, LN 1/0 --
+    PhiPreTrainedModel._init_weights, phi.py:833-842).  Yields (name, tensor) one at a time to bound memory."""
+    g = torch.Generator(device=dev).manual_seed(seed)
+
+    def mat(o, i):
+        return torch.randn(o, i, device=dev, generator=g) * 0.02
+    yield "showo.model.embed_tokens.weight", mat(V, D)
+    for l in range(NL):
+        p = f"showo.model.layers.{l}."
+        for n, (o, i) in {"self_attn.q_proj": (D, D), "self_attn.k_proj": (D, D), "self_attn.v_proj": (D, D),
+                          "self_attn.dense": (D, D), "mlp.fc1": (F, D), "mlp.fc2": (D, F)}.items():
+            yield p + n + ".weight", mat(o, i)
+            yield p + n + ".bias", torch.zeros(o, device=dev)
+        for n, c in {"input_layernorm": D, "self_attn.q_layernorm": 64, "self_attn.k_layernorm": 64}.items():
+            yield p + n + ".weight", torch.ones(c, device=dev)
+            yield p + n + ".bias", torch.zeros(c, device=dev)
+    yield "showo.model.final_layernorm.weight", torch.ones(D, device=dev)
+    yield "showo.model.final_layernorm.bias", torch.zeros(D, device=dev)
+    yield "showo.lm_head.weight", mat(V, D)
+    yield "showo.lm_head.bias", torch.zeros(V, device=dev)
+
+
+# ======================================================================================================= ours
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import showo_b200
+    from showo_b200 import _lib
+    from oracle import magvit_oracle as MO      # only the deterministic synthetic-weight generator is used here
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun for N > 1"
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.require_gpu()
+
+    model = showo_b200.Showo(False, V, 50295, materialize=False)
+    model._make_engine(dev)
+    for name, t in gpu_random_weights(torch, dev, seed=0):      # streamed one tensor at a time (no 5.8 GB fp32 copy)
+        _lib.check(lib.showo_load_weight(model._engine, name.encode(), _lib.ptr(t), t.numel(), 1), f"load {name}")
+    _lib.check(lib.showo_weights_complete(model._engine), "weights_complete")
+    model._streamed = True
+    vq = showo_b200.MAGVITv2(materialize=False)
+    vq.load_weights(MO.make_magvit_weights(1), device=dev)
+
+    cfg = t2i_config()
+    cond_h, unc_h, descs = synth_prompts(torch, B_PER_GPU, seed=1234 + rank)
+    cond_pin, unc_pin = cond_h.pin_memory(), unc_h.pin_memory()
+    unc_d = unc_h.to(dev)
+    imgs_pin = torch.empty(B_PER_GPU, 256, 256, 3, dtype=torch.uint8).pin_memory()
+    gather_buf = torch.empty(world * B_PER_GPU, 256, 256, 3, dtype=torch.uint8, device=dev) if world > 1 else None
+    ids_d = torch.empty_like(cond_h, device=dev)
+    cond_d0 = cond_h.to(dev)
+
+    def one_step(e2e: bool):
+        if e2e:
+            ids_d.copy_(cond_pin, non_blocking=True)           # H2D of this step's prompts (pinned)
+            unc_d.copy_(unc_pin, non_blocking=True)
+        else:
+            ids_d.copy_(cond_d0)                               # device-resident inputs
+        codes = model.t2i_generate(ids_d, unc_d, descs, guidance_scale=CFG_W, timesteps=T_STEPS, config=cfg)
+        imgs = vq.decode_code_uint8(torch.clamp(codes, 0, CODEBOOK - 1))
+        if world > 1:
+            dist.all_gather_into_tensor(gather_buf, imgs)
+        if e2e:
+            imgs_pin.copy_(imgs, non_blocking=True)            # D2H of the step's result
+            torch.cuda.current_stream().synchronize()
+        return imgs
+
+    def timed(e2e: bool, steps: int):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            one_step(e2e)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.barrier()
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        one_step(False)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_dev = timed(False, args.steps)
+    launches = model.kernel_launches() + vq.kernel_launches()
+    ms_e2e = timed(True, args.steps)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    n_img = world * B_PER_GPU * args.steps
+    value = n_img / (ms_dev / 1e3)
+    e2e_value = n_img / (ms_e2e / 1e3)
+    peaks = measured_peaks()
+
+    out = None
+    if rank == 0:
+        # ---- dominant kernel (tcgen05 GEMM) timed alone with CUDA events on its launch stream: the three shapes of a step
+        S = _lib.current_stream_ptr
+        shapes = [("qkv_fc1", 16 * 258, 3 * D + F, D, 0, NL), ("dense_fc2", 16 * 258, D, D + F, 1, NL), ("head_img", 16 * 256, CODEBOOK, D, 2, 1)]
+        tot_f = tot_ms = 0.0
+        per_shape = {}
+        for name, m_, n_, k_, epi, count in shapes:
+            A = (torch.randn(m_, k_, device=dev) * 0.5).bfloat16()
+            Bw = (torch.randn(n_, k_, device=dev) * 0.02).bfloat16()
+            o = torch.empty(m_, n_, device=dev, dtype=torch.bfloat16 if epi == 0 else torch.float32)
+            r = torch.zeros(m_, n_, device=dev) if epi == 1 else None
+            for _ in range(3):
+                lib.showo_gemm_bf16(_lib.ptr(A), k_, _lib.ptr(Bw), k_, m_, n_, k_, _lib.ptr(o), n_, None, _lib.ptr(r), n_, n_, epi, 0, S())
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20):
+                lib.showo_gemm_bf16(_lib.ptr(A), k_, _lib.ptr(Bw), k_, m_, n_, k_, _lib.ptr(o), n_, None, _lib.ptr(r), n_, n_, epi, 0, S())
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 20
+            fl = 2.0 * m_ * n_ * k_
+            per_shape[name] = {"ms": round(ms, 4), "tflops": round(fl / ms / 1e9, 1)}
+            tot_f += fl * count
+            tot_ms += ms * count
+            del A, Bw, o, r
+        kern_tflops = tot_f / tot_ms / 1e9
+        # ---- CPU baseline: the oracle (port of the reference) on the host cores, bounded sample
+        cpu = cpu_reference_sample(steps=1, warmup=0, quiet=True)
+        clocks = sampler.summary()
+        out = {
+            "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_dev / args.steps, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "showo_demo.yaml t2i 256x256, 18 denoise steps, CFG 5, batch 8 per GPU "
+                                   "(t2i_generate + MAGVIT-v2 decode_code + uint8), random-init Phi-1.5 (1.45 B params)",
+                       "global_batch": world * B_PER_GPU, "seq_len": L_SEQ, "timesteps": T_STEPS, "guidance": CFG_W,
+                       "parallelism": f"dp{world}", "l2": "weights 2.9 GB bf16 streamed every step >> 126 MB L2 (no flush needed)"},
+            "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": int(2 * cond_h.numel() * 8),
+                    "d2h_bytes_per_step": int(imgs_pin.numel()), "ms_per_step": round(ms_e2e / args.steps, 3)},
+            "gpu_launches": int(launches * args.steps),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": round(kern_tflops, 1), "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
+                         "frac": round(kern_tflops / peaks["bf16_burst"], 4), "traffic": None,
+                         "kernel": "gemm_tcgen05_kernel (FLOP-weighted over the 24x2 layer GEMMs + image-vocab head of one "
+                                   "denoise step, each shape timed alone with CUDA events)", "peak_source": peaks["source"],
+                         "per_shape": per_shape},
+            "roofline_job": {"algorithmic_tflop_per_image": round((F_IMG + F_DEC) / 1e12, 3),
+                             "achieved": round((F_IMG + F_DEC) * value / world / 1e12, 1), "peak": peaks["bf16_sustained"],
+                             "unit": "TFLOP/s per GPU", "frac": round((F_IMG + F_DEC) * value / world / 1e12 / peaks["bf16_sustained"], 4)},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out
+
+
+# ======================================================================================================= reference arm (CPU)
+def cpu_reference_sample(steps: int, warmup: int, quiet: bool = False):
+    """Times the oracle (CPU port of the reference's fp32 path; the Python reference itself cannot travel to the GPU box)
+    on the host cores.  One sample = ONE of the 18 denoise-step forwards of ONE image as the reference executes it
+    (cond + uncond rows, L = 387, full 58498-way head) ; MAGVIT decode of one image is timed once; images/s is the
+    extrapolation 1 / (18 * t_step + t_decode)."""
+    import torch
+    from oracle import magvit_oracle as MO
+    from oracle import showo_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    dims = O.PhiDims()
+    g = torch.Generator().manual_seed(0)
+    W = {}
+    Dd, Ff, Vv = dims.hidden, dims.ffn, dims.vocab_size
+    W["showo.model.embed_tokens.weight"] = torch.randn(Vv, Dd, generator=g) * 0.02
+    for i in range(dims.n_layers):
+        p = f"showo.model.layers.{i}."
+        for n, (o, ii) in {"self_attn.q_proj": (Dd, Dd), "self_attn.k_proj": (Dd, Dd), "self_attn.v_proj": (Dd, Dd),
+                           "self_attn.dense": (Dd, Dd), "mlp.fc1": (Ff, Dd), "mlp.fc2": (Dd, Ff)}.items():
+            W[p + n + ".weight"] = torch.randn(o, ii, generator=g) * 0.02
+            W[p + n + ".bias"] = torch.zeros(o)
+        for n, c in {"input_layernorm": Dd, "self_attn.q_layernorm": 64, "self_attn.k_layernorm": 64}.items():
+            W[p + n + ".weight"] = torch.ones(c)
+            W[p + n + ".bias"] = torch.zeros(c)
+    W["showo.model.final_layernorm.weight"] = torch.ones(Dd)
+    W["showo.model.final_layernorm.bias"] = torch.zeros(Dd)
+    W["showo.lm_head.weight"] = torch.randn(Vv, Dd, generator=g) * 0.02
+    W["showo.lm_head.bias"] = torch.zeros(Vv)
+    voc = O.ShowoVocab()
+    cond, unc = O.make_t2i_prompts(1, voc, seed=1234)
+    ids = torch.cat([cond, unc])
+    mask = O.create_attention_mask_predict_next(ids)
+    times = []
+    with torch.no_grad():
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            logits = O.showo_logits(W, dims, input_ids=ids, add_mask=mask)
+            lg = (1 + CFG_W) * logits[:1] - CFG_W * logits[1:]
+            _ = lg[:, -(N_TOK + 1):-1, voc.image_offset:-1].softmax(-1)
+            dt = time.perf_counter() - t0
+            if it >= warmup:
+                times.append(dt)
+        Wm = MO.make_magvit_weights(1)
+        codes = torch.randint(0, CODEBOOK, (1, N_TOK), generator=g)
+        t0 = time.perf_counter()
+        MO.decode_code(codes, Wm)
+        t_dec = time.perf_counter() - t0
+    t_step = sum(times) / len(times)
+    value = 1.0 / (T_STEPS * t_step + t_dec)
+    return {"value": round(value, 6), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{len(times)} x (1 of 18 denoise-step forwards of 1 image: cond+uncond rows, L=387, fp32, full head) "
+                      f"= {t_step:.2f} s each + 1 MAGVIT decode = {t_dec:.2f} s; images/s = 1/(18*t_step + t_decode)",
+            "t_step_s": round(t_step, 3), "t_decode_s": round(t_dec, 3)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cpu = cpu_reference_sample(steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    t_step, t_dec = cpu["t_step_s"], cpu["t_decode_s"]
+    out = {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * t_step, 1), "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "showo_demo.yaml t2i 256x256, 18 denoise steps, CFG 5 -- reference fp32 CPU path (oracle port), "
+                                  "bounded sample: each step = 1 of 18 denoise-step forwards of 1 image", "parallelism": "cpu"},
+           "cpu_baseline": cpu,
+           "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -72,6 +72,7 @@ struct showo_engine {
     int D = 0, H = 0, F = 0, NL = 0, V = 0, W1N = 0, W2K = 0;
     bf16* embed = nullptr;
     bf16* head_w = nullptr; float* head_b = nullptr;
+    float* head_b_img = nullptr;                         // 16B-aligned copy of head_b[image_offset : image_offset + C]
     float* fln_g = nullptr; float* fln_b = nullptr;
     std::vector<LayerW> layers;
     float* cos_tab = nullptr; float* sin_tab = nullptr;
@@ -244,7 +245,7 @@ int showo_engine_destroy(showo_engine_t* e) {
     if (!e) return 0;
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
-    dev_free(e->embed); dev_free(e->head_w); dev_free(e->head_b); dev_free(e->fln_g); dev_free(e->fln_b);
+    dev_free(e->embed); dev_free(e->head_w); dev_free(e->head_b); dev_free(e->head_b_img); dev_free(e->fln_g); dev_free(e->fln_b);
     for (auto& w : e->layers) {
         dev_free(w.w1); dev_free(w.b1); dev_free(w.w2); dev_free(w.b2); dev_free(w.b_dense); dev_free(w.b_fc2);
         dev_free(w.ln_g); dev_free(w.ln_b); dev_free(w.qg); dev_free(w.qb); dev_free(w.kg); dev_free(w.kb);
@@ -350,6 +351,12 @@ int showo_weights_complete(showo_engine_t* e) {
         vec_add_kernel<<<cdiv(e->D, 256), 256>>>(w.b_dense, w.b_fc2, w.b2, e->D);
         SHOWO_CUDA_OK(cudaGetLastError());
     }
+    {
+        const int off = e->cfg.llm_vocab_size + e->cfg.num_new_special_tokens, C = e->cfg.codebook_size;
+        SHOWO_CHECK(off + C <= e->V, "vocabulary layout: image codes exceed vocab_size");
+        if (!e->head_b_img) SHOWO_TRY(dev_alloc(&e->head_b_img, (size_t)C));
+        SHOWO_CUDA_OK(cudaMemcpy(e->head_b_img, e->head_b + off, (size_t)C * 4, cudaMemcpyDeviceToDevice));
+    }
     SHOWO_CUDA_OK(cudaDeviceSynchronize());
     e->finalized = true;
     return 0;
@@ -403,7 +410,7 @@ static int t2i_step_logits(showo_engine* e, const int64_t* ids, int B, int L, in
     SHOWO_TRY(layernorm_bf16(e->x, e->fln_g, e->fln_b, e->cfg.ln_eps, e->xh, nb * B * N, e->D, N, R, R - N - 1, st));
     GemmArgs g{};
     g.A = e->xh; g.lda = e->D; g.B = e->head_w + (size_t)off * e->D; g.ldb = e->D; g.M = nb * B * N; g.N = C; g.K = e->D;
-    g.out = e->logits_ws; g.ldc = C; g.bias = e->head_b + off;
+    g.out = e->logits_ws; g.ldc = C; g.bias = e->head_b_img;
     return gemm_bf16(g, GEMM_BIAS_F32, st);
 }
 

@@ -218,7 +218,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
                 if (p.bias != nullptr) {
-                    if (full) {
+                    if (full && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
                             const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));

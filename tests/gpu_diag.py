@@ -206,9 +206,10 @@ def sec_sampler():
         ids_d = ids.to(dev)
         out = torch.zeros(B, N, dtype=torch.int64, device=dev)
         mk = torch.zeros(B, N, dtype=torch.uint8, device=dev)
-        rc = lib.showo_sampler_step(_lib.ptr(cond.to(dev)), _lib.ptr(unc.to(dev)) if w > 0 else None, B, N, Cc, w, _lib.ptr(ids_d), L, 130,
-                                    voc.image_offset, voc.mask_token_id, floors[step], temps[step], _lib.ptr(expo.to(dev)),
-                                    _lib.ptr(unif.to(dev)), 0, step, _lib.ptr(out), _lib.ptr(mk), S())
+        cond_d, unc_d, expo_d, unif_d = cond.to(dev), unc.to(dev), expo.to(dev), unif.to(dev)
+        rc = lib.showo_sampler_step(_lib.ptr(cond_d), _lib.ptr(unc_d) if w > 0 else None, B, N, Cc, w, _lib.ptr(ids_d), L, 130,
+                                    voc.image_offset, voc.mask_token_id, floors[step], temps[step], _lib.ptr(expo_d),
+                                    _lib.ptr(unif_d), 0, step, _lib.ptr(out), _lib.ptr(mk), S())
         torch.cuda.synchronize()
         if rc:
             print("  rc", rc, lib.showo_last_error()); continue
@@ -220,7 +221,8 @@ def sec_sampler():
     ids = torch.full((B, L), voc.mask_token_id, dtype=torch.int64, device=dev)
     out = torch.zeros(B, N, dtype=torch.int64, device=dev)
     mk = torch.zeros(B, N, dtype=torch.uint8, device=dev)
-    lib.showo_sampler_step(_lib.ptr(cond.to(dev)), None, B, N, Cc, 0.0, _lib.ptr(ids), L, 130, voc.image_offset, voc.mask_token_id,
+    cond_d = cond.to(dev)
+    lib.showo_sampler_step(_lib.ptr(cond_d), None, B, N, Cc, 0.0, _lib.ptr(ids), L, 130, voc.image_offset, voc.mask_token_id,
                            200, 0.9, None, None, 1234, 0, _lib.ptr(out), _lib.ptr(mk), S())
     torch.cuda.synchronize()
     print("  philox: codes in range", int(out.min()), int(out.max()), "masked per row", mk.sum(1).tolist(),
@@ -310,8 +312,9 @@ def sec_t2i():
         # sampler on ORACLE logits (exactness of the sampler) and on engine logits (end-to-end)
         for name, lc, lu, ww in (("oracle-logits", tr.logits.to(dev).contiguous(), None, 0.0), ("engine-logits", sl[:B].contiguous(), sl[B:].contiguous(), w)):
             ids_d = ids_in.clone()
+            expo_d, unif_d = tr.expo.to(dev), tr.uniform.to(dev)
             lib.showo_sampler_step(_lib.ptr(lc), _lib.ptr(lu), B, 256, 8192, ww, _lib.ptr(ids_d), ids_d.shape[1], 130, voc.image_offset,
-                                   voc.mask_token_id, floors[s], temps[s], _lib.ptr(tr.expo.to(dev)), _lib.ptr(tr.uniform.to(dev)), 0, s,
+                                   voc.mask_token_id, floors[s], temps[s], _lib.ptr(expo_d), _lib.ptr(unif_d), 0, s,
                                    _lib.ptr(out), _lib.ptr(mk), S())
             torch.cuda.synchronize()
             print(f"    sampler[{name}] sampled mism {(out.cpu() != tr.sampled_ids).sum().item()} masking mism "
