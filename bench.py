@@ -243,7 +243,7 @@ def run_ours(args):
             del A, Bw, o, r
         kern_tflops = tot_f / tot_ms / 1e9
         # ---- CPU baseline: the oracle (port of the reference) on the host cores, bounded sample
-        cpu = cpu_reference_sample(steps=1, warmup=0, quiet=True)
+        cpu = None if os.environ.get("SHOWO_BENCH_SKIP_CPU") else cpu_reference_sample(steps=1, warmup=1, quiet=True)
         clocks = sampler.summary()
         out = {
             "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -283,7 +283,18 @@ def cpu_reference_sample(steps: int, warmup: int, quiet: bool = False):
     import torch
     from oracle import magvit_oracle as MO
     from oracle import showo_oracle as O
-    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        cores = os.cpu_count() or 1
+    # the container's CPU quota (cgroup v2 cpu.max) is what the process can actually use: on the round-1 GPU box the
+    # affinity mask showed 128 CPUs but the quota was 16 cores, and 128 threads ran 3x slower than 16 (tests/cpu_probe.py)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            cores = max(1, min(cores, int(math.ceil(int(quota) / int(period)))))
+    except Exception:
+        pass
     torch.set_num_threads(cores)
     dims = O.PhiDims()
     g = torch.Generator().manual_seed(0)

@@ -1,0 +1,98 @@
+"""Seeded inputs shared by make_golden.py (which ran the reference on them) and the tests (which replay them).
+Everything comes from numpy's Philox bit generator, so the tensors are identical on every box."""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+from oracle import showo_oracle as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+TINY = dict(hidden=256, n_layers=2, n_heads=4, ffn=1024)
+
+
+def rng(seed):
+    return np.random.Generator(np.random.Philox(seed))
+
+
+def load(name):
+    return np.load(os.path.join(HERE, name))
+
+
+def unpack_mask(z, key):
+    shape = tuple(int(v) for v in z[key + "_shape"])
+    n = int(np.prod(shape))
+    return torch.from_numpy(np.unpackbits(z[key])[:n].reshape(shape).astype(bool))
+
+
+def mask_rows(voc):
+    """id rows covering: long / short / no left padding (t2i), and mmu rows whose eoi position differs from row 0."""
+    cond, uncond = O.make_t2i_prompts(3, voc, seed=5, min_len=8, max_len=64)
+    full = cond[:1].clone()
+    r = rng(9)
+    full[0, :129] = torch.from_numpy(r.integers(0, 50257, size=129).astype("int64"))     # no padding at all
+    full[0, 0] = O.T2I
+    t2i = torch.cat([cond, uncond[:1], full])
+    codes = torch.from_numpy(r.integers(0, 8192, size=(2, 256)).astype("int64"))
+    mmu = O.make_mmu_prompts(2, voc, codes, q_len=12, seed=3)
+    return {"t2i": t2i, "mmu": mmu}
+
+
+def sampler_cases():
+    return [dict(step=0, T=18, w=5.0, B=2, N=256, seed=100), dict(step=7, T=18, w=5.0, B=2, N=256, seed=101),
+            dict(step=17, T=18, w=0.0, B=2, N=256, seed=102), dict(step=3, T=8, w=2.0, B=1, N=1024, seed=103),
+            dict(step=11, T=12, w=1.5, B=3, N=64, seed=104)]
+
+
+def sampler_case(case, voc, C=8192):
+    r = rng(case["seed"])
+    B, N = case["B"], case["N"]
+    cond = torch.from_numpy(r.standard_normal(size=(B, N, C), dtype=np.float32)) * 1.2
+    unc = torch.from_numpy(r.standard_normal(size=(B, N, C), dtype=np.float32)) * 1.2
+    w = case["w"]
+    logits = (1 + w) * cond - w * unc if w > 0 else cond
+    ids_minus = torch.full((B, N), voc.mask_token_id, dtype=torch.int64)
+    known = torch.from_numpy(r.random(size=(B, N), dtype=np.float32) < (case["step"] / case["T"]))
+    codes = torch.from_numpy(r.integers(0, C, size=(B, N)).astype("int64"))
+    ids_minus = torch.where(known, codes, ids_minus)
+    expo = torch.from_numpy(r.standard_exponential(size=(B * N, C), dtype=np.float32))
+    unif = torch.from_numpy(r.random(size=(B, N), dtype=np.float32))
+    temp_in = 1.0
+    for s in range(case["step"]):
+        temp_in = temp_in * (1.0 - (s + 1) / case["T"])
+    return dict(B=B, N=N, cond=cond, unc=unc, logits=logits, ids_minus=ids_minus, expo=expo, unif=unif, temp_in=temp_in)
+
+
+def tiny_t2i_inputs(voc):
+    cond, uncond = O.make_t2i_prompts(2, voc, seed=11)
+    r = rng(12)
+    fill = torch.from_numpy(r.random(size=(2, 256), dtype=np.float32) < 0.4)
+    codes = torch.from_numpy(r.integers(0, 8192, size=(2, 256)).astype("int64")) + voc.image_offset
+    cond[:, 130:386] = torch.where(fill, codes, cond[:, 130:386])
+    uncond[:, 129:] = cond[:, 129:]
+    mask = O.create_attention_mask_predict_next(torch.cat([cond, uncond]))
+    return cond, uncond, mask
+
+
+def tiny_mmu_inputs(voc):
+    r = rng(13)
+    codes = torch.from_numpy(r.integers(0, 8192, size=(3, 256)).astype("int64"))
+    return O.make_mmu_prompts(3, voc, codes, q_len=10, seed=14)
+
+
+def full_row_inputs(voc):
+    cond, _ = O.make_t2i_prompts(1, voc, seed=1234)
+    r = rng(15)
+    fill = torch.from_numpy(r.random(size=(1, 256), dtype=np.float32) < 0.5)
+    codes = torch.from_numpy(r.integers(0, 8192, size=(1, 256)).astype("int64")) + voc.image_offset
+    cond[:, 130:386] = torch.where(fill, codes, cond[:, 130:386])
+    return cond, O.create_attention_mask_predict_next(cond)
+
+
+def magvit_inputs():
+    r = rng(16)
+    codes = torch.from_numpy(r.integers(0, 8192, size=(1, 256)).astype("int64"))
+    pixels = torch.from_numpy(r.random(size=(1, 3, 256, 256), dtype=np.float32)) * 2 - 1
+    return codes, pixels

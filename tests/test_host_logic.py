@@ -1,0 +1,143 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every declared symbol, the product path fails
+loudly without a GPU (no CPU fallback), the Python drop-in keeps the reference's surface, and the data-parallel
+plumbing works at world_size 2 on gloo."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+import showo_b200
+from showo_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_header_symbol():
+    lib = _lib.load()
+    syms = _lib.header_symbols()
+    assert len(syms) >= 26 and "showo_t2i_generate" in syms and "magvit_decode_code" in syms
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, missing
+    assert set(syms) == set(_lib._PROTOS.keys()), set(syms) ^ set(_lib._PROTOS.keys())
+    assert lib.showo_abi_version() == 1
+    # no link-time dependency on the driver library (must dlopen on a CPU-only box)
+    out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "libcuda.so" not in out
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only check")
+def test_product_path_fails_loudly_without_gpu():
+    lib = _lib.load()
+    assert lib.showo_device_count() == 0
+    with pytest.raises(_lib.ShowoError, match="no CPU fallback"):
+        _lib.require_gpu()
+    cfg = _lib.Config(58498, 2048, 24, 32, 8192, 32, 2048, 1e-5, 10000.0, 50295, 10, 8192)
+    h = C.c_void_p()
+    assert lib.showo_engine_create(C.byref(cfg), 0, C.byref(h)) != 0
+    assert b"no CPU fallback" in lib.showo_last_error()
+    hm = C.c_void_p()
+    assert lib.magvit_engine_create(0, C.byref(hm)) != 0
+    m = showo_b200.Showo(False, 58498, 50295, phi_dims=dict(hidden=256, n_layers=1, n_heads=4, ffn=256))
+    with pytest.raises(_lib.ShowoError):
+        m(torch.zeros(1, 8, dtype=torch.int64))
+    with pytest.raises(_lib.ShowoError):
+        showo_b200.MAGVITv2(materialize=False).decode_code(torch.zeros(1, 256, dtype=torch.int64))
+
+
+def test_product_path_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "show-o_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_showo_surface_matches_reference_names():
+    import inspect
+    m = showo_b200.Showo(False, 58498, 50295, phi_dims=dict(hidden=128, n_layers=2, n_heads=2, ffn=256))
+    assert m.config.mask_token_id == 58497 and m.output_size == 58498 and m.vocab_size == 58498
+    keys = set(m.state_dict().keys())
+    for k in ("showo.model.embed_tokens.weight", "showo.model.layers.1.self_attn.q_proj.weight",
+              "showo.model.layers.0.self_attn.k_layernorm.bias", "showo.model.layers.1.mlp.fc2.bias",
+              "showo.model.layers.0.input_layernorm.weight", "showo.model.final_layernorm.bias", "showo.lm_head.bias"):
+        assert k in keys, k
+    assert m.state_dict()["showo.lm_head.weight"].shape == (58498, 128)
+    fwd = list(inspect.signature(m.forward).parameters)
+    assert fwd[:8] == ["input_ids", "input_embeddings", "attention_mask", "labels", "label_smoothing", "batch_size_t2i",
+                       "batch_size_lm", "batch_size_mmu"]
+    t2i = inspect.signature(m.t2i_generate).parameters
+    assert list(t2i)[:9] == ["input_ids", "uncond_input_ids", "attention_mask", "temperature", "timesteps",
+                             "guidance_scale", "noise_schedule", "generator", "config"]
+    assert t2i["timesteps"].default == 18 and t2i["guidance_scale"].default == 0 and t2i["temperature"].default == 1.0
+    mmu = inspect.signature(m.mmu_generate).parameters
+    assert list(mmu) == ["idx", "input_embeddings", "attention_mask", "max_new_tokens", "temperature", "top_k", "eot_token"]
+    e = m.showo.model.embed_tokens(torch.tensor([[1, 2]]))           # called from outside by inference_mmu.py:134
+    assert e.shape == (1, 2, 128)
+    m.showo.resize_token_embeddings(58500)
+    assert m.showo.lm_head.weight.shape == (58500, 128)
+    w = showo_b200.Showo(True, 58498, 50295, phi_dims=dict(hidden=128, n_layers=1, n_heads=2, ffn=256))
+    assert "mm_projector.0.weight" in w.state_dict() and w.state_dict()["mm_projector.2.weight"].shape == (2048, 2048)
+
+
+def test_magvit_surface():
+    vq = showo_b200.MAGVITv2()
+    sd = vq.state_dict()
+    assert sum(v.numel() for v in sd.values()) == 55439171 + 39947833
+    assert sd["decoder.up.3.block.0.nin_shortcut.weight"].shape == (256, 512, 1, 1)
+    assert sd["encoder.down.0.downsample.conv.weight"].shape == (128, 128, 3, 3)
+    assert vq._grid(torch.zeros(1, 1024), None) == (32, 32) and vq._grid(torch.zeros(1, 512), (16, 32)) == (16, 32)
+
+
+def test_shard_rows_partitions_the_batch():
+    from showo_b200.parallel import shard_rows
+    for n, w in ((64, 8), (10, 4), (3, 8), (16, 1)):
+        spans = [shard_rows(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+        assert max(e - b for b, e in spans) - min(e - b for b, e in spans) <= 1
+
+
+_WORKER = r"""
+import os, sys, torch
+sys.path.insert(0, {root!r})
+import showo_b200
+from showo_b200 import parallel as P
+rank, world = P.init(backend="gloo")
+b, e = P.shard_rows(8, rank, world)
+local = torch.full((e - b, 4, 4, 3), rank + 1, dtype=torch.uint8)
+local[:, 0, 0, 0] = torch.arange(b, e, dtype=torch.uint8)
+allimg = P.gather_rows(local, world)
+assert allimg.shape == (8, 4, 4, 3), allimg.shape
+assert allimg[:, 0, 0, 0].tolist() == list(range(8))
+assert allimg[:4, 1, 1, 1].eq(1).all() and allimg[4:, 1, 1, 1].eq(2).all()
+t = P.max_over_ranks(float(rank + 1) * 1.5, torch.device("cpu"))
+assert t == 3.0, t
+codes = P.gather_rows(torch.full((e - b, 16), rank, dtype=torch.int64), world)
+assert codes.shape == (8, 16) and codes[:, 0].tolist() == [0] * 4 + [1] * 4
+torch.distributed.barrier()
+torch.distributed.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_data_parallel_gather_world2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29533", str(script)], capture_output=True, text=True, env=env,
+                       timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
+
+
+def test_bench_reference_arm_contract_offline():
+    """`bench.py --impl reference` on non-zero ranks exits 0 without work (driver launches it under torchrun)."""
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, env=env, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == ""
