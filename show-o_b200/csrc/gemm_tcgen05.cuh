@@ -182,6 +182,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         // ===================================================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1)
         const int quarter = warp & 3;
         const int row_in_tile = quarter * 32 + lane;
+        // 16-byte vector stores / loads need 16 B-aligned rows (odd ldc such as the 58498-wide logits take the scalar path)
+        constexpr int kOutElem = (EPI == EPI_BIAS_BF16 || EPI == EPI_CONV_BF16) ? 2 : 4;
+        bool out_vec_ok = ((p.ldc * kOutElem) % 16 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+        if (EPI == EPI_RESID_F32 || (EPI == EPI_CONV_BF16 && p.resid != nullptr))
+            out_vec_ok = out_vec_ok && ((p.ldr * kOutElem) % 16 == 0) && ((reinterpret_cast<uintptr_t>(p.resid) & 15) == 0);
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int tm = tile % tiles_m, tn = tile / tiles_m;
@@ -236,7 +241,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         for (int j = 0; j < 32; ++j) f[j] = gelu_new_f(f[j]);
                     }
                     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.ldc + n0;
-                    if (full) {
+                    if (full && out_vec_ok) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 8) {
                             uint4 pk;
@@ -252,7 +257,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.ldc + n0;
                     const __nv_bfloat16* r = p.resid ? reinterpret_cast<const __nv_bfloat16*>(p.resid) + m * p.ldr + n0
                                                      : nullptr;
-                    if (full) {
+                    if (full && out_vec_ok) {
                         if (r) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 8) {
@@ -283,7 +288,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 } else if constexpr (EPI == EPI_RESID_F32) {
                     float* o = reinterpret_cast<float*>(p.out) + m * p.ldc + n0;
                     const float* r = reinterpret_cast<const float*>(p.resid) + m * p.ldr + n0;
-                    if (full) {
+                    if (full && out_vec_ok) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
                             const float4 r4 = *reinterpret_cast<const float4*>(r + j);
@@ -296,7 +301,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     }
                 } else {  // EPI_BIAS_F32
                     float* o = reinterpret_cast<float*>(p.out) + m * p.ldc + n0;
-                    if (full && ((p.ldc & 3) == 0)) {
+                    if (full && out_vec_ok) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4)
                             *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);

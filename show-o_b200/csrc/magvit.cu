@@ -203,7 +203,8 @@ __global__ void __launch_bounds__(256) conv_out3_kernel(const bf16* __restrict__
         const float v[3] = {a0, a1, a2};
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            float t = fminf(fmaxf((v[c] + 1.0f) * 0.5f, 0.f), 1.f) * 255.0f;
+            // same fp32 op sequence as torch.clamp((x + 1) / 2, 0, 1) * 255 (no FMA contraction)
+            float t = __fmul_rn(fminf(fmaxf(__fmul_rn(__fadd_rn(v[c], 1.0f), 0.5f), 0.f), 1.f), 255.0f);
             out_u8[p * 3 + c] = (uint8_t)t;          // .astype(uint8) truncates
         }
     }
