@@ -139,17 +139,17 @@ static int run_layers(showo_engine* e, int n_seq, int rows_per_seq, int pos0, in
     for (int l = 0; l < e->NL; ++l) {
         const LayerW& w = e->layers[l];
         SHOWO_TRY(layernorm_bf16(e->x, w.ln_g, w.ln_b, e->cfg.ln_eps, e->xh, M, D, M, M, 0, st));
-        GemmArgs g1{};
-        g1.A = e->xh; g1.lda = D; g1.B = w.w1; g1.ldb = D; g1.M = M; g1.N = e->W1N; g1.K = D;
-        g1.out = e->buf; g1.ldc = e->W1N; g1.bias = w.b1; g1.gelu_from = 3 * D;
-        SHOWO_TRY(gemm_bf16(g1, GEMM_BIAS_BF16, st));
         bf16* kc = e->kcache + (size_t)l * layer_cache_stride(e);
         bf16* vc = e->vtcache + (size_t)l * layer_cache_stride(e);
-        QkRopeArgs r{};
-        r.qkv = e->buf; r.ld = e->W1N; r.n_rows = M; r.rows_per_seq = rows_per_seq; r.pos0 = pos0; r.H = e->H; r.D = D;
-        r.q_gamma = w.qg; r.q_beta = w.qb; r.k_gamma = w.kg; r.k_beta = w.kb; r.eps = e->cfg.ln_eps;
-        r.cos_tab = e->cos_tab; r.sin_tab = e->sin_tab; r.kcache = kc; r.vtcache = vc; r.Lmax = e->cap_L;
-        SHOWO_TRY(qk_norm_rope_scatter(r, st));
+        // GEMM1 + (q/k LayerNorm, partial rotary, K / V^T cache scatter, gelu_new) in one kernel
+        GemmArgs g1{};
+        g1.A = e->xh; g1.lda = D; g1.B = w.w1; g1.ldb = D; g1.M = M; g1.N = e->W1N; g1.K = D;
+        g1.out = e->buf; g1.ldc = e->W1N; g1.bias = w.b1;
+        QkvFuse qf{};
+        qf.D = D; qf.H = e->H; qf.rows_per_seq = rows_per_seq; qf.pos0 = pos0; qf.Lmax = e->cap_L;
+        qf.q_gamma = w.qg; qf.q_beta = w.qb; qf.k_gamma = w.kg; qf.k_beta = w.kb; qf.eps = e->cfg.ln_eps;
+        qf.cos_tab = e->cos_tab; qf.sin_tab = e->sin_tab; qf.kcache = kc; qf.vtcache = vc;
+        SHOWO_TRY(gemm_qkv_bf16(g1, qf, st));
         AttnArgs a{};
         a.q = e->buf + 2 * D; a.ld = e->W1N; a.n_seq = n_seq; a.H = e->H; a.rows_per_seq = rows_per_seq; a.pos0 = pos0;
         a.kcache = kc; a.vtcache = vc; a.Lmax = e->cap_L; a.n_keys = n_keys; a.masks = e->d_masks; a.scale = 0.125f;

@@ -144,6 +144,34 @@ int gemm_bf16(const GemmArgs& a, GemmEpi epi, cudaStream_t st) {
     SHOWO_CHECK(false, "gemm: block_n must be 64, 128 or 256");
 }
 
+template <int BN>
+static int gemm_qkv_bn(const GemmArgs& a, const QkvFuse& f, cudaStream_t st) {
+    CUtensorMap ma, mb;
+    uint64_t da[2] = {(uint64_t)a.K, (uint64_t)a.M}, sa[1] = {(uint64_t)a.lda * 2};
+    uint32_t ba[2] = {64, 128};
+    SHOWO_TRY(make_map(&ma, a.A, 2, da, sa, ba));
+    uint64_t db[2] = {(uint64_t)a.K, (uint64_t)a.N}, sb[1] = {(uint64_t)a.ldb * 2};
+    uint32_t bb[2] = {64, (uint32_t)BN};
+    SHOWO_TRY(make_map(&mb, a.B, 2, db, sb, bb));
+    GemmParams p{};
+    p.M = a.M; p.N = a.N; p.K = a.K; p.out = a.out; p.ldc = a.ldc; p.bias = a.bias; p.gelu_from = 3 * f.D;
+    p.qkv_D = f.D; p.qkv_H = f.H; p.qkv_rows_per_seq = f.rows_per_seq; p.qkv_pos0 = f.pos0; p.qkv_Lmax = f.Lmax;
+    p.q_gamma = f.q_gamma; p.q_beta = f.q_beta; p.k_gamma = f.k_gamma; p.k_beta = f.k_beta; p.qk_eps = f.eps;
+    p.cos_tab = f.cos_tab; p.sin_tab = f.sin_tab; p.kcache = f.kcache; p.vtcache = f.vtcache;
+    return launch<BN, EPI_QKV_BF16, A_PLAIN>(ma, mb, p, cdiv(a.M, 128) * cdiv(a.N, BN), st);
+}
+
+int gemm_qkv_bf16(const GemmArgs& a, const QkvFuse& f, cudaStream_t st) {
+    SHOWO_CHECK(a.M > 0 && a.K > 0 && a.N > 3 * f.D, "gemm_qkv: bad problem");
+    SHOWO_CHECK((a.lda % 8) == 0 && (a.ldb % 8) == 0 && (a.ldc % 8) == 0, "gemm_qkv: leading dimensions must be multiples of 8");
+    SHOWO_CHECK(a.bias != nullptr && (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0, "gemm_qkv: bias must be 16-byte aligned");
+    SHOWO_CHECK(f.D % 64 == 0 && a.N % 64 == 0 && f.H * 64 == f.D, "gemm_qkv: D must be H*64 and N a multiple of 64");
+    SHOWO_CHECK(f.pos0 + f.rows_per_seq <= f.Lmax && a.M % f.rows_per_seq == 0, "gemm_qkv: rows / positions exceed the KV cache");
+    if (f.D % 256 == 0 && a.M > 256) return gemm_qkv_bn<256>(a, f, st);
+    if (f.D % 128 == 0 && a.M > 256) return gemm_qkv_bn<128>(a, f, st);
+    return gemm_qkv_bn<64>(a, f, st);
+}
+
 int conv_nhwc_bf16(const ConvArgs& a, cudaStream_t st) {
     SHOWO_CHECK(a.cin % 64 == 0, "conv: cin must be a multiple of 64 (pad the activation)");
     SHOWO_CHECK(a.taps == 9 || a.taps == 1 || a.taps == 4, "conv: taps must be 9 (3x3), 4 (2x2 forward) or 1 (1x1)");

@@ -18,12 +18,17 @@
 //   EPI_RESID_F32  : out_f32  = resid[m,n] + acc + bias[n]                    (in place allowed)
 //   EPI_BIAS_F32   : out_f32  = acc + bias[n]                                 (logits)
 //   EPI_CONV_BF16  : out_bf16 = acc + bias[n] (+ resid_bf16[m,n]); rows are NHWC pixels of the conv tile
+//   EPI_QKV_BF16   : the layer's fused k|v|q|fc1 projection: per 64-column head slice, in registers (one row per thread):
+//                    k,q: + bias, LayerNorm(64) (weights shared across heads), partial rotary on dims [0,32) at the row's
+//                    position; k -> KV cache [seq][H][Lmax][64], q -> out (bf16, row-major); v: + bias -> V^T cache
+//                    [seq][H][64][Lmax] (warp = 32 consecutive positions -> coalesced); fc1: + bias, gelu_new -> out.
+//                    (phi.py:657-694 q/k/v proj + q/k layernorm + rotary, phi.py:208-211 fc1 + gelu_new)
 #pragma once
 #include "common.cuh"
 
 namespace showo {
 
-enum { EPI_BIAS_BF16 = 0, EPI_RESID_F32 = 1, EPI_BIAS_F32 = 2, EPI_CONV_BF16 = 3 };
+enum { EPI_BIAS_BF16 = 0, EPI_RESID_F32 = 1, EPI_BIAS_F32 = 2, EPI_CONV_BF16 = 3, EPI_QKV_BF16 = 4 };
 enum { A_PLAIN = 0, A_CONV3 = 1 };
 
 struct GemmParams {
@@ -41,6 +46,11 @@ struct GemmParams {
     int conv_taps;          // 9 (3x3) or 1 (1x1)
     int conv_cin;           // channels per tap; K == taps * cin
     int conv_pad;           // 1 for 3x3 same-padding, 0 for 1x1
+    // EPI_QKV_BF16 (fused k|v|q|fc1 projection epilogue): columns [0,D) = k, [D,2D) = v, [2D,3D) = q, [3D,N) = fc1
+    int qkv_D, qkv_H, qkv_rows_per_seq, qkv_pos0, qkv_Lmax;
+    const float* q_gamma; const float* q_beta; const float* k_gamma; const float* k_beta; float qk_eps;
+    const float* cos_tab; const float* sin_tab;     // [max_pos][32]
+    __nv_bfloat16* kcache; __nv_bfloat16* vtcache;  // [seq][H][Lmax][64], [seq][H][64][Lmax]
 };
 
 template <int BN>
@@ -183,7 +193,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int quarter = warp & 3;
         const int row_in_tile = quarter * 32 + lane;
         // 16-byte vector stores / loads need 16 B-aligned rows (odd ldc such as the 58498-wide logits take the scalar path)
-        constexpr int kOutElem = (EPI == EPI_BIAS_BF16 || EPI == EPI_CONV_BF16) ? 2 : 4;
+        constexpr int kOutElem = (EPI == EPI_BIAS_BF16 || EPI == EPI_CONV_BF16 || EPI == EPI_QKV_BF16) ? 2 : 4;
         bool out_vec_ok = ((p.ldc * kOutElem) % 16 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
         if (EPI == EPI_RESID_F32 || (EPI == EPI_CONV_BF16 && p.resid != nullptr))
             out_vec_ok = out_vec_ok && ((p.ldr * kOutElem) % 16 == 0) && ((reinterpret_cast<uintptr_t>(p.resid) & 15) == 0);
@@ -210,6 +220,90 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr0 = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16);
+            if constexpr (EPI == EPI_QKV_BF16) {
+                const int D = p.qkv_D;
+                const int seq = row_ok ? (int)(m / p.qkv_rows_per_seq) : 0;
+                const int pos = row_ok ? p.qkv_pos0 + (int)(m % p.qkv_rows_per_seq) : 0;
+                const int region0 = (tn * BN) / D;          // a BN tile never straddles regions (D % BN == 0)
+                float cs[16], sn[16];
+                if (region0 == 0 || region0 == 2) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 c4 = __ldg(reinterpret_cast<const float4*>(p.cos_tab + (int64_t)pos * 32 + j));
+                        const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.sin_tab + (int64_t)pos * 32 + j));
+                        cs[j] = c4.x; cs[j + 1] = c4.y; cs[j + 2] = c4.z; cs[j + 3] = c4.w;
+                        sn[j] = s4.x; sn[j + 1] = s4.y; sn[j + 2] = s4.z; sn[j + 3] = s4.w;
+                    }
+                }
+#pragma unroll 1
+                for (int c = 0; c < BN; c += 64) {
+                    uint32_t v0[32], v1[32];
+                    __syncwarp();
+                    tmem_ld32(taddr0 + c, v0);
+                    tmem_ld32(taddr0 + c + 32, v1);
+                    tmem_ld_wait();
+                    const int n0 = tn * BN + c;
+                    if (!(row_ok && n0 < p.N)) continue;
+                    float f[64];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { f[j] = __uint_as_float(v0[j]); f[32 + j] = __uint_as_float(v1[j]); }
+#pragma unroll
+                    for (int j = 0; j < 64; j += 4) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+                        f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+                    }
+                    const int region = n0 / D;
+                    if (region >= 3) {                       // fc1 + gelu_new
+#pragma unroll
+                        for (int j = 0; j < 64; ++j) f[j] = gelu_new_f(f[j]);
+                    } else if (region == 1) {                // v -> transposed cache, nothing to the activation buffer
+                        const int h = (n0 - D) >> 6;
+                        __nv_bfloat16* vt = p.vtcache + ((int64_t)seq * p.qkv_H + h) * 64 * (int64_t)p.qkv_Lmax + pos;
+#pragma unroll
+                        for (int j = 0; j < 64; ++j) vt[(int64_t)j * p.qkv_Lmax] = __float2bfloat16(f[j]);
+                        continue;
+                    } else {                                 // k or q: LayerNorm(64) + partial rotary
+                        const float* gam = region == 0 ? p.k_gamma : p.q_gamma;
+                        const float* bet = region == 0 ? p.k_beta : p.q_beta;
+                        float s = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 64; ++j) s += f[j];
+                        const float mean = s * (1.f / 64.f);
+                        float q = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 64; ++j) { f[j] -= mean; q += f[j] * f[j]; }
+                        const float rstd = rsqrtf(q * (1.f / 64.f) + p.qk_eps);
+#pragma unroll
+                        for (int j = 0; j < 64; ++j) f[j] = f[j] * rstd * __ldg(gam + j) + __ldg(bet + j);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {       // rotate_half pairing (j, j+16), emb = cat(freqs, freqs)
+                            const float a = f[j], b = f[j + 16];
+                            f[j] = a * cs[j] - b * sn[j];
+                            f[j + 16] = b * cs[j] + a * sn[j];
+                        }
+                        if (region == 0) {                   // k -> cache row [pos][64]
+                            const int h = n0 >> 6;
+                            __nv_bfloat16* kd = p.kcache + (((int64_t)seq * p.qkv_H + h) * p.qkv_Lmax + pos) * 64;
+#pragma unroll
+                            for (int j = 0; j < 64; j += 8) {
+                                uint4 pk;
+                                pk.x = pack_bf16(f[j], f[j + 1]); pk.y = pack_bf16(f[j + 2], f[j + 3]);
+                                pk.z = pack_bf16(f[j + 4], f[j + 5]); pk.w = pack_bf16(f[j + 6], f[j + 7]);
+                                *reinterpret_cast<uint4*>(kd + j) = pk;
+                            }
+                            continue;
+                        }
+                    }
+                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.ldc + n0;
+#pragma unroll
+                    for (int j = 0; j < 64; j += 8) {
+                        uint4 pk;
+                        pk.x = pack_bf16(f[j], f[j + 1]); pk.y = pack_bf16(f[j + 2], f[j + 3]);
+                        pk.z = pack_bf16(f[j + 4], f[j + 5]); pk.w = pack_bf16(f[j + 6], f[j + 7]);
+                        *reinterpret_cast<uint4*>(o + j) = pk;
+                    }
+                }
+            } else {
 #pragma unroll 1
             for (int c = 0; c < BN; c += 32) {
                 uint32_t v[32];
@@ -312,6 +406,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 }
                 }  // row_ok
             }
+            }  // generic epilogues
             __syncwarp();
             tc_fence_before();
             mbar_arrive(&tmem_empty[acc]);

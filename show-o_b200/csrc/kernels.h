@@ -24,6 +24,16 @@ struct GemmArgs {
 };
 int gemm_bf16(const GemmArgs& a, GemmEpi epi, cudaStream_t st);
 
+// The layer's fused projection GEMM (W1 = [Wk; Wv; Wq; Wfc1]) with the q/k LayerNorm + partial rotary + KV-cache scatter
+// fused into the epilogue (EPI_QKV_BF16 in gemm_tcgen05.cuh).  out receives q (cols [2D,3D)) and gelu(fc1) (cols [3D,N)).
+struct QkvFuse {
+    int D, H, rows_per_seq, pos0, Lmax;
+    const float* q_gamma; const float* q_beta; const float* k_gamma; const float* k_beta; float eps;
+    const float* cos_tab; const float* sin_tab;
+    bf16* kcache; bf16* vtcache;
+};
+int gemm_qkv_bf16(const GemmArgs& a, const QkvFuse& f, cudaStream_t st);
+
 // implicit-GEMM convolution on NHWC bf16 (3x3 pad 1, or 1x1), stride 1.  cin multiple of 64, weights [Cout_pad, taps*cin].
 struct ConvArgs {
     const bf16* x;          // [NB, H, W, cin]

@@ -32,16 +32,16 @@ __global__ void pack_conv_kernel(const float* __restrict__ src, bf16* __restrict
 
 // ------------------------------------------------------------------------------------------------ GroupNorm (+swish)
 // stats[n][g] = (sum, sumsq) over H*W*(C/32) elements.  One thread owns 8 consecutive channels of a pixel.
-__global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ x, float* __restrict__ stats, int HW,
+// Deterministic two-stage reduction (no atomics): each CTA reduces its pixel slab in a fixed order into
+// partials[n][block][g], gn_finalize_kernel sums the blocks in order -> bit-reproducible images run to run.
+__global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ x, float* __restrict__ partials, int HW,
                                                        int C, int pix_per_block) {
-    __shared__ float s_sum[32], s_sq[32];
+    __shared__ float4 part[256];
     const int n = blockIdx.y;
     const int oct = C >> 3;                    // octets per pixel
     const int o = threadIdx.x % oct;
     const int pl = threadIdx.x / oct;
     const int pstride = 256 / oct;
-    if (threadIdx.x < 32) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
-    __syncthreads();
     const int p0 = blockIdx.x * pix_per_block;
     const int p1 = min(p0 + pix_per_block, HW);
     float a0 = 0.f, a1 = 0.f, q0 = 0.f, q1 = 0.f;
@@ -56,15 +56,35 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ 
         a1 += (f2.x + f2.y) + (f3.x + f3.y);
         q1 += (f2.x * f2.x + f2.y * f2.y) + (f3.x * f3.x + f3.y * f3.y);
     }
-    const int cpg = C >> 5;
-    const int g0 = (o * 8) / cpg, g1 = (o * 8 + 4) / cpg;
-    atomicAdd(&s_sum[g0], a0); atomicAdd(&s_sq[g0], q0);
-    atomicAdd(&s_sum[g1], a1); atomicAdd(&s_sq[g1], q1);
+    part[threadIdx.x] = make_float4(a0, q0, a1, q1);
     __syncthreads();
     if (threadIdx.x < 32) {
-        atomicAdd(&stats[((int64_t)n * 32 + threadIdx.x) * 2], s_sum[threadIdx.x]);
-        atomicAdd(&stats[((int64_t)n * 32 + threadIdx.x) * 2 + 1], s_sq[threadIdx.x]);
+        const int g = threadIdx.x;
+        const int cpg = C >> 5;                // 4, 8 or 16 channels per group
+        float s = 0.f, q = 0.f;
+        // half-octets [h0, h1) of this group; half-octet index = channel / 4
+        const int h0 = g * cpg / 4, h1 = (g + 1) * cpg / 4;
+        for (int hh = h0; hh < h1; ++hh) {
+            const int oo = hh >> 1, half = hh & 1;
+            for (int r = 0; r < pstride; ++r) {
+                const float4 v = part[r * oct + oo];
+                s += half ? v.z : v.x;
+                q += half ? v.w : v.y;
+            }
+        }
+        float* dst = partials + (((int64_t)n * gridDim.x + blockIdx.x) * 32 + g) * 2;
+        dst[0] = s; dst[1] = q;
     }
+}
+__global__ void gn_finalize_kernel(const float* __restrict__ partials, float* __restrict__ stats, int nblk) {
+    const int n = blockIdx.x, g = threadIdx.x;
+    float s = 0.f, q = 0.f;
+    for (int b = 0; b < nblk; ++b) {
+        const float* src = partials + (((int64_t)n * nblk + b) * 32 + g) * 2;
+        s += src[0]; q += src[1];
+    }
+    stats[((int64_t)n * 32 + g) * 2] = s;
+    stats[((int64_t)n * 32 + g) * 2 + 1] = q;
 }
 __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ stats,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -333,7 +353,7 @@ struct magvit_engine {
     std::set<std::string> loaded;
     float* stage = nullptr; size_t stage_cap = 0;
     bf16* bufs[4] = {nullptr, nullptr, nullptr, nullptr}; size_t buf_cap = 0;
-    float* stats = nullptr;
+    float* stats = nullptr; float* partials = nullptr;
     float* scores = nullptr; size_t scores_cap = 0; bf16* probs = nullptr; bf16* vt = nullptr;
     int64_t launches_last = 0;
 };
@@ -393,11 +413,14 @@ static int gn(magvit_engine* m, const std::string& name, const bf16* x, bf16* y,
               cudaStream_t st) {
     auto it = m->norm.find(name);
     SHOWO_CHECK(it != m->norm.end() && it->second.c == C, "groupnorm " + name + ": unknown or channel mismatch");
-    SHOWO_CUDA_OK(cudaMemsetAsync(m->stats, 0, (size_t)NB * 64 * 4, st));
     const int HW = H * W;
-    const int ppb = HW >= 4096 ? 256 : (HW >= 256 ? 64 : 16);
+    SHOWO_CHECK(NB <= 32, "groupnorm: batch too large for the partials buffer (max 32 images per call)");
+    const int nblk = cdiv(HW, 64) < 128 ? cdiv(HW, 64) : 128;
+    const int ppb = cdiv(HW, nblk);
     dim3 grid(cdiv(HW, ppb), NB);
-    gn_stats_kernel<<<grid, 256, 0, st>>>(x, m->stats, HW, C, ppb);
+    gn_stats_kernel<<<grid, 256, 0, st>>>(x, m->partials, HW, C, ppb);
+    note_launch();
+    gn_finalize_kernel<<<NB, 32, 0, st>>>(m->partials, m->stats, (int)grid.x);
     note_launch();
     const int64_t total = (int64_t)NB * HW * (C / 8);
     const int g2 = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
@@ -560,7 +583,8 @@ int magvit_engine_create(int device, magvit_engine_t** out) {
     reg_norm(m, "decoder.norm_out", bi); reg_conv(m, "decoder.conv_out", 3, bi, 3);
     reg_conv(m, "decoder.post_quant_conv", kZ, kZ, 1);
     SHOWO_TRY(magvit_alloc_all(m));
-    SHOWO_CUDA_OK(cudaMalloc(&m->stats, 4096 * 64 * 4));
+    SHOWO_CUDA_OK(cudaMalloc(&m->stats, 32 * 64 * 4));
+    SHOWO_CUDA_OK(cudaMalloc(&m->partials, (size_t)32 * 128 * 64 * 4));
     *out = m;
     return 0;
 }
@@ -574,6 +598,7 @@ int magvit_engine_destroy(magvit_engine_t* m) {
     for (int i = 0; i < 4; ++i) if (m->bufs[i]) cudaFree(m->bufs[i]);
     if (m->stage) cudaFree(m->stage);
     if (m->stats) cudaFree(m->stats);
+    if (m->partials) cudaFree(m->partials);
     if (m->scores) cudaFree(m->scores); if (m->probs) cudaFree(m->probs); if (m->vt) cudaFree(m->vt);
     delete m;
     return 0;
