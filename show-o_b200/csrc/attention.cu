@@ -27,6 +27,27 @@ __device__ __forceinline__ bool omni_tile_possible(const showo_seq_mask_t& m, in
     return causal || full || win;
 }
 
+// is EVERY (q in [q_lo,q_hi], k in [k_lo,k_hi)) pair allowed (so the per-element predicate can be skipped)?
+__device__ __forceinline__ bool omni_tile_all_allowed(const showo_seq_mask_t& m, int q_lo, int q_hi, int k_lo, int k_hi,
+                                                      int n_keys) {
+    if (k_hi > n_keys) return false;
+    if (k_lo < m.pad_end && q_hi >= m.pad_end) return false;       // some pad column x some row past the pads
+    const bool causal = (k_hi - 1) <= q_lo;
+    const bool full = (q_lo >= m.full_begin) && (q_hi < m.full_end);
+    const bool win = (k_lo >= m.win_begin) && (k_hi <= m.win_end);
+    return causal || full || win;
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_row) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(smem_u32(smem_row)));
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile(
         "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -64,6 +85,10 @@ __global__ void __launch_bounds__(128) omni_attention_kernel(AttnArgs a) {
         qf[kk][3] = r1_ok ? *reinterpret_cast<const uint32_t*>(qrow1 + c + 8) : 0u;
     }
     const int qpos0 = a.pos0 + r0, qpos1 = a.pos0 + r1;
+    // warps whose 16 rows all lie past the sequence's rows (the tail tile of 258 = 4*64 + 2) only help with the loads
+    const bool warp_active = (q0 + warp * 16) < a.rows_per_seq;
+    const int wq_lo = a.pos0 + q0 + warp * 16;
+    const int wq_hi = a.pos0 + min(q0 + warp * 16 + 15, a.rows_per_seq - 1);
     const int cta_q_lo = a.pos0 + q0;
     const int cta_q_hi = a.pos0 + min(q0 + 63, a.rows_per_seq - 1);
 
@@ -112,62 +137,74 @@ __global__ void __launch_bounds__(128) omni_attention_kernel(AttnArgs a) {
         float s[8][4];
 #pragma unroll
         for (int nb = 0; nb < 8; ++nb) { s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f; }
+        if (warp_active) {
+        // one ldmatrix.x4 feeds two MMAs: matrices = (key block nb, d 0..7), (nb, d 8..15), (nb+1, d 0..7), (nb+1, d 8..15)
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
 #pragma unroll
-            for (int nb = 0; nb < 8; ++nb) {
-                const bf16* kr = &Ks[buf][nb * 8 + g][kk * 16 + t4 * 2];
-                const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kr);
-                const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kr + 8);
-                mma_bf16_16816(s[nb], qf[kk], b0, b1);
+            for (int nb = 0; nb < 8; nb += 2) {
+                uint32_t b[4];
+                ldmatrix_x4(b, &Ks[buf][(nb + (lane >> 4)) * 8 + (lane & 7)][kk * 16 + ((lane >> 3) & 1) * 8]);
+                mma_bf16_16816(s[nb], qf[kk], b[0], b[1]);
+                mma_bf16_16816(s[nb + 1], qf[kk], b[2], b[3]);
             }
         }
-        // ---- scale + mask + online softmax
+        // ---- mask (only on tiles the predicate does not fully allow for this warp's 16 rows) + online softmax.
+        //      Maxima are tracked on the raw scores; p = exp2(s*c - m*c) is one FFMA + one MUFU per element.
         const int k0 = kt * kTileK;
+        if (!omni_tile_all_allowed(msk, wq_lo, wq_hi, k0, k0 + kTileK, a.n_keys)) {
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int col = k0 + nb * 8 + t4 * 2 + (e & 1);
+                    const int qp = (e < 2) ? qpos0 : qpos1;
+                    const bool ok = (col < a.n_keys) && omni_allowed(msk, qp, col);
+                    s[nb][e] = ok ? s[nb][e] : kNegBig;
+                }
+            }
+        }
         float tm0 = kNegBig, tm1 = kNegBig;
 #pragma unroll
         for (int nb = 0; nb < 8; ++nb) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int col = k0 + nb * 8 + t4 * 2 + (e & 1);
-                const int qp = (e < 2) ? qpos0 : qpos1;
-                const bool ok = (col < a.n_keys) && omni_allowed(msk, qp, col);
-                const float v = ok ? s[nb][e] * sc : kNegBig;
-                s[nb][e] = v;
-                if (e < 2) tm0 = fmaxf(tm0, v); else tm1 = fmaxf(tm1, v);
-            }
+            tm0 = fmaxf(tm0, fmaxf(s[nb][0], s[nb][1]));
+            tm1 = fmaxf(tm1, fmaxf(s[nb][2], s[nb][3]));
         }
         tm0 = fmaxf(tm0, __shfl_xor_sync(0xffffffffu, tm0, 1));
         tm0 = fmaxf(tm0, __shfl_xor_sync(0xffffffffu, tm0, 2));
         tm1 = fmaxf(tm1, __shfl_xor_sync(0xffffffffu, tm1, 1));
         tm1 = fmaxf(tm1, __shfl_xor_sync(0xffffffffu, tm1, 2));
         const float mn0 = fmaxf(m0, tm0), mn1 = fmaxf(m1, tm1);
-        const float al0 = exp2f(m0 - mn0), al1 = exp2f(m1 - mn1);
+        const float al0 = ex2_approx((m0 - mn0) * sc), al1 = ex2_approx((m1 - mn1) * sc);
         m0 = mn0; m1 = mn1;
+        // rows that have not met an allowed key yet keep offset 0: fma(-1e30, c, +1e30*c) would NOT cancel exactly
+        // (exact product vs rounded addend) and could overflow exp2; with offset 0 their p is exactly 0
+        const float ms0 = (m0 == kNegBig) ? 0.f : -m0 * sc, ms1 = (m1 == kNegBig) ? 0.f : -m1 * sc;
         l0 *= al0; l1 *= al1;
 #pragma unroll
         for (int nd = 0; nd < 8; ++nd) { o[nd][0] *= al0; o[nd][1] *= al0; o[nd][2] *= al1; o[nd][3] *= al1; }
         uint32_t pf[4][4];
 #pragma unroll
         for (int nb = 0; nb < 8; ++nb) {
-            const float p0 = exp2f(s[nb][0] - m0), p1 = exp2f(s[nb][1] - m0);
-            const float p2 = exp2f(s[nb][2] - m1), p3 = exp2f(s[nb][3] - m1);
+            const float p0 = ex2_approx(fmaf(s[nb][0], sc, ms0)), p1 = ex2_approx(fmaf(s[nb][1], sc, ms0));
+            const float p2 = ex2_approx(fmaf(s[nb][2], sc, ms1)), p3 = ex2_approx(fmaf(s[nb][3], sc, ms1));
             l0 += p0 + p1; l1 += p2 + p3;
             const int kk = nb >> 1;
             if ((nb & 1) == 0) { pf[kk][0] = pack_bf16(p0, p1); pf[kk][1] = pack_bf16(p2, p3); }
             else               { pf[kk][2] = pack_bf16(p0, p1); pf[kk][3] = pack_bf16(p2, p3); }
         }
-        // ---- O += P V   (B operand = V^T tile: [dim][key], keys contiguous)
+        // ---- O += P V   (B operand = V^T tile: [dim][key], keys contiguous; same ldmatrix pattern)
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
 #pragma unroll
-            for (int nd = 0; nd < 8; ++nd) {
-                const bf16* vr = &Vs[buf][nd * 8 + g][kk * 16 + t4 * 2];
-                const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vr);
-                const uint32_t b1 = *reinterpret_cast<const uint32_t*>(vr + 8);
-                mma_bf16_16816(o[nd], pf[kk], b0, b1);
+            for (int nd = 0; nd < 8; nd += 2) {
+                uint32_t b[4];
+                ldmatrix_x4(b, &Vs[buf][(nd + (lane >> 4)) * 8 + (lane & 7)][kk * 16 + ((lane >> 3) & 1) * 8]);
+                mma_bf16_16816(o[nd], pf[kk], b[0], b[1]);
+                mma_bf16_16816(o[nd + 1], pf[kk], b[2], b[3]);
             }
         }
+        }  // warp_active
         __syncthreads();
         buf ^= 1;
         kt = kt_next;
