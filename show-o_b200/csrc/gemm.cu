@@ -48,10 +48,10 @@ static std::mutex g_maps_mu;
 
 // bf16 tensor map, 128B swizzle, zero OOB fill.  dims/strides innermost first; strides in bytes for dims 1..rank-1.
 static int make_map(CUtensorMap* out, const void* ptr, uint32_t rank, const uint64_t* dims, const uint64_t* strides,
-                    const uint32_t* box) {
+                    const uint32_t* box, int swizzle_bytes = 128) {
     MapKey key{ptr, dims[0], rank > 1 ? dims[1] : 0, rank > 2 ? dims[2] : 0, rank > 3 ? dims[3] : 0,
                rank > 1 ? strides[0] : 0, rank > 2 ? strides[1] : 0, rank > 3 ? strides[2] : 0,
-               box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0, rank};
+               box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0, rank | ((uint32_t)swizzle_bytes << 8)};
     {
         std::lock_guard<std::mutex> lk(g_maps_mu);
         auto it = g_maps.find(key);
@@ -65,7 +65,8 @@ static int make_map(CUtensorMap* out, const void* ptr, uint32_t rank, const uint
     for (uint32_t i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; }
     for (uint32_t i = 0; i + 1 < rank; ++i) gs[i] = strides[i];
     CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gd, gs, bx, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_last_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r) + " rank " +
@@ -79,6 +80,27 @@ static int make_map(CUtensorMap* out, const void* ptr, uint32_t rank, const uint
     return 0;
 }
 
+// A/B switch while tuning: SHOWO_GEMM_BK=32 selects 9 x 24 KB stages (64B swizzle) instead of 4 x 48 KB (128B swizzle)
+static bool gemm_bk32() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SHOWO_GEMM_BK"); v = (e && atoi(e) == 32) ? 1 : 0; }
+    return v == 1;
+}
+
+// SHOWO_GEMM_CL=2: clusters of 2 CTAs along M with the B tile TMA-multicast (A/B switch while tuning)
+static int gemm_cluster() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SHOWO_GEMM_CL"); v = e ? atoi(e) : 1; }
+    return v;
+}
+
+// SHOWO_GEMM_CG=2: CTA pairs issuing cta_group::2 MMAs (M = 256 per pair, B tile split across the pair)
+static int gemm_cta_group() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SHOWO_GEMM_CG"); v = e ? atoi(e) : 2; }   // default: CTA pairs
+    return v;
+}
+
 int gemm_num_sms() {
     static int n = 0;
     if (n == 0) {
@@ -89,39 +111,53 @@ int gemm_num_sms() {
     return n;
 }
 
-template <int BN, int EPI, int AMODE>
+template <int BN, int EPI, int AMODE, int BK = 64, int CL = 1, int CG = 1>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int num_tiles, cudaStream_t st) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, BK, CG>;
     static bool attr_set = false;
-    auto kern = gemm_tcgen05_kernel<BN, EPI, AMODE>;
+    auto kern = gemm_tcgen05_kernel<BN, EPI, AMODE, BK, CL, CG>;
     if (!attr_set) {
         SHOWO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         attr_set = true;
     }
     int grid = num_tiles < gemm_num_sms() ? num_tiles : gemm_num_sms();
+    if constexpr (CL > 1) {
+        // num_tiles counts work units (CL m-tiles each); one cluster per unit, as many clusters as fit the SMs
+        const int max_clusters = gemm_num_sms() / CL;
+        const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(clusters * CL); cfg.blockDim = dim3(Cfg::kThreads); cfg.dynamicSmemBytes = Cfg::kSmemBytes; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        SHOWO_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ma, mb, p));
+        note_launch();
+        return 0;
+    }
     kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(ma, mb, p);
     note_launch();
     SHOWO_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-template <int BN>
+template <int BN, int BK = 64, int CL = 1, int CG = 1>
 static int gemm_bn(const GemmArgs& a, GemmEpi epi, cudaStream_t st) {
     CUtensorMap ma, mb;
     uint64_t da[2] = {(uint64_t)a.K, (uint64_t)a.M}, sa[1] = {(uint64_t)a.lda * 2};
-    uint32_t ba[2] = {64, 128};
-    SHOWO_TRY(make_map(&ma, a.A, 2, da, sa, ba));
+    uint32_t ba[2] = {BK, 128};
+    SHOWO_TRY(make_map(&ma, a.A, 2, da, sa, ba, BK * 2));
     uint64_t db[2] = {(uint64_t)a.K, (uint64_t)a.N}, sb[1] = {(uint64_t)a.ldb * 2};
-    uint32_t bb[2] = {64, (uint32_t)BN};
-    SHOWO_TRY(make_map(&mb, a.B, 2, db, sb, bb));
+    uint32_t bb[2] = {BK, (uint32_t)(BN / CL)};
+    SHOWO_TRY(make_map(&mb, a.B, 2, db, sb, bb, BK * 2));
     GemmParams p{};
     p.M = a.M; p.N = a.N; p.K = a.K;
     p.out = a.out; p.ldc = a.ldc; p.bias = a.bias; p.resid = a.resid; p.ldr = a.ldr; p.gelu_from = a.gelu_from;
-    const int tiles = cdiv(a.M, 128) * cdiv(a.N, BN);
+    const int tiles = cdiv(cdiv(a.M, 128), CL) * cdiv(a.N, BN);
     switch (epi) {
-        case GEMM_BIAS_BF16: return launch<BN, EPI_BIAS_BF16, A_PLAIN>(ma, mb, p, tiles, st);
-        case GEMM_RESID_F32: return launch<BN, EPI_RESID_F32, A_PLAIN>(ma, mb, p, tiles, st);
-        case GEMM_BIAS_F32: return launch<BN, EPI_BIAS_F32, A_PLAIN>(ma, mb, p, tiles, st);
+        case GEMM_BIAS_BF16: return launch<BN, EPI_BIAS_BF16, A_PLAIN, BK, CL, CG>(ma, mb, p, tiles, st);
+        case GEMM_RESID_F32: return launch<BN, EPI_RESID_F32, A_PLAIN, BK, CL, CG>(ma, mb, p, tiles, st);
+        case GEMM_BIAS_F32: return launch<BN, EPI_BIAS_F32, A_PLAIN, BK, CL, CG>(ma, mb, p, tiles, st);
     }
     SHOWO_CHECK(false, "bad epilogue");
 }
@@ -138,27 +174,30 @@ int gemm_bf16(const GemmArgs& a, GemmEpi epi, cudaStream_t st) {
         else if (a.N >= 128) bn = 128;
         else bn = 64;
     }
+    if (bn == 256 && gemm_cta_group() == 2 && a.M > 128) return gemm_bn<256, 64, 2, 2>(a, epi, st);
+    if (bn == 256 && gemm_cluster() == 2 && a.M > 128) return gemm_bn<256, 64, 2>(a, epi, st);
+    if (bn == 256 && gemm_bk32()) return gemm_bn<256, 32>(a, epi, st);
     if (bn == 256) return gemm_bn<256>(a, epi, st);
     if (bn == 128) return gemm_bn<128>(a, epi, st);
     if (bn == 64) return gemm_bn<64>(a, epi, st);
     SHOWO_CHECK(false, "gemm: block_n must be 64, 128 or 256");
 }
 
-template <int BN>
+template <int BN, int BK = 64, int CL = 1, int CG = 1>
 static int gemm_qkv_bn(const GemmArgs& a, const QkvFuse& f, cudaStream_t st) {
     CUtensorMap ma, mb;
     uint64_t da[2] = {(uint64_t)a.K, (uint64_t)a.M}, sa[1] = {(uint64_t)a.lda * 2};
-    uint32_t ba[2] = {64, 128};
-    SHOWO_TRY(make_map(&ma, a.A, 2, da, sa, ba));
+    uint32_t ba[2] = {BK, 128};
+    SHOWO_TRY(make_map(&ma, a.A, 2, da, sa, ba, BK * 2));
     uint64_t db[2] = {(uint64_t)a.K, (uint64_t)a.N}, sb[1] = {(uint64_t)a.ldb * 2};
-    uint32_t bb[2] = {64, (uint32_t)BN};
-    SHOWO_TRY(make_map(&mb, a.B, 2, db, sb, bb));
+    uint32_t bb[2] = {BK, (uint32_t)(BN / CL)};
+    SHOWO_TRY(make_map(&mb, a.B, 2, db, sb, bb, BK * 2));
     GemmParams p{};
     p.M = a.M; p.N = a.N; p.K = a.K; p.out = a.out; p.ldc = a.ldc; p.bias = a.bias; p.gelu_from = 3 * f.D;
     p.qkv_D = f.D; p.qkv_H = f.H; p.qkv_rows_per_seq = f.rows_per_seq; p.qkv_pos0 = f.pos0; p.qkv_Lmax = f.Lmax;
     p.q_gamma = f.q_gamma; p.q_beta = f.q_beta; p.k_gamma = f.k_gamma; p.k_beta = f.k_beta; p.qk_eps = f.eps;
     p.cos_tab = f.cos_tab; p.sin_tab = f.sin_tab; p.kcache = f.kcache; p.vtcache = f.vtcache;
-    return launch<BN, EPI_QKV_BF16, A_PLAIN>(ma, mb, p, cdiv(a.M, 128) * cdiv(a.N, BN), st);
+    return launch<BN, EPI_QKV_BF16, A_PLAIN, BK, CL, CG>(ma, mb, p, cdiv(cdiv(a.M, 128), CL) * cdiv(a.N, BN), st);
 }
 
 int gemm_qkv_bf16(const GemmArgs& a, const QkvFuse& f, cudaStream_t st) {
@@ -167,6 +206,9 @@ int gemm_qkv_bf16(const GemmArgs& a, const QkvFuse& f, cudaStream_t st) {
     SHOWO_CHECK(a.bias != nullptr && (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0, "gemm_qkv: bias must be 16-byte aligned");
     SHOWO_CHECK(f.D % 64 == 0 && a.N % 64 == 0 && f.H * 64 == f.D, "gemm_qkv: D must be H*64 and N a multiple of 64");
     SHOWO_CHECK(f.pos0 + f.rows_per_seq <= f.Lmax && a.M % f.rows_per_seq == 0, "gemm_qkv: rows / positions exceed the KV cache");
+    if (f.D % 256 == 0 && a.M > 256 && gemm_cta_group() == 2) return gemm_qkv_bn<256, 64, 2, 2>(a, f, st);
+    if (f.D % 256 == 0 && a.M > 256 && gemm_cluster() == 2) return gemm_qkv_bn<256, 64, 2>(a, f, st);
+    if (f.D % 256 == 0 && a.M > 256 && gemm_bk32()) return gemm_qkv_bn<256, 32>(a, f, st);
     if (f.D % 256 == 0 && a.M > 256) return gemm_qkv_bn<256>(a, f, st);
     if (f.D % 128 == 0 && a.M > 256) return gemm_qkv_bn<128>(a, f, st);
     return gemm_qkv_bn<64>(a, f, st);

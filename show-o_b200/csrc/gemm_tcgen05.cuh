@@ -53,24 +53,25 @@ struct GemmParams {
     __nv_bfloat16* kcache; __nv_bfloat16* vtcache;  // [seq][H][Lmax][64], [seq][H][64][Lmax]
 };
 
-template <int BN>
+template <int BN, int BK_ = 64, int CG = 1>
 struct GemmCfg {
     static constexpr int BM = 128;
-    static constexpr int BK = 64;
+    static constexpr int BK = BK_;                          // 64 -> 128B-swizzled rows, 32 -> 64B-swizzled rows (more, smaller stages)
     static constexpr int kAB = BM * BK * 2;                 // 16 KB
-    static constexpr int kBB = BN * BK * 2;
+    static constexpr int kBB = BN * BK * 2 / CG;          // cta_group::2: each CTA of the pair holds half of the B tile
     static constexpr int kStageBytes = kAB + kBB;
-    static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int kStages = (CG == 2) ? 6 : (BK_ == 64) ? ((BN == 256) ? 4 : (BN == 128 ? 6 : 8)) : ((BN == 256) ? 9 : (BN == 128 ? 13 : 16));
     static constexpr int kTmemCols = 2 * BN;                // 2 accumulator stages (power of two for BN in {64,128,256})
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 512 /*barriers*/;
     static constexpr int kThreads = 192;
 };
 
-template <int BN, int EPI, int AMODE>
+template <int BN, int EPI, int AMODE, int BK_ = 64, int CL = 1, int CG = 1>
 __global__ void __launch_bounds__(192, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const GemmParams p) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, BK_, CG>;
+    static_assert(CG == 1 || (CG == 2 && CL == 2 && BN == 256 && BK_ == 64), "cta_group::2 needs a CTA pair");
     constexpr int BM = Cfg::BM, BK = Cfg::BK, kStages = Cfg::kStages;
 
     extern __shared__ uint8_t smem_raw[];
@@ -94,7 +95,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         tiles_m = (p.M + BM - 1) / BM;
     }
     const int tiles_n = (p.N + BN - 1) / BN;
-    const int num_tiles = tiles_m * tiles_n;
+    // Work unit = CL m-tiles (one per CTA of the cluster) that share one B tile: each CTA TMA-loads 1/CL of the B tile and
+    // multicasts it to the whole cluster, which cuts the L2->SM traffic per flop (the measured limiter at CL = 1).
+    static_assert(CL == 1 || (AMODE == A_PLAIN && (BN % CL) == 0), "clusters only for the plain GEMM");
+    const int crank = (CL > 1) ? (int)cluster_ctarank() : 0;
+    const int tiles_mc = (tiles_m + CL - 1) / CL;
+    const int num_units = tiles_mc * tiles_n;
+    const int unit0 = blockIdx.x / CL, unit_stride = gridDim.x / CL;
     const int num_kb = (AMODE == A_CONV3) ? p.conv_taps * ((p.conv_cin + BK - 1) / BK) : (p.K + BK - 1) / BK;
 
     if (warp == 0 && lane == 0) {
@@ -105,19 +112,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (lane == 0) {
             for (int s = 0; s < kStages; ++s) {
                 mbar_init(&full_bar[s], 1);
-                mbar_init(&empty_bar[s], 1);
+                mbar_init(&empty_bar[s], CG == 2 ? 1 : CL);   // CL>1 multicast: one arrival per CTA writing into this smem
             }
             for (int a = 0; a < 2; ++a) {
                 mbar_init(&tmem_full[a], 1);
-                mbar_init(&tmem_empty[a], 128);
+                mbar_init(&tmem_empty[a], 128 * CG);          // cta_group::2: the leader waits for both CTAs epilogues
             }
             mbar_fence_init();
         }
         __syncwarp();
-        tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+        if constexpr (CG == 2) tmem_alloc_cg2<Cfg::kTmemCols>(tmem_slot);
+        else tmem_alloc<Cfg::kTmemCols>(tmem_slot);
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (CL > 1) cluster_sync_all();      // peer barriers must be initialised before any multicast lands
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -126,8 +135,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int tm = tile % tiles_m, tn = tile / tiles_m;
+            for (int unit = unit0; unit < num_units; unit += unit_stride) {
+                const int tm = (unit % tiles_mc) * CL + crank, tn = unit / tiles_mc;
                 int img = 0, y0 = 0, x0 = 0;
                 if constexpr (AMODE == A_CONV3) {
                     const int tw = cdiv_dev(p.conv_W, p.conv_TW), th = cdiv_dev(p.conv_H, p.conv_TH);
@@ -138,6 +147,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 }
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if constexpr (CG == 2) {
+                        // both CTAs load their A tile and their half of B; all bytes are credited to the LEADER barrier
+                        if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+                        tma_load_2d_cg2(smem_a + stage * Cfg::kAB, &tmap_a, &full_bar[stage], kb * BK, tm * BM);
+                        tma_load_2d_cg2(smem_b + stage * Cfg::kBB, &tmap_b, &full_bar[stage], kb * BK, tn * BN + crank * (BN / 2));
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
                     if constexpr (AMODE == A_CONV3) {
                         const int cchunks = (p.conv_cin + BK - 1) / BK;
@@ -151,7 +168,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                                     tn * BN);
                     } else {
                         tma_load_2d(smem_a + stage * Cfg::kAB, &tmap_a, &full_bar[stage], kb * BK, tm * BM);
-                        tma_load_2d(smem_b + stage * Cfg::kBB, &tmap_b, &full_bar[stage], kb * BK, tn * BN);
+                        if constexpr (CL == 1) {
+                            tma_load_2d(smem_b + stage * Cfg::kBB, &tmap_b, &full_bar[stage], kb * BK, tn * BN);
+                        } else {   // my 1/CL slice of the B tile, delivered to every CTA of the cluster (tmap_b box = BN/CL rows)
+                            tma_load_2d_multicast(smem_b + stage * Cfg::kBB + crank * (Cfg::kBB / CL), &tmap_b, &full_bar[stage],
+                                                  kb * BK, tn * BN + crank * (BN / CL), (uint16_t)((1u << CL) - 1));
+                        }
                     }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
@@ -159,11 +181,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
     } else if (warp == 1) {
         // ===================================================== MMA issuer
-        constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+        constexpr uint32_t idesc = umma_idesc_bf16(BM * CG, BN);     // cta_group::2: one M = 256 instruction for the pair
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const bool issuer = (CG == 1) || (crank == 0);               // only the pair leader issues 2-SM MMAs
+        for (int unit = unit0; issuer && unit < num_units; unit += unit_stride, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -177,12 +200,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::kBB);
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
-                        const uint64_t da = umma_desc_k128(a_addr + k * 32);
-                        const uint64_t db = umma_desc_k128(b_addr + k * 32);
-                        umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
+                        const uint64_t da = umma_desc_kmajor<BK * 2>(a_addr + k * 32);
+                        const uint64_t db = umma_desc_kmajor<BK * 2>(b_addr + k * 32);
+                        if constexpr (CG == 2) umma_bf16_cg2(d_tmem, da, db, idesc, (kb | k) != 0);
+                        else umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
                     }
-                    umma_commit(&empty_bar[stage]);                 // frees the smem slot when these MMAs retire
-                    if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
+                    if constexpr (CG == 2) {                          // frees the slot / publishes the accumulator in BOTH CTAs
+                        umma_commit_cg2(&empty_bar[stage], 3);
+                        if (kb == num_kb - 1) umma_commit_cg2(&tmem_full[acc], 3);
+                    } else {
+                        if constexpr (CL == 1) umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
+                        else umma_commit_multicast(&empty_bar[stage], (uint16_t)((1u << CL) - 1));   // ... in every CTA of the cluster
+                        if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
+                    }
                 }
                 __syncwarp();
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -198,8 +228,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (EPI == EPI_RESID_F32 || (EPI == EPI_CONV_BF16 && p.resid != nullptr))
             out_vec_ok = out_vec_ok && ((p.ldr * kOutElem) % 16 == 0) && ((reinterpret_cast<uintptr_t>(p.resid) & 15) == 0);
         int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int tm = tile % tiles_m, tn = tile / tiles_m;
+        for (int unit = unit0; unit < num_units; unit += unit_stride, ++it) {
+            const int tm = (unit % tiles_mc) * CL + crank, tn = unit / tiles_mc;
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             // output row of this thread
@@ -409,15 +439,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }  // generic epilogues
             __syncwarp();
             tc_fence_before();
-            mbar_arrive(&tmem_empty[acc]);
+            if (CG == 2 && crank != 0) mbar_arrive_remote(&tmem_empty[acc], 0);   // the leader owns the accumulator hand-off
+            else mbar_arrive(&tmem_empty[acc]);
         }
     }
 
     tc_fence_before();
     __syncthreads();
+    if constexpr (CL > 1) cluster_sync_all();      // no CTA may exit while a peer can still multicast into it
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+        if constexpr (CG == 2) tmem_dealloc_cg2<Cfg::kTmemCols>(tmem_base);
+        else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
     }
 }
 
