@@ -164,6 +164,7 @@ static int gemm_bn(const GemmArgs& a, GemmEpi epi, cudaStream_t st) {
 
 int gemm_bf16(const GemmArgs& a, GemmEpi epi, cudaStream_t st) {
     SHOWO_CHECK(a.M > 0 && a.N > 0 && a.K > 0, "gemm: empty problem");
+    if (a.M <= 16 && a.K % 64 == 0 && a.block_n == 0) return gemm_skinny(a, (int)epi, nullptr, st);   // decode: HBM-bound weight streaming
     SHOWO_CHECK((a.lda % 8) == 0 && (a.ldb % 8) == 0, "gemm: lda/ldb must be multiples of 8 elements (16 B)");
     SHOWO_CHECK((reinterpret_cast<uintptr_t>(a.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.B) & 15) == 0,
                 "gemm: A/B must be 16-byte aligned");
@@ -201,6 +202,7 @@ static int gemm_qkv_bn(const GemmArgs& a, const QkvFuse& f, cudaStream_t st) {
 }
 
 int gemm_qkv_bf16(const GemmArgs& a, const QkvFuse& f, cudaStream_t st) {
+    if (a.M <= 16 && a.K % 64 == 0) return gemm_skinny(a, 3, &f, st);
     SHOWO_CHECK(a.M > 0 && a.K > 0 && a.N > 3 * f.D, "gemm_qkv: bad problem");
     SHOWO_CHECK((a.lda % 8) == 0 && (a.ldb % 8) == 0 && (a.ldc % 8) == 0, "gemm_qkv: leading dimensions must be multiples of 8");
     SHOWO_CHECK(a.bias != nullptr && (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0, "gemm_qkv: bias must be 16-byte aligned");

@@ -1,0 +1,297 @@
+// Weight-streaming "skinny" GEMM for the decode path (M <= 16 token rows: one new token per sequence):
+//     C[M,N] = X[M,K] * W[N,K]^T (+ fused epilogue)
+// HBM-bound: every weight is read exactly once, 16 B per thread per load, 8 rows x 128 B per warp-load (100 % sector
+// efficiency), several loads in flight per thread.  The 16-row X slab lives in shared memory; the contraction runs on
+// tensor cores (mma.sync m16n8k16, M = 16 fits exactly) -- CUDA cores would be compute-bound at 16 rows.
+//
+// Fragment trick: a thread's 16 B weight load covers 8 consecutive k of ONE feature row, whereas the mma B fragment
+// wants k = {2t, 2t+1, 2t+8, 2t+9}.  The contraction order is free, so k is permuted: within a 64-wide chunk thread t4
+// owns physical k = t4*16 + 4j + {0,1,2,3} for k16-step j, and the A (X) fragments are gathered from smem with the same
+// permutation.
+//
+// Parallelism: one CTA = 64 output features x one K split (grid = N/64 x splits, >= ~1 CTA wave over 148 SMs even for
+// the N = 2048, K = 10240 projection).  Split-K partials go to a workspace; the LAST CTA of a feature tile (atomic ticket)
+// sums them in split order -- deterministic -- and runs the epilogue on the complete [16 x 64] fp32 tile.
+// Epilogues: bias(+gelu_new) -> bf16, residual + bias -> fp32, bias -> fp32, and the fused k|v|q|fc1 one (a 64-feature
+// tile is exactly one attention head: LayerNorm(64) + partial rotary + KV-cache scatter, phi.py:657-694).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace showo {
+
+enum { SK_BIAS_BF16 = 0, SK_RESID_F32 = 1, SK_BIAS_F32 = 2, SK_QKV = 3 };
+
+struct SkinnyParams {
+    const bf16* X; int64_t lda; const bf16* W; int64_t ldb;
+    int M, N, K, splits, kc;             // kc = K per split (multiple of 64)
+    void* out; int64_t ldc; const float* bias; const float* resid; int64_t ldr; int gelu_from;
+    float* partials; int* tickets;
+    QkvFuse qf;
+};
+
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint4 ldg_stream(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+constexpr int kSkThreads = 128;
+constexpr int kSkTileN = 64;
+
+template <int EPI>
+__global__ void __launch_bounds__(kSkThreads) skinny_gemm_kernel(SkinnyParams p) {
+    extern __shared__ __align__(16) uint8_t sk_smem[];
+    const int xs_stride = p.kc + 2;                                   // +1 word: conflict-free permuted A-fragment loads
+    bf16* xs = reinterpret_cast<bf16*>(sk_smem);                      // [16][kc + 2]
+    float* tile = reinterpret_cast<float*>(sk_smem + (size_t)16 * xs_stride * 2 + 16);   // [16][64] fp32
+    tile = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tile) + 15) & ~uintptr_t(15));
+    __shared__ int s_last;
+
+    const int tn = blockIdx.x, split = blockIdx.y;
+    const int n0 = tn * kSkTileN, k0 = split * p.kc;
+    const int kc = min(p.kc, p.K - k0);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+
+    // ---- start streaming the weights first (they do not depend on X): warp w owns features n0 + w*16 + {0..7} (block 0) and + {8..15} (block 1)
+    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    const int f0 = n0 + warp * 16 + g, f1 = f0 + 8;
+    const bool f0_ok = f0 < p.N, f1_ok = f1 < p.N;
+    const bf16* w0 = p.W + (int64_t)(f0_ok ? f0 : 0) * p.ldb + k0 + t4 * 16;
+    const bf16* w1 = p.W + (int64_t)(f1_ok ? f1 : 0) * p.ldb + k0 + t4 * 16;
+    const bf16* xr0 = xs + g * xs_stride + t4 * 16;
+    const bf16* xr1 = xs + (g + 8) * xs_stride + t4 * 16;
+    const int nchunk = kc / 64;
+    constexpr int kDepth = 4;                      // chunks in flight per thread (4 x 64 B)
+    uint4 wb[kDepth][2][2];
+#pragma unroll
+    for (int d = 0; d < kDepth; ++d) {
+        if (d < nchunk) {
+            wb[d][0][0] = ldg_stream(w0 + d * 64); wb[d][0][1] = ldg_stream(w0 + d * 64 + 8);
+            wb[d][1][0] = ldg_stream(w1 + d * 64); wb[d][1][1] = ldg_stream(w1 + d * 64 + 8);
+        }
+    }
+    // ---- X slab -> smem (rows >= M are zero) while the first weight chunks are in flight
+    for (int i = tid; i < 16 * (p.kc / 8); i += kSkThreads) {
+        const int r = i / (p.kc / 8), c = (i % (p.kc / 8)) * 8;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (r < p.M && c < kc) v = *reinterpret_cast<const uint4*>(p.X + (int64_t)r * p.lda + k0 + c);
+        uint32_t* d = reinterpret_cast<uint32_t*>(xs + r * xs_stride + c);
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+    __syncthreads();
+
+    for (int c0 = 0; c0 < nchunk; c0 += kDepth) {
+#pragma unroll
+        for (int d = 0; d < kDepth; ++d) {
+            const int c = c0 + d;
+            if (c >= nchunk) break;
+            const uint4 a0 = wb[d][0][0], a1 = wb[d][0][1], b0 = wb[d][1][0], b1 = wb[d][1][1];
+            if (c + kDepth < nchunk) {             // refill this slot for chunk c + kDepth
+                wb[d][0][0] = ldg_stream(w0 + (c + kDepth) * 64); wb[d][0][1] = ldg_stream(w0 + (c + kDepth) * 64 + 8);
+                wb[d][1][0] = ldg_stream(w1 + (c + kDepth) * 64); wb[d][1][1] = ldg_stream(w1 + (c + kDepth) * 64 + 8);
+            }
+            const uint32_t wq0[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};   // feature f0: k = t4*16 + 0..15
+            const uint32_t wq1[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            const uint32_t* x0 = reinterpret_cast<const uint32_t*>(xr0 + c * 64);
+            const uint32_t* x1 = reinterpret_cast<const uint32_t*>(xr1 + c * 64);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {          // k16-step j uses physical k = t4*16 + 4j + {0,1 | 2,3}
+                uint32_t af[4] = {x0[2 * j], x1[2 * j], x0[2 * j + 1], x1[2 * j + 1]};
+                mma16816(acc[0], af, wq0[2 * j], wq0[2 * j + 1]);
+                mma16816(acc[1], af, wq1[2 * j], wq1[2 * j + 1]);
+            }
+        }
+    }
+    // ---- partial tile -> smem [16][64]
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+        const int col = warp * 16 + b * 8 + t4 * 2;
+        tile[g * 64 + col] = acc[b][0]; tile[g * 64 + col + 1] = acc[b][1];
+        tile[(g + 8) * 64 + col] = acc[b][2]; tile[(g + 8) * 64 + col + 1] = acc[b][3];
+    }
+    __syncthreads();
+    if (p.splits > 1) {
+        float* mine = p.partials + ((int64_t)tn * p.splits + split) * (16 * 64);
+        for (int i = tid; i < 16 * 64 / 4; i += kSkThreads)
+            reinterpret_cast<float4*>(mine)[i] = reinterpret_cast<const float4*>(tile)[i];
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            const int t = atomicAdd(&p.tickets[tn], 1);
+            s_last = (t == p.splits - 1);
+            if (s_last) p.tickets[tn] = 0;         // self-resetting for the next launch
+        }
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        const float* base = p.partials + (int64_t)tn * p.splits * (16 * 64);
+        for (int i = tid; i < 16 * 64 / 4; i += kSkThreads) {       // fixed split order => deterministic sum
+            float4 s = __ldcg(reinterpret_cast<const float4*>(base) + i);
+            for (int sp = 1; sp < p.splits; ++sp) {
+                const float4 v = __ldcg(reinterpret_cast<const float4*>(base + (int64_t)sp * 16 * 64) + i);
+                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            }
+            reinterpret_cast<float4*>(tile)[i] = s;
+        }
+        __syncthreads();
+    }
+
+    // ---- epilogue on the complete tile: thread -> (row = tid/8, 8 columns at (tid%8)*8)
+    const int r = tid >> 3, cq = (tid & 7) * 8;
+    const int n = n0 + cq;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = tile[r * 64 + cq + j];
+    if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (n + j < p.N) f[j] += __ldg(p.bias + n + j);
+    }
+    const bool row_ok = r < p.M;
+    if constexpr (EPI == SK_QKV) {
+        const QkvFuse& q = p.qf;
+        const int region = n0 / q.D;                       // 64-feature tile == one head of k / v / q, or 64 fc1 columns
+        if (region >= 3) {
+            if (row_ok) {
+                bf16* o = reinterpret_cast<bf16*>(p.out) + (int64_t)r * p.ldc + n;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = __float2bfloat16(gelu_new_f(f[j]));
+            }
+            return;
+        }
+        const int seq = r / q.rows_per_seq, pos = q.pos0 + r % q.rows_per_seq;
+        if (region == 1) {
+            if (row_ok) {
+                const int h = (n0 - q.D) >> 6;
+                bf16* vt = q.vtcache + ((int64_t)seq * q.H + h) * 64 * (int64_t)q.Lmax + pos;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) vt[(int64_t)(cq + j) * q.Lmax] = __float2bfloat16(f[j]);
+            }
+            return;
+        }
+        // k or q: LayerNorm over the 64 columns of the row (8 threads, lanes differing in bits 0..2), then rotary
+        const float* gam = region == 0 ? q.k_gamma : q.q_gamma;
+        const float* bet = region == 0 ? q.k_beta : q.q_beta;
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += f[j];
+        s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4);
+        const float mean = s * (1.f / 64.f);
+        float v = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { f[j] -= mean; v += f[j] * f[j]; }
+        v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 4);
+        const float rstd = rsqrtf(v * (1.f / 64.f) + q.eps);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = f[j] * rstd * __ldg(gam + cq + j) + __ldg(bet + cq + j);
+        // rotate_half pairing (i, i+16) on dims [0,32): column octets 0,1 pair with octets 2,3 (lane xor 2)
+        float pr[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pr[j] = __shfl_xor_sync(0xffffffffu, f[j], 2);
+        if (cq < 32 && row_ok) {
+            const int i0 = cq & 15;                       // frequency index of column cq (emb = cat(freqs, freqs))
+            const float sgn = cq < 16 ? -1.f : 1.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float c = __ldg(q.cos_tab + (int64_t)pos * 32 + i0 + j), sn = __ldg(q.sin_tab + (int64_t)pos * 32 + i0 + j);
+                f[j] = f[j] * c + sgn * pr[j] * sn;
+            }
+        }
+        if (!row_ok) return;
+        if (region == 0) {
+            const int h = n0 >> 6;
+            bf16* kd = q.kcache + (((int64_t)seq * q.H + h) * q.Lmax + pos) * 64 + cq;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) kd[j] = __float2bfloat16(f[j]);
+        } else {
+            bf16* o = reinterpret_cast<bf16*>(p.out) + (int64_t)r * p.ldc + n;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = __float2bfloat16(f[j]);
+        }
+    } else {
+        if (!row_ok) return;
+        if constexpr (EPI == SK_BIAS_BF16) {
+            bf16* o = reinterpret_cast<bf16*>(p.out) + (int64_t)r * p.ldc + n;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (n + j < p.N) o[j] = __float2bfloat16(n + j >= p.gelu_from ? gelu_new_f(f[j]) : f[j]);
+        } else if constexpr (EPI == SK_RESID_F32) {
+            float* o = reinterpret_cast<float*>(p.out) + (int64_t)r * p.ldc + n;
+            const float* rs = p.resid + (int64_t)r * p.ldr + n;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) if (n + j < p.N) o[j] = f[j] + rs[j];
+        } else {
+            float* o = reinterpret_cast<float*>(p.out) + (int64_t)r * p.ldc + n;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) if (n + j < p.N) o[j] = f[j];
+        }
+    }
+}
+
+static float* g_partials = nullptr; static size_t g_partials_cap = 0;
+static int* g_tickets = nullptr; static size_t g_tickets_cap = 0;
+
+int gemm_skinny(const GemmArgs& a, int epi, const QkvFuse* qf, cudaStream_t st) {
+    SHOWO_CHECK(a.M >= 1 && a.M <= 16, "gemm_skinny: M must be in [1,16]");
+    SHOWO_CHECK(a.K % 64 == 0 && a.lda % 8 == 0 && a.ldb % 8 == 0, "gemm_skinny: K must be a multiple of 64, lda/ldb of 8");
+    const int tiles = cdiv(a.N, kSkTileN);
+    // enough CTAs to cover the SMs a few times over, K per split a multiple of 64 and <= 2048 (X slab <= 64 KB of smem)
+    int splits = 1;
+    // at least one full wave of CTAs, X slab <= 64 KB of smem; fewer, longer-streaming CTAs beat many short ones
+    while ((tiles * splits < gemm_num_sms() && (a.K / (splits * 2)) >= 512 && (a.K % (splits * 2 * 64)) == 0) ||
+           a.K / splits > 2048)
+        splits *= 2;
+    SHOWO_CHECK(a.K % (splits * 64) == 0, "gemm_skinny: K not divisible into 64-aligned splits");
+    SkinnyParams p{};
+    p.X = a.A; p.lda = a.lda; p.W = a.B; p.ldb = a.ldb; p.M = a.M; p.N = a.N; p.K = a.K; p.splits = splits; p.kc = a.K / splits;
+    p.out = a.out; p.ldc = a.ldc; p.bias = a.bias; p.resid = a.resid; p.ldr = a.ldr; p.gelu_from = a.gelu_from;
+    if (qf) p.qf = *qf;
+    if (splits > 1) {
+        const size_t need = (size_t)tiles * splits * 16 * 64;
+        if (need > g_partials_cap) {
+            SHOWO_CUDA_OK(cudaStreamSynchronize(st));
+            if (g_partials) cudaFree(g_partials);
+            SHOWO_CUDA_OK(cudaMalloc(&g_partials, need * 4));
+            g_partials_cap = need;
+        }
+        if ((size_t)tiles > g_tickets_cap) {
+            SHOWO_CUDA_OK(cudaStreamSynchronize(st));
+            if (g_tickets) cudaFree(g_tickets);
+            SHOWO_CUDA_OK(cudaMalloc(&g_tickets, (size_t)tiles * 4));
+            SHOWO_CUDA_OK(cudaMemset(g_tickets, 0, (size_t)tiles * 4));
+            g_tickets_cap = tiles;
+        }
+        p.partials = g_partials; p.tickets = g_tickets;
+    }
+    const size_t smem = (size_t)16 * (p.kc + 2) * 2 + 32 + 16 * 64 * 4;
+    dim3 grid(tiles, splits);
+#define SK_LAUNCH(E)                                                                                              \
+    do {                                                                                                          \
+        static bool attr = false;                                                                                 \
+        if (!attr) {                                                                                              \
+            SHOWO_CUDA_OK(cudaFuncSetAttribute(skinny_gemm_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024)); \
+            attr = true;                                                                                          \
+        }                                                                                                         \
+        skinny_gemm_kernel<E><<<grid, kSkThreads, smem, st>>>(p);                                                 \
+    } while (0)
+    switch (epi) {
+        case SK_BIAS_BF16: SK_LAUNCH(SK_BIAS_BF16); break;
+        case SK_RESID_F32: SK_LAUNCH(SK_RESID_F32); break;
+        case SK_BIAS_F32: SK_LAUNCH(SK_BIAS_F32); break;
+        case SK_QKV: SHOWO_CHECK(qf && qf->D % 64 == 0 && qf->pos0 + qf->rows_per_seq <= qf->Lmax, "gemm_skinny: bad qkv fuse args");
+            SK_LAUNCH(SK_QKV); break;
+        default: SHOWO_CHECK(false, "gemm_skinny: bad epilogue");
+    }
+#undef SK_LAUNCH
+    note_launch();
+    SHOWO_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace showo

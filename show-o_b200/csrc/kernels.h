@@ -33,6 +33,8 @@ struct QkvFuse {
     bf16* kcache; bf16* vtcache;
 };
 int gemm_qkv_bf16(const GemmArgs& a, const QkvFuse& f, cudaStream_t st);
+// weight-streaming path for M <= 16 rows (decode); epi: 0 bias->bf16(+gelu), 1 resid+bias->f32, 2 bias->f32, 3 fused qkv (gemv.cu)
+int gemm_skinny(const GemmArgs& a, int epi, const QkvFuse* qf, cudaStream_t st);
 
 // implicit-GEMM convolution on NHWC bf16 (3x3 pad 1, or 1x1), stride 1.  cin multiple of 64, weights [Cout_pad, taps*cin].
 struct ConvArgs {

@@ -1,0 +1,22 @@
+"""Small driver for profiling the MMU decode loop (full-size random weights, B=16, L0=276): used under ncu."""
+import os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import showo_b200
+from showo_b200 import _lib
+import bench
+
+dev = torch.device("cuda", 0)
+lib = _lib.require_gpu()
+model = showo_b200.Showo(False, bench.V, 50295, materialize=False)
+model._make_engine(dev)
+for name, t in bench.gpu_random_weights(torch, dev, seed=0):
+    _lib.check(lib.showo_load_weight(model._engine, name.encode(), _lib.ptr(t), t.numel(), 1), name)
+_lib.check(lib.showo_weights_complete(model._engine), "complete")
+model._streamed = True
+n_new = int(sys.argv[1]) if len(sys.argv) > 1 else 6
+ids = torch.randint(0, 50000, (16, 276), device=dev)
+descs = [(0, 0, 0, 0, 259)] * 16
+for _ in range(2):
+    toks, _ = model.mmu_generate_batched(ids, attention_mask=descs, max_new_tokens=n_new, top_k=1)
+torch.cuda.synchronize()
+print("done", toks.shape)

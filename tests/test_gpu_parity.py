@@ -80,6 +80,34 @@ def test_gemm_tcgen05_against_fp32(lib, dev, Mm, N, K, bn):
     assert (outr - (ref + res)).abs().max().item() < 1e-3
 
 
+@pytest.mark.parametrize("Mm,N,K", [(16, 2048, 10240), (16, 58498, 2048), (3, 1000, 256), (16, 14336, 2048), (1, 64, 64),
+                                    (9, 2048, 2048)])
+def test_skinny_weight_streaming_gemm(lib, dev, Mm, N, K):
+    """decode path (M <= 16, block_n = 0): mma.sync weight streaming with deterministic split-K."""
+    g = torch.Generator(device=dev).manual_seed(Mm + N)
+    A = (torch.randn(Mm, K, device=dev, generator=g) * 0.5).bfloat16()
+    Bw = (torch.randn(N, K, device=dev, generator=g) * 0.05).bfloat16()
+    bias = torch.randn(N, device=dev, generator=g)
+    ref = A.float() @ Bw.float().t() + bias
+    outs = []
+    for _ in range(2):
+        out = torch.full((Mm, N), float("nan"), device=dev)
+        _lib.check(lib.showo_gemm_bf16(_lib.ptr(A), K, _lib.ptr(Bw), K, Mm, N, K, _lib.ptr(out), N, _lib.ptr(bias), None, 0, N, 2, 0, S()))
+        outs.append(out)
+    assert (outs[0] - ref).abs().max().item() < 2e-3
+    assert torch.equal(outs[0], outs[1])                      # split-K partials are summed in a fixed order
+    gf = (N // 2) // 64 * 64
+    out16 = torch.zeros(Mm, N, device=dev, dtype=torch.bfloat16)
+    _lib.check(lib.showo_gemm_bf16(_lib.ptr(A), K, _lib.ptr(Bw), K, Mm, N, K, _lib.ptr(out16), N, _lib.ptr(bias), None, 0, gf, 0, 0, S()))
+    r16 = ref.clone()
+    r16[:, gf:] = O.gelu_new(ref[:, gf:])
+    assert ((out16.float() - r16).abs() <= r16.abs() * 2 ** -7 + 1e-2).all()
+    res = torch.randn(Mm, N, device=dev, generator=g)
+    outr = res.clone()
+    _lib.check(lib.showo_gemm_bf16(_lib.ptr(A), K, _lib.ptr(Bw), K, Mm, N, K, _lib.ptr(outr), N, _lib.ptr(bias), _lib.ptr(outr), N, N, 1, 0, S()))
+    assert (outr - (ref + res)).abs().max().item() < 2e-3
+
+
 def test_gemm_linearity_and_strided_operands(lib, dev):
     """size-independent properties at full size: C(A1 + A2) = C(A1) + C(A2) for exactly representable sums; A may be
     a strided column block of a wider buffer (the engine reads attn|act out of the k|v|q|act buffer)."""
