@@ -62,6 +62,8 @@ constexpr float kNegBig = -1.0e30f;
 __global__ void __launch_bounds__(128) omni_attention_kernel(AttnArgs a) {
     __shared__ __align__(16) bf16 Ks[2][kTileK][kPad];
     __shared__ __align__(16) bf16 Vs[2][64][kPad];
+    pdl_trigger();
+    pdl_wait();
 
     const int seq = blockIdx.z, h = blockIdx.y;
     const int q0 = blockIdx.x * 64;
@@ -227,7 +229,7 @@ int omni_attention(const AttnArgs& a, cudaStream_t st) {
     SHOWO_CHECK(a.Lmax % 64 == 0, "attention: Lmax must be a multiple of 64");
     SHOWO_CHECK(a.n_keys <= a.Lmax, "attention: n_keys exceeds the cache length");
     dim3 grid(cdiv(a.rows_per_seq, 64), a.H, a.n_seq);
-    omni_attention_kernel<<<grid, 128, 0, st>>>(a);
+    SHOWO_CUDA_OK(launch_kernel(omni_attention_kernel, grid, dim3(128), 0, st, 1, a));
     note_launch();
     SHOWO_CUDA_OK(cudaGetLastError());
     return 0;

@@ -7,6 +7,7 @@
 #include <stdio.h>
 
 #include <string>
+#include <utility>
 
 namespace showo {
 
@@ -40,6 +41,35 @@ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 #ifdef __CUDACC__
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// Hot-loop kernels are launched with programmaticStreamSerialization: each kernel signals `pdl_trigger()` as soon as it is
+// running and calls `pdl_wait()` before it touches anything a predecessor wrote.  The next kernel's CTAs can then be
+// scheduled (and run their prologue: barrier init, TMEM alloc, descriptor prefetch) while the predecessor drains, which
+// hides the launch + drain gap between the ~2100 dependent kernels of one t2i_generate.  Set SHOWO_PDL=0 to disable.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                        int cluster_x, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    int n = 0;
+    if (cluster_x > 1) {
+        at[n].id = cudaLaunchAttributeClusterDimension;
+        at[n].val.clusterDim.x = cluster_x; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    if (pdl_enabled()) {
+        at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    cfg.attrs = at; cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 // ---------------------------------------------------------------- device helpers
 __host__ __device__ __forceinline__ int cdiv_dev(int a, int b) { return (a + b - 1) / b; }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -14,6 +14,8 @@ __global__ void __launch_bounds__(256) layernorm_bf16_kernel(const float* __rest
                                                              const float* __restrict__ beta, float eps,
                                                              bf16* __restrict__ out, int n_rows_out, int D,
                                                              int rows_out_per_seq, int rows_in_per_seq, int row_off) {
+    pdl_trigger();
+    pdl_wait();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= n_rows_out) return;
@@ -61,11 +63,11 @@ int layernorm_bf16(const float* x, const float* gamma, const float* beta, float 
     const int wpb = 8;
     const int grid = cdiv(n_rows_out, wpb);
     if (D <= 512)
-        layernorm_bf16_kernel<4><<<grid, wpb * 32, 0, st>>>(x, gamma, beta, eps, out, n_rows_out, D, rows_out_per_seq,
-                                                            rows_in_per_seq, row_off);
+        SHOWO_CUDA_OK(launch_kernel(layernorm_bf16_kernel<4>, dim3(grid), dim3(wpb * 32), 0, st, 1, x, gamma, beta, eps, out, n_rows_out, D,
+                                    rows_out_per_seq, rows_in_per_seq, row_off));
     else
-        layernorm_bf16_kernel<16><<<grid, wpb * 32, 0, st>>>(x, gamma, beta, eps, out, n_rows_out, D, rows_out_per_seq,
-                                                             rows_in_per_seq, row_off);
+        SHOWO_CUDA_OK(launch_kernel(layernorm_bf16_kernel<16>, dim3(grid), dim3(wpb * 32), 0, st, 1, x, gamma, beta, eps, out, n_rows_out, D,
+                                    rows_out_per_seq, rows_in_per_seq, row_off));
     note_launch();
     SHOWO_CUDA_OK(cudaGetLastError());
     return 0;

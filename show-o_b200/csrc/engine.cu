@@ -23,6 +23,11 @@ static thread_local std::string g_last_error;
 void set_last_error(const std::string& msg) { g_last_error = msg; }
 static std::atomic<int64_t> g_launches{0};
 void note_launch(int n) { g_launches += n; }
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SHOWO_PDL"); v = (e && atoi(e) == 0) ? 0 : 1; }
+    return v == 1;
+}
 int64_t launches_total() { return g_launches.load(); }
 const char* last_error_cstr() { return g_last_error.c_str(); }
 

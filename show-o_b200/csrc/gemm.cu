@@ -125,17 +125,11 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams
         // num_tiles counts work units (CL m-tiles each); one cluster per unit, as many clusters as fit the SMs
         const int max_clusters = gemm_num_sms() / CL;
         const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(clusters * CL); cfg.blockDim = dim3(Cfg::kThreads); cfg.dynamicSmemBytes = Cfg::kSmemBytes; cfg.stream = st;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        SHOWO_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ma, mb, p));
+        SHOWO_CUDA_OK(launch_kernel(kern, dim3(clusters * CL), dim3(Cfg::kThreads), Cfg::kSmemBytes, st, CL, ma, mb, p));
         note_launch();
         return 0;
     }
-    kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(ma, mb, p);
+    SHOWO_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, st, 1, ma, mb, p));
     note_launch();
     SHOWO_CUDA_OK(cudaGetLastError());
     return 0;

@@ -129,6 +129,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if constexpr (CL > 1) cluster_sync_all();      // peer barriers must be initialised before any multicast lands
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();      // the next kernel may start scheduling its CTAs ...
+    pdl_wait();         // ... and this one must not read what its predecessor wrote before that predecessor has completed
 
     if (warp == 0) {
         // ===================================================== TMA producer
