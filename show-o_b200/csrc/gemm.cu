@@ -81,6 +81,11 @@ static int make_map(CUtensorMap* out, const void* ptr, uint32_t rank, const uint
 }
 
 // A/B switch while tuning: SHOWO_GEMM_BK=32 selects 9 x 24 KB stages (64B swizzle) instead of 4 x 48 KB (128B swizzle)
+static int gemm_bk() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SHOWO_GEMM_BK"); v = e ? atoi(e) : 128; }   // default: 3 x 64 KB stages, 8 MMAs per stage
+    return v;
+}
 static bool gemm_bk32() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("SHOWO_GEMM_BK"); v = (e && atoi(e) == 32) ? 1 : 0; }
@@ -139,11 +144,12 @@ template <int BN, int BK = 64, int CL = 1, int CG = 1>
 static int gemm_bn(const GemmArgs& a, GemmEpi epi, cudaStream_t st) {
     CUtensorMap ma, mb;
     uint64_t da[2] = {(uint64_t)a.K, (uint64_t)a.M}, sa[1] = {(uint64_t)a.lda * 2};
-    uint32_t ba[2] = {BK, 128};
-    SHOWO_TRY(make_map(&ma, a.A, 2, da, sa, ba, BK * 2));
+    constexpr int kBox = BK > 64 ? 64 : BK;       // TMA boxes are one 128B swizzle atom (64 bf16) wide at most
+    uint32_t ba[2] = {kBox, 128};
+    SHOWO_TRY(make_map(&ma, a.A, 2, da, sa, ba, kBox * 2));
     uint64_t db[2] = {(uint64_t)a.K, (uint64_t)a.N}, sb[1] = {(uint64_t)a.ldb * 2};
-    uint32_t bb[2] = {BK, (uint32_t)(BN / CL)};
-    SHOWO_TRY(make_map(&mb, a.B, 2, db, sb, bb, BK * 2));
+    uint32_t bb[2] = {kBox, (uint32_t)(BN / CL)};
+    SHOWO_TRY(make_map(&mb, a.B, 2, db, sb, bb, kBox * 2));
     GemmParams p{};
     p.M = a.M; p.N = a.N; p.K = a.K;
     p.out = a.out; p.ldc = a.ldc; p.bias = a.bias; p.resid = a.resid; p.ldr = a.ldr; p.gelu_from = a.gelu_from;
@@ -169,6 +175,7 @@ int gemm_bf16(const GemmArgs& a, GemmEpi epi, cudaStream_t st) {
         else if (a.N >= 128) bn = 128;
         else bn = 64;
     }
+    if (bn == 256 && gemm_cta_group() == 2 && a.M > 128 && gemm_bk() == 128 && a.K % 128 == 0) return gemm_bn<256, 128, 2, 2>(a, epi, st);
     if (bn == 256 && gemm_cta_group() == 2 && a.M > 128) return gemm_bn<256, 64, 2, 2>(a, epi, st);
     if (bn == 256 && gemm_cluster() == 2 && a.M > 128) return gemm_bn<256, 64, 2>(a, epi, st);
     if (bn == 256 && gemm_bk32()) return gemm_bn<256, 32>(a, epi, st);
@@ -182,11 +189,12 @@ template <int BN, int BK = 64, int CL = 1, int CG = 1>
 static int gemm_qkv_bn(const GemmArgs& a, const QkvFuse& f, cudaStream_t st) {
     CUtensorMap ma, mb;
     uint64_t da[2] = {(uint64_t)a.K, (uint64_t)a.M}, sa[1] = {(uint64_t)a.lda * 2};
-    uint32_t ba[2] = {BK, 128};
-    SHOWO_TRY(make_map(&ma, a.A, 2, da, sa, ba, BK * 2));
+    constexpr int kBox = BK > 64 ? 64 : BK;       // TMA boxes are one 128B swizzle atom (64 bf16) wide at most
+    uint32_t ba[2] = {kBox, 128};
+    SHOWO_TRY(make_map(&ma, a.A, 2, da, sa, ba, kBox * 2));
     uint64_t db[2] = {(uint64_t)a.K, (uint64_t)a.N}, sb[1] = {(uint64_t)a.ldb * 2};
-    uint32_t bb[2] = {BK, (uint32_t)(BN / CL)};
-    SHOWO_TRY(make_map(&mb, a.B, 2, db, sb, bb, BK * 2));
+    uint32_t bb[2] = {kBox, (uint32_t)(BN / CL)};
+    SHOWO_TRY(make_map(&mb, a.B, 2, db, sb, bb, kBox * 2));
     GemmParams p{};
     p.M = a.M; p.N = a.N; p.K = a.K; p.out = a.out; p.ldc = a.ldc; p.bias = a.bias; p.gelu_from = 3 * f.D;
     p.qkv_D = f.D; p.qkv_H = f.H; p.qkv_rows_per_seq = f.rows_per_seq; p.qkv_pos0 = f.pos0; p.qkv_Lmax = f.Lmax;
@@ -202,6 +210,7 @@ int gemm_qkv_bf16(const GemmArgs& a, const QkvFuse& f, cudaStream_t st) {
     SHOWO_CHECK(a.bias != nullptr && (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0, "gemm_qkv: bias must be 16-byte aligned");
     SHOWO_CHECK(f.D % 64 == 0 && a.N % 64 == 0 && f.H * 64 == f.D, "gemm_qkv: D must be H*64 and N a multiple of 64");
     SHOWO_CHECK(f.pos0 + f.rows_per_seq <= f.Lmax && a.M % f.rows_per_seq == 0, "gemm_qkv: rows / positions exceed the KV cache");
+    if (f.D % 256 == 0 && a.M > 256 && gemm_cta_group() == 2 && gemm_bk() == 128 && a.K % 128 == 0) return gemm_qkv_bn<256, 128, 2, 2>(a, f, st);
     if (f.D % 256 == 0 && a.M > 256 && gemm_cta_group() == 2) return gemm_qkv_bn<256, 64, 2, 2>(a, f, st);
     if (f.D % 256 == 0 && a.M > 256 && gemm_cluster() == 2) return gemm_qkv_bn<256, 64, 2>(a, f, st);
     if (f.D % 256 == 0 && a.M > 256 && gemm_bk32()) return gemm_qkv_bn<256, 32>(a, f, st);

@@ -60,7 +60,7 @@ struct GemmCfg {
     static constexpr int kAB = BM * BK * 2;                 // 16 KB
     static constexpr int kBB = BN * BK * 2 / CG;          // cta_group::2: each CTA of the pair holds half of the B tile
     static constexpr int kStageBytes = kAB + kBB;
-    static constexpr int kStages = (CG == 2) ? 6 : (BK_ == 64) ? ((BN == 256) ? 4 : (BN == 128 ? 6 : 8)) : ((BN == 256) ? 9 : (BN == 128 ? 13 : 16));
+    static constexpr int kStages = (CG == 2) ? (BK_ == 128 ? 3 : 6) : (BK_ == 64) ? ((BN == 256) ? 4 : (BN == 128 ? 6 : 8)) : ((BN == 256) ? 9 : (BN == 128 ? 13 : 16));
     static constexpr int kTmemCols = 2 * BN;                // 2 accumulator stages (power of two for BN in {64,128,256})
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 512 /*barriers*/;
     static constexpr int kThreads = 192;
@@ -71,7 +71,8 @@ __global__ void __launch_bounds__(192, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const GemmParams p) {
     using Cfg = GemmCfg<BN, BK_, CG>;
-    static_assert(CG == 1 || (CG == 2 && CL == 2 && BN == 256 && BK_ == 64), "cta_group::2 needs a CTA pair");
+    static_assert(CG == 1 || (CG == 2 && CL == 2 && BN == 256 && (BK_ == 64 || BK_ == 128)), "cta_group::2 needs a CTA pair");
+    static_assert(BK_ != 128 || CG == 2, "BK = 128 (two 64-wide sub-boxes per stage) is only wired for the CTA-pair path");
     constexpr int BM = Cfg::BM, BK = Cfg::BK, kStages = Cfg::kStages;
 
     extern __shared__ uint8_t smem_raw[];
@@ -152,8 +153,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     if constexpr (CG == 2) {
                         // both CTAs load their A tile and their half of B; all bytes are credited to the LEADER barrier
                         if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
-                        tma_load_2d_cg2(smem_a + stage * Cfg::kAB, &tmap_a, &full_bar[stage], kb * BK, tm * BM);
-                        tma_load_2d_cg2(smem_b + stage * Cfg::kBB, &tmap_b, &full_bar[stage], kb * BK, tn * BN + crank * (BN / 2));
+#pragma unroll
+                        for (int h = 0; h < BK / 64; ++h) {      // a stage = BK/64 sub-tiles of 64 k (one 128B swizzle atom wide)
+                            tma_load_2d_cg2(smem_a + stage * Cfg::kAB + h * (BM * 128), &tmap_a, &full_bar[stage], kb * BK + h * 64, tm * BM);
+                            tma_load_2d_cg2(smem_b + stage * Cfg::kBB + h * ((BN / 2) * 128), &tmap_b, &full_bar[stage], kb * BK + h * 64,
+                                            tn * BN + crank * (BN / 2));
+                        }
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
                         continue;
                     }
@@ -202,8 +207,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::kBB);
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
-                        const uint64_t da = umma_desc_kmajor<BK * 2>(a_addr + k * 32);
-                        const uint64_t db = umma_desc_kmajor<BK * 2>(b_addr + k * 32);
+                        constexpr int kRowB = (BK >= 64) ? 128 : BK * 2;            // bytes per smem row (swizzle width)
+                        const uint64_t da = umma_desc_kmajor<kRowB>(a_addr + (k >> 2) * (BM * 128) + (k & 3) * 32);
+                        const uint64_t db = umma_desc_kmajor<kRowB>(b_addr + (k >> 2) * ((BN / CG) * 128) + (k & 3) * 32);
                         if constexpr (CG == 2) umma_bf16_cg2(d_tmem, da, db, idesc, (kb | k) != 0);
                         else umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
                     }
