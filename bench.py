@@ -48,6 +48,15 @@ def measured_peaks():
     return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
 
 
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/r1_traffic.json)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["gemm_tcgen05_kernel"]
+        return {k: {"dram_bytes": v["dram_bytes"], "algorithmic_bytes": v["algorithmic_bytes"]} for k, v in t.items()}
+    except Exception:
+        return None
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi style clock / throttle-reason sampling during the timed region (pynvml)."""
 
@@ -133,13 +142,31 @@ def gpu_random_weights(torch, dev, seed=0):
     yield "showo.lm_head.bias", torch.zeros(V, device=dev)
 
 
+def gpu_random_magvit_weights(torch, dev, seed=1):
+    """Random-init MAGVIT-v2 state_dict (nn.Conv2d default: U(+-1/sqrt(fan_in)); GroupNorm 1/0) generated on the device."""
+    from showo_b200.magvit_model import _param_shapes
+    g = torch.Generator(device=dev).manual_seed(seed)
+    W = {}
+    shapes = _param_shapes()
+    for name, shp in shapes.items():
+        if len(shp) == 4:
+            bound = 1.0 / math.sqrt(shp[1] * shp[2] * shp[3])
+            W[name] = (torch.rand(shp, device=dev, generator=g) * 2 - 1) * bound
+        elif ".norm" in name:
+            W[name] = torch.ones(shp, device=dev) if name.endswith("weight") else torch.zeros(shp, device=dev)
+        else:
+            ws = shapes[name[:-5] + ".weight"]
+            bound = 1.0 / math.sqrt(ws[1] * ws[2] * ws[3])
+            W[name] = (torch.rand(shp, device=dev, generator=g) * 2 - 1) * bound
+    return W
+
+
 # ======================================================================================================= ours
 def run_ours(args):
     import torch
     import torch.distributed as dist
     import showo_b200
     from showo_b200 import _lib
-    from oracle import magvit_oracle as MO      # only the deterministic synthetic-weight generator is used here
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -158,7 +185,7 @@ def run_ours(args):
     _lib.check(lib.showo_weights_complete(model._engine), "weights_complete")
     model._streamed = True
     vq = showo_b200.MAGVITv2(materialize=False)
-    vq.load_weights(MO.make_magvit_weights(1), device=dev)
+    vq.load_weights(gpu_random_magvit_weights(torch, dev, seed=1), device=dev)
 
     cfg = t2i_config()
     cond_h, unc_h, descs = synth_prompts(torch, B_PER_GPU, seed=1234 + rank)
@@ -261,7 +288,7 @@ def run_ours(args):
             "gpu_launches": int(launches * args.steps),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": round(kern_tflops, 1), "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
-                         "frac": round(kern_tflops / peaks["bf16_burst"], 4), "traffic": None,
+                         "frac": round(kern_tflops / peaks["bf16_burst"], 4), "traffic": ncu_traffic(),
                          "kernel": "gemm_tcgen05_kernel (FLOP-weighted over the 24x2 layer GEMMs + image-vocab head of one "
                                    "denoise step, each shape timed alone with CUDA events)", "peak_source": peaks["source"],
                          "per_shape": per_shape},
