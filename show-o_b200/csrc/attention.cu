@@ -228,6 +228,7 @@ int omni_attention(const AttnArgs& a, cudaStream_t st) {
     if (a.n_seq == 0 || a.rows_per_seq == 0) return 0;
     SHOWO_CHECK(a.Lmax % 64 == 0, "attention: Lmax must be a multiple of 64");
     SHOWO_CHECK(a.n_keys <= a.Lmax, "attention: n_keys exceeds the cache length");
+    if (attention_tc_supported(a)) return omni_attention_tc(a, st);      // whole score row fits in TMEM: tcgen05 path
     dim3 grid(cdiv(a.rows_per_seq, 64), a.H, a.n_seq);
     SHOWO_CUDA_OK(launch_kernel(omni_attention_kernel, grid, dim3(128), 0, st, 1, a));
     note_launch();

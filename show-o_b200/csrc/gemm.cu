@@ -106,6 +106,14 @@ static int gemm_cta_group() {
     return v;
 }
 
+// 2-D bf16 tensor map with 128B swizzle for other TMA users (attention_tc.cu): dims = {inner, rows}, row stride in bytes
+int make_tmap_2d(void* out_cutensormap, const void* ptr, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes,
+                 uint32_t box_inner, uint32_t box_rows) {
+    uint64_t d[2] = {inner, rows}, s[1] = {row_stride_bytes};
+    uint32_t b[2] = {box_inner, box_rows};
+    return make_map(reinterpret_cast<CUtensorMap*>(out_cutensormap), ptr, 2, d, s, b, 128);
+}
+
 int gemm_num_sms() {
     static int n = 0;
     if (n == 0) {

@@ -49,6 +49,8 @@ struct ConvArgs {
 };
 int conv_nhwc_bf16(const ConvArgs& a, cudaStream_t st);
 int gemm_num_sms();
+int make_tmap_2d(void* out_cutensormap, const void* ptr, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes,
+                 uint32_t box_inner, uint32_t box_rows);
 
 // ------------------------------------------------------------------ elementwise / norm (elementwise.cu)
 // out[r, :] = bf16(LN(x[map(r), :]))   with map(r) = (r / rows_out) * rows_in + row_off + r % rows_out
@@ -86,6 +88,9 @@ struct AttnArgs {
     float scale;                         // 1/sqrt(head_dim)
 };
 int omni_attention(const AttnArgs& a, cudaStream_t st);
+// tcgen05/TMEM/TMA variant for n_keys <= 448 (attention_tc.cu); omni_attention() dispatches to it when supported
+bool attention_tc_supported(const AttnArgs& a);
+int omni_attention_tc(const AttnArgs& a, cudaStream_t st);
 // single-query (decode) variant: one query row per sequence at position n_keys-1
 int omni_attention_decode(const AttnArgs& a, cudaStream_t st);
 
