@@ -35,6 +35,17 @@ __global__ void vec_add_kernel(const float* a, const float* b, float* o, int n) 
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) o[i] = a[i] + b[i];
 }
+// unpack the fused greedy head's per-row key -> token id; publish it (tok for the next embedding gather, out[b*stride]) and
+// reset the key for the next step
+__global__ void mmu_finish_token_kernel(unsigned long long* keys, int B, int64_t* tok, int64_t* out, int out_stride) {
+    const int b = threadIdx.x;
+    if (b >= B) return;
+    const unsigned long long k = keys[b];
+    const int64_t id = (int64_t)(0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull));
+    tok[b] = id;
+    out[(int64_t)b * out_stride] = id;
+    keys[b] = 0ull;
+}
 __global__ void mmu_lengths_kernel(const int64_t* toks, int max_new, int64_t eot, int32_t* lens) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     int n = max_new;
@@ -91,6 +102,7 @@ struct showo_engine {
     showo_seq_mask_t* d_masks = nullptr;
     float* logits_ws = nullptr; float* conf_ws = nullptr; int* sampled_ws = nullptr;
     int64_t* tok_ws = nullptr; int64_t tok_ws_cap = 0;
+    unsigned long long* argmax_keys = nullptr;            // [16] packed (logit, ~index) maxima of the fused greedy head
     int64_t launches_last = 0;
 };
 
@@ -143,13 +155,17 @@ static int run_layers(showo_engine* e, int n_seq, int rows_per_seq, int pos0, in
     const int D = e->D, F = e->F;
     for (int l = 0; l < e->NL; ++l) {
         const LayerW& w = e->layers[l];
-        SHOWO_TRY(layernorm_bf16(e->x, w.ln_g, w.ln_b, e->cfg.ln_eps, e->xh, M, D, M, M, 0, st));
+        // The skinny GEMM can normalise its own 16-row slab (GemmArgs::ln_x), but measured slower than the stand-alone
+        // LayerNorm launch (224 CTAs each re-reading 16 x 8 KB three times: 2.81 vs 2.14 ms per decode step) -> off.
+        const bool fuse_ln = false;
+        if (!fuse_ln) SHOWO_TRY(layernorm_bf16(e->x, w.ln_g, w.ln_b, e->cfg.ln_eps, e->xh, M, D, M, M, 0, st));
         bf16* kc = e->kcache + (size_t)l * layer_cache_stride(e);
         bf16* vc = e->vtcache + (size_t)l * layer_cache_stride(e);
         // GEMM1 + (q/k LayerNorm, partial rotary, K / V^T cache scatter, gelu_new) in one kernel
         GemmArgs g1{};
         g1.A = e->xh; g1.lda = D; g1.B = w.w1; g1.ldb = D; g1.M = M; g1.N = e->W1N; g1.K = D;
         g1.out = e->buf; g1.ldc = e->W1N; g1.bias = w.b1;
+        if (fuse_ln) { g1.ln_x = e->x; g1.ln_g = w.ln_g; g1.ln_b = w.ln_b; g1.ln_eps = e->cfg.ln_eps; }
         QkvFuse qf{};
         qf.D = D; qf.H = e->H; qf.rows_per_seq = rows_per_seq; qf.pos0 = pos0; qf.Lmax = e->cap_L;
         qf.q_gamma = w.qg; qf.q_beta = w.qb; qf.k_gamma = w.kg; qf.k_beta = w.kb; qf.eps = e->cfg.ln_eps;
@@ -257,7 +273,7 @@ int showo_engine_destroy(showo_engine_t* e) {
     }
     dev_free(e->cos_tab); dev_free(e->sin_tab); dev_free(e->stage);
     dev_free(e->x); dev_free(e->xh); dev_free(e->buf); dev_free(e->kcache); dev_free(e->vtcache); dev_free(e->d_masks);
-    dev_free(e->logits_ws); dev_free(e->conf_ws); dev_free(e->sampled_ws); dev_free(e->tok_ws);
+    dev_free(e->logits_ws); dev_free(e->conf_ws); dev_free(e->sampled_ws); dev_free(e->tok_ws); dev_free(e->argmax_keys);
     delete e;
     return 0;
 }
@@ -539,13 +555,34 @@ int showo_mmu_generate(showo_engine_t* e, const int64_t* ids_dev, const float* e
     GemmArgs g{};
     g.A = e->xh; g.lda = D; g.B = e->head_w; g.ldb = D; g.M = B; g.N = V; g.K = D;
     g.out = e->logits_ws; g.ldc = V; g.bias = e->head_b;
-    SHOWO_TRY(gemm_bf16(g, GEMM_BIAS_F32, st));
     // token t of row b lives at out_tokens[b*max_new + t]; argmax writes a [B] vector -> strided copy via tok_ws
     if (e->tok_ws_cap < B) {
         dev_free(e->tok_ws);
         SHOWO_TRY(dev_alloc(&e->tok_ws, (size_t)B));
         e->tok_ws_cap = B;
     }
+    if (B <= 16 && D % 64 == 0) {
+        // decode fast path: greedy pick fused into the head GEMM (no logits tensor, no argmax pass), final LayerNorm fused
+        // into the head GEMM's input staging, per-layer LayerNorm fused into the projection GEMM (run_layers, decode)
+        if (!e->argmax_keys) {
+            SHOWO_TRY(dev_alloc(&e->argmax_keys, (size_t)16));
+            SHOWO_CUDA_OK(cudaMemsetAsync(e->argmax_keys, 0, 16 * 8, st));
+        }
+        GemmArgs ga = g;
+        ga.out = nullptr; ga.argmax_keys = e->argmax_keys;
+        SHOWO_TRY(gemm_skinny(ga, 4 /*SK_ARGMAX*/, nullptr, st));                      // prefill: xh already holds LN(last row)
+        for (int t = 0; t < max_new_tokens; ++t) {
+            mmu_finish_token_kernel<<<1, 32, 0, st>>>(e->argmax_keys, B, e->tok_ws, out_tokens_dev + t, max_new_tokens);
+            SHOWO_CUDA_OK(cudaGetLastError());
+            note_launch();
+            if (t == max_new_tokens - 1) break;
+            SHOWO_TRY(embed_gather(e->tok_ws, 1, 0, e->embed, e->x, B, 1, D, V, st));
+            SHOWO_TRY(run_layers(e, B, 1, L0 + t, L0 + t + 1, true, st));
+            SHOWO_TRY(layernorm_bf16(e->x, e->fln_g, e->fln_b, e->cfg.ln_eps, e->xh, B, D, B, B, 0, st));
+            SHOWO_TRY(gemm_skinny(ga, 4 /*SK_ARGMAX*/, nullptr, st));
+        }
+    } else {
+    SHOWO_TRY(gemm_bf16(g, GEMM_BIAS_F32, st));
     for (int t = 0; t < max_new_tokens; ++t) {
         SHOWO_TRY(argmax_rows(e->logits_ws, V, B, V, e->tok_ws, st));
         SHOWO_CUDA_OK(cudaMemcpy2DAsync(out_tokens_dev + t, (size_t)max_new_tokens * 8, e->tok_ws, 8, 8, B,
@@ -556,6 +593,7 @@ int showo_mmu_generate(showo_engine_t* e, const int64_t* ids_dev, const float* e
         SHOWO_TRY(run_layers(e, B, 1, L0 + t, L0 + t + 1, true, st));
         SHOWO_TRY(layernorm_bf16(e->x, e->fln_g, e->fln_b, e->cfg.ln_eps, e->xh, B, D, B, B, 0, st));
         SHOWO_TRY(gemm_bf16(g, GEMM_BIAS_F32, st));
+    }
     }
     if (out_lengths_dev) {
         mmu_lengths_kernel<<<1, B, 0, st>>>(out_tokens_dev, max_new_tokens, eot_token, out_lengths_dev);

@@ -19,7 +19,7 @@
 
 namespace showo {
 
-enum { SK_BIAS_BF16 = 0, SK_RESID_F32 = 1, SK_BIAS_F32 = 2, SK_QKV = 3 };
+enum { SK_BIAS_BF16 = 0, SK_RESID_F32 = 1, SK_BIAS_F32 = 2, SK_QKV = 3, SK_ARGMAX = 4 };
 
 struct SkinnyParams {
     const bf16* X; int64_t lda; const bf16* W; int64_t ldb;
@@ -27,6 +27,9 @@ struct SkinnyParams {
     void* out; int64_t ldc; const float* bias; const float* resid; int64_t ldr; int gelu_from;
     float* partials; int* tickets;
     QkvFuse qf;
+    // optional fused input LayerNorm (splits == 1, K == row width): X is ignored, the slab is LN(ln_x) computed per CTA
+    const float* ln_x; const float* ln_g; const float* ln_b; float ln_eps;
+    unsigned long long* argmax_keys;     // SK_ARGMAX: per-row packed (orderable logit, ~index) maxima, atomicMax'ed
 };
 
 __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -78,6 +81,38 @@ __global__ void __launch_bounds__(kSkThreads) skinny_gemm_kernel(SkinnyParams p)
         }
     }
     // ---- X slab -> smem (rows >= M are zero) while the first weight chunks are in flight
+    if (p.ln_x != nullptr) {
+        // fused LayerNorm of the fp32 residual rows (phi.py:776 / :1065): 8 threads per row, two passes over the L2-resident row
+        const int r = tid >> 3, sub = tid & 7;
+        const float* xr = p.ln_x + (int64_t)r * p.K;
+        const bool rv = r < p.M;                 // rows >= M run the same (predicated) code: the shuffles stay convergent
+        float s = 0.f;
+        for (int c = sub * 4; c < p.K; c += 32) {
+            const float4 v = rv ? *reinterpret_cast<const float4*>(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            s += (v.x + v.y) + (v.z + v.w);
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4);
+        const float mean = s / (float)p.K;
+        float q = 0.f;
+        for (int c = sub * 4; c < p.K; c += 32) {
+            const float4 v = rv ? *reinterpret_cast<const float4*>(xr + c) : make_float4(mean, mean, mean, mean);
+            const float a0 = v.x - mean, a1 = v.y - mean, a2 = v.z - mean, a3 = v.w - mean;
+            q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+        }
+        q += __shfl_xor_sync(0xffffffffu, q, 1); q += __shfl_xor_sync(0xffffffffu, q, 2); q += __shfl_xor_sync(0xffffffffu, q, 4);
+        const float rstd = rsqrtf(q / (float)p.K + p.ln_eps);
+        for (int c = sub * 4; c < p.K; c += 32) {
+            uint32_t lo = 0u, hi = 0u;
+            if (rv) {
+                const float4 v = *reinterpret_cast<const float4*>(xr + c);
+                const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.ln_g + c)), b4 = __ldg(reinterpret_cast<const float4*>(p.ln_b + c));
+                lo = pack_bf16((v.x - mean) * rstd * g4.x + b4.x, (v.y - mean) * rstd * g4.y + b4.y);
+                hi = pack_bf16((v.z - mean) * rstd * g4.z + b4.z, (v.w - mean) * rstd * g4.w + b4.w);
+            }
+            uint32_t* d = reinterpret_cast<uint32_t*>(xs + r * xs_stride + c);
+            d[0] = lo; d[1] = hi;
+        }
+    } else
     for (int i = tid; i < 16 * (p.kc / 8); i += kSkThreads) {
         const int r = i / (p.kc / 8), c = (i % (p.kc / 8)) * 8;
         uint4 v = make_uint4(0, 0, 0, 0);
@@ -215,6 +250,25 @@ __global__ void __launch_bounds__(kSkThreads) skinny_gemm_kernel(SkinnyParams p)
             for (int j = 0; j < 8; ++j) o[j] = __float2bfloat16(f[j]);
         }
     } else {
+        if constexpr (EPI == SK_ARGMAX) {
+            // greedy next token without materialising the logits: per-row max of this 64-column tile, then one atomicMax of
+            // a packed key (order-preserving float bits << 32 | ~index: ties resolve to the smallest index, like argmax)
+            float bv = -3.0e38f; int bi = 0x7fffffff;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) if (n + j < p.N && f[j] > bv) { bv = f[j]; bi = n + j; }
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            if (row_ok && (tid & 7) == 0 && bi != 0x7fffffff) {
+                const uint32_t fb = __float_as_uint(bv);
+                const uint32_t ord = (fb & 0x80000000u) ? ~fb : (fb | 0x80000000u);
+                atomicMax(p.argmax_keys + r, ((unsigned long long)ord << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)bi));
+            }
+            return;
+        }
         if (!row_ok) return;
         if constexpr (EPI == SK_BIAS_BF16) {
             bf16* o = reinterpret_cast<bf16*>(p.out) + (int64_t)r * p.ldc + n;
@@ -252,6 +306,9 @@ int gemm_skinny(const GemmArgs& a, int epi, const QkvFuse* qf, cudaStream_t st) 
     p.X = a.A; p.lda = a.lda; p.W = a.B; p.ldb = a.ldb; p.M = a.M; p.N = a.N; p.K = a.K; p.splits = splits; p.kc = a.K / splits;
     p.out = a.out; p.ldc = a.ldc; p.bias = a.bias; p.resid = a.resid; p.ldr = a.ldr; p.gelu_from = a.gelu_from;
     if (qf) p.qf = *qf;
+    p.ln_x = a.ln_x; p.ln_g = a.ln_g; p.ln_b = a.ln_b; p.ln_eps = a.ln_eps; p.argmax_keys = a.argmax_keys;
+    if (a.ln_x) SHOWO_CHECK(splits == 1 && a.K % 32 == 0, "gemm_skinny: fused LayerNorm needs the whole row in one split");
+    if (epi == SK_ARGMAX) SHOWO_CHECK(a.argmax_keys != nullptr, "gemm_skinny: argmax epilogue needs a key buffer");
     if (splits > 1) {
         const size_t need = (size_t)tiles * splits * 16 * 64;
         if (need > g_partials_cap) {
@@ -284,6 +341,7 @@ int gemm_skinny(const GemmArgs& a, int epi, const QkvFuse* qf, cudaStream_t st) 
         case SK_BIAS_BF16: SK_LAUNCH(SK_BIAS_BF16); break;
         case SK_RESID_F32: SK_LAUNCH(SK_RESID_F32); break;
         case SK_BIAS_F32: SK_LAUNCH(SK_BIAS_F32); break;
+        case SK_ARGMAX: SK_LAUNCH(SK_ARGMAX); break;
         case SK_QKV: SHOWO_CHECK(qf && qf->D % 64 == 0 && qf->pos0 + qf->rows_per_seq <= qf->Lmax, "gemm_skinny: bad qkv fuse args");
             SK_LAUNCH(SK_QKV); break;
         default: SHOWO_CHECK(false, "gemm_skinny: bad epilogue");
