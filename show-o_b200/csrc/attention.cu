@@ -315,10 +315,129 @@ __global__ void __launch_bounds__(128) omni_attention_decode_kernel(AttnArgs a) 
     if (half == 0) qrow[d] = __float2bfloat16(acc / sum);
 }
 
+// Bulk-copy variant (default): the whole K block of a (sequence, head) is contiguous in the cache ([n_keys][64] bf16) and
+// each V^T row is a contiguous run, so ONE cp.async.bulk brings K and 64 row copies bring V^T -- all bytes of the CTA are
+// in flight at once (70 KB at 276 keys, 2-3 CTAs per SM) instead of a few 16 B loads per thread, and the math then
+// runs out of shared memory: 8 lanes per key (one 128 B row per quarter-warp, conflict-free), two threads per output dim.
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(128) omni_attention_decode_bulk_kernel(AttnArgs a, int n_pad, int vstride) {
+    extern __shared__ __align__(128) uint8_t dec_smem[];
+    bf16* Ks = reinterpret_cast<bf16*>(dec_smem);                                        // [n_pad][64]
+    uint8_t* Vs = dec_smem + (size_t)n_pad * 128;                                        // [64][vstride bytes]
+    float* sc_s = reinterpret_cast<float*>(Vs + (size_t)64 * vstride);                   // [n_pad]
+    __shared__ float red[8];
+    __shared__ __align__(8) uint64_t bars[2];
+    const int h = blockIdx.x, seq = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+    __syncthreads();
+    pdl_trigger();
+    pdl_wait();                                  // this step's K / V rows and q come from the predecessor GEMM
+    const bf16* kbase = a.kcache + ((int64_t)seq * a.H + h) * (int64_t)a.Lmax * 64;
+    const bf16* vbase = a.vtcache + ((int64_t)seq * a.H + h) * 64 * (int64_t)a.Lmax;
+    if (tid == 0) {
+        mbar_arrive_expect_tx(&bars[0], (uint32_t)a.n_keys * 128u);
+        bulk_g2s(Ks, kbase, (uint32_t)a.n_keys * 128u, &bars[0]);
+        mbar_arrive_expect_tx(&bars[1], 64u * (uint32_t)n_pad * 2u);
+    }
+    __syncthreads();
+    if (tid < 64) bulk_g2s(Vs + (size_t)tid * vstride, vbase + (int64_t)tid * a.Lmax, (uint32_t)n_pad * 2u, &bars[1]);
+
+    const showo_seq_mask_t msk = a.masks[seq];
+    const int qpos = a.pos0;
+    bf16* qrow = a.q + (int64_t)seq * a.rows_per_seq * a.ld + h * 64;
+    const int sub = lane & 7, kq = lane >> 3;
+    float q[8];
+    {
+        const uint4 u = *reinterpret_cast<const uint4*>(qrow + sub * 8);
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(h2[j]); q[2 * j] = f.x; q[2 * j + 1] = f.y; }
+    }
+    const float sc = a.scale * 1.4426950408889634f;
+    float mx = kNegBig;
+    mbar_wait(&bars[0], 0);
+    for (int k0 = warp * 4; k0 < n_pad; k0 += 16) {           // warp-uniform trip count: the shuffles stay convergent
+        const int k = k0 + kq;
+        float acc = 0.f;
+        if (k < a.n_keys) {
+            const uint4 u = *reinterpret_cast<const uint4*>(Ks + (size_t)k * 64 + sub * 8);
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = __bfloat1622float2(h2[j]);
+                acc += q[2 * j] * f.x + q[2 * j + 1] * f.y;
+            }
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        if (k < n_pad) {
+            const float s = (k < a.n_keys && omni_allowed(msk, qpos, k)) ? acc * sc : kNegBig;
+            if (sub == 0) sc_s[k] = s;
+            mx = fmaxf(mx, s);
+        }
+    }
+    mx = warp_max(mx);
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    float sum = 0.f;
+    for (int k = tid; k < n_pad; k += 128) {
+        const float p = exp2f(sc_s[k] - mx);     // masked / pad keys: exp2(-1e30) = 0
+        sc_s[k] = p;
+        sum += p;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) red[4 + warp] = sum;
+    __syncthreads();
+    sum = red[4] + red[5] + red[6] + red[7];
+    // o[d] = sum_k p[k] V^T[d][k]; two threads per d split the 8-key chunks
+    const int d = tid >> 1, half = tid & 1;
+    const uint8_t* vr = Vs + (size_t)d * vstride;
+    float acc = 0.f;
+    const int n8 = a.n_keys >> 3;
+    mbar_wait(&bars[1], 0);
+    for (int c = half; c < n8; c += 2) {
+        const uint4 u = *reinterpret_cast<const uint4*>(vr + c * 16);
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = __bfloat1622float2(h2[j]);
+            acc += sc_s[c * 8 + 2 * j] * f.x + sc_s[c * 8 + 2 * j + 1] * f.y;
+        }
+    }
+    if (half == 0)                               // ragged tail: the pad columns of the copy are never multiplied
+        for (int k = n8 * 8; k < a.n_keys; ++k) acc += sc_s[k] * __bfloat162float(reinterpret_cast<const bf16*>(vr)[k]);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    __syncthreads();   // everyone has read q before it is overwritten
+    if (half == 0) qrow[d] = __float2bfloat16(acc / sum);
+}
+
 int omni_attention_decode(const AttnArgs& a, cudaStream_t st) {
     if (a.n_seq == 0) return 0;
     SHOWO_CHECK(a.n_keys <= a.Lmax && a.n_keys * 4 <= 48 * 1024, "attention decode: n_keys too large");
     dim3 grid(a.H, a.n_seq);
+    static int variant = -1;                     // SHOWO_DECODE_ATTN=1 selects the per-thread-load kernel (A/B switch)
+    if (variant < 0) { const char* e = getenv("SHOWO_DECODE_ATTN"); variant = e ? atoi(e) : 2; }
+    const int n_pad = (a.n_keys + 7) & ~7;
+    const int vstride = n_pad * 2 + 16;
+    const size_t smem = (size_t)n_pad * 128 + (size_t)64 * vstride + (size_t)n_pad * 4;
+    if (variant == 2 && a.Lmax % 8 == 0 && n_pad <= a.Lmax && smem <= 200 * 1024 && a.ld % 8 == 0) {
+        static bool attr = false;
+        if (!attr) {
+            SHOWO_CUDA_OK(cudaFuncSetAttribute(omni_attention_decode_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr = true;
+        }
+        SHOWO_CUDA_OK(launch_kernel(omni_attention_decode_bulk_kernel, grid, dim3(128), smem, st, 1, a, n_pad, vstride));
+        note_launch();
+        return 0;
+    }
     omni_attention_decode_kernel<<<grid, 128, a.n_keys * sizeof(float), st>>>(a);
     note_launch();
     SHOWO_CUDA_OK(cudaGetLastError());

@@ -45,6 +45,117 @@ __device__ __forceinline__ uint4 ldg_stream(const void* p) {
     return r;
 }
 
+// Epilogue on a complete [16 x 64] fp32 tile: thread -> (row = tid/8, 8 columns at (tid%8)*8), f = its 8 pre-bias sums.
+// Called by all 128 threads of 4 full warps (the q/k LayerNorm and the argmax reduce across 8-lane groups).
+template <int EPI>
+__device__ __forceinline__ void skinny_epilogue(const SkinnyParams& p, float (&f)[8], int n0, int tid) {
+    const int r = tid >> 3, cq = (tid & 7) * 8;
+    const int n = n0 + cq;
+    if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (n + j < p.N) f[j] += __ldg(p.bias + n + j);
+    }
+    const bool row_ok = r < p.M;
+    if constexpr (EPI == SK_QKV) {
+        const QkvFuse& q = p.qf;
+        const int region = n0 / q.D;                       // 64-feature tile == one head of k / v / q, or 64 fc1 columns
+        if (region >= 3) {
+            if (row_ok) {
+                bf16* o = reinterpret_cast<bf16*>(p.out) + (int64_t)r * p.ldc + n;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = __float2bfloat16(gelu_new_f(f[j]));
+            }
+            return;
+        }
+        const int seq = r / q.rows_per_seq, pos = q.pos0 + r % q.rows_per_seq;
+        if (region == 1) {
+            if (row_ok) {
+                const int h = (n0 - q.D) >> 6;
+                bf16* vt = q.vtcache + ((int64_t)seq * q.H + h) * 64 * (int64_t)q.Lmax + pos;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) vt[(int64_t)(cq + j) * q.Lmax] = __float2bfloat16(f[j]);
+            }
+            return;
+        }
+        // k or q: LayerNorm over the 64 columns of the row (8 threads, lanes differing in bits 0..2), then rotary
+        const float* gam = region == 0 ? q.k_gamma : q.q_gamma;
+        const float* bet = region == 0 ? q.k_beta : q.q_beta;
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += f[j];
+        s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4);
+        const float mean = s * (1.f / 64.f);
+        float v = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { f[j] -= mean; v += f[j] * f[j]; }
+        v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 4);
+        const float rstd = rsqrtf(v * (1.f / 64.f) + q.eps);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = f[j] * rstd * __ldg(gam + cq + j) + __ldg(bet + cq + j);
+        // rotate_half pairing (i, i+16) on dims [0,32): column octets 0,1 pair with octets 2,3 (lane xor 2)
+        float pr[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pr[j] = __shfl_xor_sync(0xffffffffu, f[j], 2);
+        if (cq < 32 && row_ok) {
+            const int i0 = cq & 15;                       // frequency index of column cq (emb = cat(freqs, freqs))
+            const float sgn = cq < 16 ? -1.f : 1.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float c = __ldg(q.cos_tab + (int64_t)pos * 32 + i0 + j), sn = __ldg(q.sin_tab + (int64_t)pos * 32 + i0 + j);
+                f[j] = f[j] * c + sgn * pr[j] * sn;
+            }
+        }
+        if (!row_ok) return;
+        if (region == 0) {
+            const int h = n0 >> 6;
+            bf16* kd = q.kcache + (((int64_t)seq * q.H + h) * q.Lmax + pos) * 64 + cq;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) kd[j] = __float2bfloat16(f[j]);
+        } else {
+            bf16* o = reinterpret_cast<bf16*>(p.out) + (int64_t)r * p.ldc + n;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = __float2bfloat16(f[j]);
+        }
+    } else {
+        if constexpr (EPI == SK_ARGMAX) {
+            // greedy next token without materialising the logits: per-row max of this 64-column tile, then one atomicMax of
+            // a packed key (order-preserving float bits << 32 | ~index: ties resolve to the smallest index, like argmax)
+            float bv = -3.0e38f; int bi = 0x7fffffff;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) if (n + j < p.N && f[j] > bv) { bv = f[j]; bi = n + j; }
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            if (row_ok && (tid & 7) == 0 && bi != 0x7fffffff) {
+                const uint32_t fb = __float_as_uint(bv);
+                const uint32_t ord = (fb & 0x80000000u) ? ~fb : (fb | 0x80000000u);
+                atomicMax(p.argmax_keys + r, ((unsigned long long)ord << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)bi));
+            }
+            return;
+        }
+        if (!row_ok) return;
+        if constexpr (EPI == SK_BIAS_BF16) {
+            bf16* o = reinterpret_cast<bf16*>(p.out) + (int64_t)r * p.ldc + n;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (n + j < p.N) o[j] = __float2bfloat16(n + j >= p.gelu_from ? gelu_new_f(f[j]) : f[j]);
+        } else if constexpr (EPI == SK_RESID_F32) {
+            float* o = reinterpret_cast<float*>(p.out) + (int64_t)r * p.ldc + n;
+            const float* rs = p.resid + (int64_t)r * p.ldr + n;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) if (n + j < p.N) o[j] = f[j] + rs[j];
+        } else {
+            float* o = reinterpret_cast<float*>(p.out) + (int64_t)r * p.ldc + n;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) if (n + j < p.N) o[j] = f[j];
+        }
+    }
+}
+
+
 constexpr int kSkThreads = 128;
 constexpr int kSkTileN = 64;
 
@@ -179,122 +290,272 @@ __global__ void __launch_bounds__(kSkThreads) skinny_gemm_kernel(SkinnyParams p)
     }
 
     // ---- epilogue on the complete tile: thread -> (row = tid/8, 8 columns at (tid%8)*8)
-    const int r = tid >> 3, cq = (tid & 7) * 8;
-    const int n = n0 + cq;
     float f[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = tile[r * 64 + cq + j];
-    if (p.bias) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) if (n + j < p.N) f[j] += __ldg(p.bias + n + j);
+    for (int j = 0; j < 8; ++j) f[j] = tile[(tid >> 3) * 64 + (tid & 7) * 8 + j];
+    skinny_epilogue<EPI>(p, f, n0, tid);
+}
+
+// ================================================================================================ TMA-streamed variant
+// The register-prefetch kernel above keeps only (warps resident) x 256 B of weights in flight per SM and measured
+// 1.7 TB/s.  This one decouples the bytes in flight from occupancy: one persistent CTA per SM, a producer thread issuing
+// TMA boxes into an 8 x 20 KB shared-memory ring (160 KB in flight per SM), four consumer warps running mma.sync from
+// the 128B-swizzled tiles through ldmatrix.  Work is cut stream-K style: the (feature tile, 128-wide k chunk) pairs are
+// linearised and every CTA streams an equal contiguous range, so all SMs pull the same number of bytes whatever N and K
+// are.  A tile whose chunks span several CTAs is completed by the last arriver (atomic ticket), which sums the partial
+// tiles in CTA order -- deterministic.  The 16-row X chunk rides along with each weight chunk (TMA zero-fills rows
+// >= M; it is L2-resident), so there is no slab and no K limit.  Under programmatic dependent launch the producer
+// starts the weight stream BEFORE griddepcontrol.wait (weights never depend on the predecessor); only the X boxes wait.
+constexpr int kSk2Stages = 8;
+constexpr int kSk2ChunkK = 128;
+constexpr int kSk2WBytes = 64 * kSk2ChunkK * 2;                       // 16 KB: two [64 x 64] boxes
+constexpr int kSk2XBytes = 16 * kSk2ChunkK * 2;                       // 4 KB: two [16 x 64] boxes
+constexpr int kSk2StageBytes = kSk2WBytes + kSk2XBytes;               // 20 KB (multiple of 1024: swizzle atoms stay aligned)
+constexpr int kSk2PartStride = 72;                                    // floats per row of a warp's partial tile
+constexpr int kSk2Threads = 160;                                      // warps 0-3 consume, warp 4 produces
+constexpr size_t kSk2Smem = 1024 + (size_t)kSk2Stages * kSk2StageBytes + 4 * 16 * kSk2PartStride * 4 + 256;
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+struct Skinny2Sched { int tiles, cpt, grid; long long total; };       // cpt = chunks per tile = K / 128
+__device__ __forceinline__ long long sk2_begin(const Skinny2Sched& sc, int cta) { return (long long)cta * sc.total / sc.grid; }
+__device__ __forceinline__ int sk2_cta_of(const Skinny2Sched& sc, long long chunk) {
+    return (int)(((chunk + 1) * sc.grid - 1) / sc.total);
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(kSk2Threads, 1) skinny2_gemm_kernel(const __grid_constant__ CUtensorMap mw,
+                                                                        const __grid_constant__ CUtensorMap mx,
+                                                                        SkinnyParams p, Skinny2Sched sc) {
+    extern __shared__ uint8_t sk2_raw[];
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sk2_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* ring = base;
+    float* part = reinterpret_cast<float*>(base + (size_t)kSk2Stages * kSk2StageBytes);          // [4][16][72]
+    uint64_t* full = reinterpret_cast<uint64_t*>(part + 4 * 16 * kSk2PartStride);
+    uint64_t* empty = full + kSk2Stages;
+    int* s_flag = reinterpret_cast<int*>(empty + kSk2Stages);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long c_begin = sk2_begin(sc, blockIdx.x), c_end = sk2_begin(sc, blockIdx.x + 1);
+    if (tid == 0) {
+        for (int i = 0; i < kSk2Stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 4); }
+        mbar_fence_init();
+        tma_prefetch_desc(&mw); tma_prefetch_desc(&mx);
     }
-    const bool row_ok = r < p.M;
-    if constexpr (EPI == SK_QKV) {
-        const QkvFuse& q = p.qf;
-        const int region = n0 / q.D;                       // 64-feature tile == one head of k / v / q, or 64 fc1 columns
-        if (region >= 3) {
-            if (row_ok) {
-                bf16* o = reinterpret_cast<bf16*>(p.out) + (int64_t)r * p.ldc + n;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = __float2bfloat16(gelu_new_f(f[j]));
+    __syncthreads();
+    pdl_trigger();
+
+    if (warp == 4) {
+        // ------------------------------------------------------------------------------------------------ producer
+        if (lane == 0) {
+            const long long n = c_end - c_begin;
+            const int pre = (int)(n < kSk2Stages ? n : kSk2Stages);
+            for (int it = 0; it < pre; ++it) {                       // weights first: independent of the predecessor kernel
+                const long long c = c_begin + it;
+                const int tile = (int)(c / sc.cpt), kc = (int)(c % sc.cpt);
+                uint8_t* st = ring + (size_t)it * kSk2StageBytes;
+                mbar_arrive_expect_tx(&full[it], kSk2StageBytes);
+                tma_load_2d(st, &mw, &full[it], kc * kSk2ChunkK, tile * 64);
+                tma_load_2d(st + 8192, &mw, &full[it], kc * kSk2ChunkK + 64, tile * 64);
             }
-            return;
-        }
-        const int seq = r / q.rows_per_seq, pos = q.pos0 + r % q.rows_per_seq;
-        if (region == 1) {
-            if (row_ok) {
-                const int h = (n0 - q.D) >> 6;
-                bf16* vt = q.vtcache + ((int64_t)seq * q.H + h) * 64 * (int64_t)q.Lmax + pos;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) vt[(int64_t)(cq + j) * q.Lmax] = __float2bfloat16(f[j]);
+            pdl_wait();
+            for (int it = 0; it < pre; ++it) {
+                const int kc = (int)((c_begin + it) % sc.cpt);
+                uint8_t* st = ring + (size_t)it * kSk2StageBytes + kSk2WBytes;
+                tma_load_2d(st, &mx, &full[it], kc * kSk2ChunkK, 0);
+                tma_load_2d(st + 2048, &mx, &full[it], kc * kSk2ChunkK + 64, 0);
             }
-            return;
-        }
-        // k or q: LayerNorm over the 64 columns of the row (8 threads, lanes differing in bits 0..2), then rotary
-        const float* gam = region == 0 ? q.k_gamma : q.q_gamma;
-        const float* bet = region == 0 ? q.k_beta : q.q_beta;
-        float s = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) s += f[j];
-        s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4);
-        const float mean = s * (1.f / 64.f);
-        float v = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { f[j] -= mean; v += f[j] * f[j]; }
-        v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 4);
-        const float rstd = rsqrtf(v * (1.f / 64.f) + q.eps);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = f[j] * rstd * __ldg(gam + cq + j) + __ldg(bet + cq + j);
-        // rotate_half pairing (i, i+16) on dims [0,32): column octets 0,1 pair with octets 2,3 (lane xor 2)
-        float pr[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) pr[j] = __shfl_xor_sync(0xffffffffu, f[j], 2);
-        if (cq < 32 && row_ok) {
-            const int i0 = cq & 15;                       // frequency index of column cq (emb = cat(freqs, freqs))
-            const float sgn = cq < 16 ? -1.f : 1.f;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float c = __ldg(q.cos_tab + (int64_t)pos * 32 + i0 + j), sn = __ldg(q.sin_tab + (int64_t)pos * 32 + i0 + j);
-                f[j] = f[j] * c + sgn * pr[j] * sn;
+            for (long long it = pre; it < n; ++it) {
+                const int s = (int)(it % kSk2Stages);
+                const uint32_t ph = (uint32_t)((it / kSk2Stages) & 1);
+                mbar_wait(&empty[s], ph ^ 1u);
+                const long long c = c_begin + it;
+                const int tile = (int)(c / sc.cpt), kc = (int)(c % sc.cpt);
+                uint8_t* st = ring + (size_t)s * kSk2StageBytes;
+                mbar_arrive_expect_tx(&full[s], kSk2StageBytes);
+                tma_load_2d(st, &mw, &full[s], kc * kSk2ChunkK, tile * 64);
+                tma_load_2d(st + 8192, &mw, &full[s], kc * kSk2ChunkK + 64, tile * 64);
+                tma_load_2d(st + kSk2WBytes, &mx, &full[s], kc * kSk2ChunkK, 0);
+                tma_load_2d(st + kSk2WBytes + 2048, &mx, &full[s], kc * kSk2ChunkK + 64, 0);
             }
         }
-        if (!row_ok) return;
-        if (region == 0) {
-            const int h = n0 >> 6;
-            bf16* kd = q.kcache + (((int64_t)seq * q.H + h) * q.Lmax + pos) * 64 + cq;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) kd[j] = __float2bfloat16(f[j]);
-        } else {
-            bf16* o = reinterpret_cast<bf16*>(p.out) + (int64_t)r * p.ldc + n;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = __float2bfloat16(f[j]);
-        }
-    } else {
-        if constexpr (EPI == SK_ARGMAX) {
-            // greedy next token without materialising the logits: per-row max of this 64-column tile, then one atomicMax of
-            // a packed key (order-preserving float bits << 32 | ~index: ties resolve to the smallest index, like argmax)
-            float bv = -3.0e38f; int bi = 0x7fffffff;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) if (n + j < p.N && f[j] > bv) { bv = f[j]; bi = n + j; }
-#pragma unroll
-            for (int o = 1; o < 8; o <<= 1) {
-                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-            }
-            if (row_ok && (tid & 7) == 0 && bi != 0x7fffffff) {
-                const uint32_t fb = __float_as_uint(bv);
-                const uint32_t ord = (fb & 0x80000000u) ? ~fb : (fb | 0x80000000u);
-                atomicMax(p.argmax_keys + r, ((unsigned long long)ord << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)bi));
-            }
-            return;
-        }
-        if (!row_ok) return;
-        if constexpr (EPI == SK_BIAS_BF16) {
-            bf16* o = reinterpret_cast<bf16*>(p.out) + (int64_t)r * p.ldc + n;
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (n + j < p.N) o[j] = __float2bfloat16(n + j >= p.gelu_from ? gelu_new_f(f[j]) : f[j]);
-        } else if constexpr (EPI == SK_RESID_F32) {
-            float* o = reinterpret_cast<float*>(p.out) + (int64_t)r * p.ldc + n;
-            const float* rs = p.resid + (int64_t)r * p.ldr + n;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) if (n + j < p.N) o[j] = f[j] + rs[j];
-        } else {
-            float* o = reinterpret_cast<float*>(p.out) + (int64_t)r * p.ldc + n;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) if (n + j < p.N) o[j] = f[j];
-        }
+        return;
     }
+
+    // ---------------------------------------------------------------------------------------------------- consumers
+    pdl_wait();                                   // the epilogue reads the residual / writes buffers of the predecessor
+    // warp w contracts k16 steps {2w, 2w+1} of every chunk against all 64 features: k16 step ks lives in box ks>>2 at
+    // 16 B chunks (ks&3)*2 + {0,1} of the 128 B rows (SWIZZLE_128B: chunk ^= row & 7)
+    const int mat = lane >> 3, r8 = lane & 7;
+    uint32_t a_off[2], b_off[2];
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+        const int ks = 2 * warp + kk, box = ks >> 2, kq = ks & 3;
+        a_off[kk] = kSk2WBytes + box * 2048 + ((mat & 1) * 8 + r8) * 128 + (((kq * 2 + (mat >> 1)) ^ r8) << 4);
+        b_off[kk] = box * 8192 + ((mat >> 1) * 8 + r8) * 128 + (((kq * 2 + (mat & 1)) ^ r8) << 4);
+    }
+    const uint32_t ring_u32 = smem_u32(ring);
+    const int g = lane >> 2, t4 = lane & 3;
+    long long c = c_begin, it = 0;
+    while (c < c_end) {
+        const int tile = (int)(c / sc.cpt);
+        const long long tile_c0 = (long long)tile * sc.cpt;
+        const long long seg_begin = c;
+        const long long seg_end = (tile_c0 + sc.cpt < c_end) ? tile_c0 + sc.cpt : c_end;
+        float acc[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; acc[i][2] = 0.f; acc[i][3] = 0.f; }
+        for (; c < seg_end; ++c, ++it) {
+            const int s = (int)(it % kSk2Stages);
+            mbar_wait(&full[s], (uint32_t)((it / kSk2Stages) & 1));
+            const uint32_t st = ring_u32 + (uint32_t)s * kSk2StageBytes;
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+                uint32_t af[4];
+                ldsm_x4(af, st + a_off[kk]);
+#pragma unroll
+                for (int jp = 0; jp < 4; ++jp) {
+                    uint32_t bf[4];
+                    ldsm_x4(bf, st + b_off[kk] + jp * 2048);          // n-blocks 2jp, 2jp+1 (16 rows x 128 B)
+                    mma16816(acc[2 * jp], af, bf[0], bf[1]);
+                    mma16816(acc[2 * jp + 1], af, bf[2], bf[3]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+        // ---- cross-warp (k split) reduction through smem, then the [16 x 64] tile in the epilogue's thread mapping
+        float* mine = part + warp * 16 * kSk2PartStride;
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) {
+            *reinterpret_cast<float2*>(mine + g * kSk2PartStride + nb * 8 + t4 * 2) = make_float2(acc[nb][0], acc[nb][1]);
+            *reinterpret_cast<float2*>(mine + (g + 8) * kSk2PartStride + nb * 8 + t4 * 2) = make_float2(acc[nb][2], acc[nb][3]);
+        }
+        consumer_bar();
+        const int r = tid >> 3, cq = (tid & 7) * 8;
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const float4 u0 = *reinterpret_cast<const float4*>(part + (w * 16 + r) * kSk2PartStride + cq);
+            const float4 u1 = *reinterpret_cast<const float4*>(part + (w * 16 + r) * kSk2PartStride + cq + 4);
+            f[0] += u0.x; f[1] += u0.y; f[2] += u0.z; f[3] += u0.w; f[4] += u1.x; f[5] += u1.y; f[6] += u1.z; f[7] += u1.w;
+        }
+        consumer_bar();                           // `part` may be overwritten by the next segment from here on
+        const bool whole = seg_begin == tile_c0 && seg_end == tile_c0 + sc.cpt;
+        bool finish = true;
+        if (!whole) {
+            // partial tile -> workspace slot (slot 1: the segment starts the tile, slot 0: it starts inside it)
+            float* ws = p.partials + ((long long)blockIdx.x * 2 + (seg_begin == tile_c0 ? 1 : 0)) * 1024 + r * 64 + cq;
+            reinterpret_cast<float4*>(ws)[0] = make_float4(f[0], f[1], f[2], f[3]);
+            reinterpret_cast<float4*>(ws)[1] = make_float4(f[4], f[5], f[6], f[7]);
+            __threadfence();
+            consumer_bar();
+            const int first = sk2_cta_of(sc, tile_c0), last = sk2_cta_of(sc, tile_c0 + sc.cpt - 1);
+            if (tid == 0) {
+                const int t = atomicAdd(&p.tickets[tile], 1);
+                const int fin = (t == last - first);
+                if (fin) p.tickets[tile] = 0;      // self-resetting for the next launch
+                *s_flag = fin;
+            }
+            consumer_bar();
+            finish = *s_flag != 0;
+            consumer_bar();                       // s_flag is rewritten by the next partial segment
+            if (finish) {
+                __threadfence();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = 0.f;
+                for (int cta = first; cta <= last; ++cta) {           // CTA order => deterministic sum
+                    const long long b0 = sk2_begin(sc, cta);
+                    const float* src = p.partials + ((long long)cta * 2 + (b0 <= tile_c0 ? 1 : 0)) * 1024 + r * 64 + cq;
+                    const float4 u0 = __ldcg(reinterpret_cast<const float4*>(src));
+                    const float4 u1 = __ldcg(reinterpret_cast<const float4*>(src) + 1);
+                    f[0] += u0.x; f[1] += u0.y; f[2] += u0.z; f[3] += u0.w; f[4] += u1.x; f[5] += u1.y; f[6] += u1.z; f[7] += u1.w;
+                }
+            }
+        }
+        if (finish) skinny_epilogue<EPI>(p, f, tile * 64, tid);
+    }
+}
+
+// SHOWO_SKINNY=1 selects the register-prefetch kernel (A/B switch while tuning)
+static int skinny_variant() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SHOWO_SKINNY"); v = e ? atoi(e) : 2; }
+    return v;
 }
 
 static float* g_partials = nullptr; static size_t g_partials_cap = 0;
 static int* g_tickets = nullptr; static size_t g_tickets_cap = 0;
 
+static int ensure_skinny_ws(size_t partial_floats, size_t tiles, cudaStream_t st) {
+    if (partial_floats > g_partials_cap) {
+        SHOWO_CUDA_OK(cudaStreamSynchronize(st));
+        if (g_partials) cudaFree(g_partials);
+        SHOWO_CUDA_OK(cudaMalloc(&g_partials, partial_floats * 4));
+        g_partials_cap = partial_floats;
+    }
+    if (tiles > g_tickets_cap) {
+        SHOWO_CUDA_OK(cudaStreamSynchronize(st));
+        if (g_tickets) cudaFree(g_tickets);
+        SHOWO_CUDA_OK(cudaMalloc(&g_tickets, tiles * 4));
+        SHOWO_CUDA_OK(cudaMemset(g_tickets, 0, tiles * 4));
+        g_tickets_cap = tiles;
+    }
+    return 0;
+}
+
+static int gemm_skinny2(const GemmArgs& a, int epi, const QkvFuse* qf, int tiles, cudaStream_t st) {
+    SHOWO_CHECK((reinterpret_cast<uintptr_t>(a.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.B) & 15) == 0,
+                "gemm_skinny: operands must be 16-byte aligned");
+    Skinny2Sched sc{};
+    sc.tiles = tiles; sc.cpt = a.K / kSk2ChunkK; sc.total = (long long)tiles * sc.cpt;
+    sc.grid = (int)std::min<long long>(gemm_num_sms(), sc.total);
+    SkinnyParams p{};
+    p.X = a.A; p.lda = a.lda; p.W = a.B; p.ldb = a.ldb; p.M = a.M; p.N = a.N; p.K = a.K; p.splits = 1; p.kc = a.K;
+    p.out = a.out; p.ldc = a.ldc; p.bias = a.bias; p.resid = a.resid; p.ldr = a.ldr; p.gelu_from = a.gelu_from;
+    if (qf) p.qf = *qf;
+    p.argmax_keys = a.argmax_keys;
+    if (epi == SK_ARGMAX) SHOWO_CHECK(a.argmax_keys != nullptr, "gemm_skinny: argmax epilogue needs a key buffer");
+    SHOWO_TRY(ensure_skinny_ws((size_t)sc.grid * 2 * 1024, (size_t)tiles, st));
+    p.partials = g_partials; p.tickets = g_tickets;
+    CUtensorMap mw, mx;
+    SHOWO_TRY(make_tmap_2d(&mw, a.B, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldb * 2, 64, 64));
+    SHOWO_TRY(make_tmap_2d(&mx, a.A, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda * 2, 64, 16));
+#define SK2_LAUNCH(E)                                                                                             \
+    do {                                                                                                          \
+        static bool attr = false;                                                                                 \
+        if (!attr) {                                                                                              \
+            SHOWO_CUDA_OK(cudaFuncSetAttribute(skinny2_gemm_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSk2Smem)); \
+            attr = true;                                                                                          \
+        }                                                                                                         \
+        SHOWO_CUDA_OK(launch_kernel(skinny2_gemm_kernel<E>, dim3(sc.grid), dim3(kSk2Threads), kSk2Smem, st, 1, mw, mx, p, sc)); \
+    } while (0)
+    switch (epi) {
+        case SK_BIAS_BF16: SK2_LAUNCH(SK_BIAS_BF16); break;
+        case SK_RESID_F32: SK2_LAUNCH(SK_RESID_F32); break;
+        case SK_BIAS_F32: SK2_LAUNCH(SK_BIAS_F32); break;
+        case SK_ARGMAX: SK2_LAUNCH(SK_ARGMAX); break;
+        case SK_QKV: SHOWO_CHECK(qf && qf->D % 64 == 0 && qf->pos0 + qf->rows_per_seq <= qf->Lmax, "gemm_skinny: bad qkv fuse args");
+            SK2_LAUNCH(SK_QKV); break;
+        default: SHOWO_CHECK(false, "gemm_skinny: bad epilogue");
+    }
+#undef SK2_LAUNCH
+    note_launch();
+    return 0;
+}
+
 int gemm_skinny(const GemmArgs& a, int epi, const QkvFuse* qf, cudaStream_t st) {
     SHOWO_CHECK(a.M >= 1 && a.M <= 16, "gemm_skinny: M must be in [1,16]");
     SHOWO_CHECK(a.K % 64 == 0 && a.lda % 8 == 0 && a.ldb % 8 == 0, "gemm_skinny: K must be a multiple of 64, lda/ldb of 8");
     const int tiles = cdiv(a.N, kSkTileN);
+    if (skinny_variant() == 2 && a.K % kSk2ChunkK == 0 && a.ln_x == nullptr)
+        return gemm_skinny2(a, epi, qf, tiles, st);
     // enough CTAs to cover the SMs a few times over, K per split a multiple of 64 and <= 2048 (X slab <= 64 KB of smem)
     int splits = 1;
     // at least one full wave of CTAs, X slab <= 64 KB of smem; fewer, longer-streaming CTAs beat many short ones

@@ -19,4 +19,17 @@ descs = [(0, 0, 0, 0, 259)] * 16
 for _ in range(2):
     toks, _ = model.mmu_generate_batched(ids, attention_mask=descs, max_new_tokens=n_new, top_k=1)
 torch.cuda.synchronize()
+if os.environ.get("MMU_TIMING"):
+    # ms per decode step from the difference of two generation lengths (prefill cancels)
+    def run(n):
+        best = 1e9
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            model.mmu_generate_batched(ids, attention_mask=descs, max_new_tokens=n, top_k=1)
+            e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return best
+    a, b = run(8), run(72)
+    print("decode ms/step %.4f  (prefill+8 steps %.3f ms)  env %s" % ((b - a) / 64, a, {k: v for k, v in os.environ.items() if k.startswith("SHOWO_")}))
 print("done", toks.shape)
