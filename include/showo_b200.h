@@ -112,11 +112,19 @@ SHOWO_API int showo_sampler_step(const float* logits_cond_dev, const float* logi
 /* models/modeling_showo.py:183-240  Showo.mmu_generate, batched with a KV cache: row b is exactly what the
  * reference returns for a B=1 call on row b (greedy when top_k == 1).  ids_dev [B, L0] int64 (or embeds_dev
  * [B, L0, hidden] fp32).  out_tokens_dev [B, max_new_tokens] int64, out_lengths_dev [B] int32 (tokens produced
- * up to and including eot; eot_token < 0 disables early stop).  Only top_k == 1 (the reference script's
- * setting, inference_mmu.py:81) is supported. */
+ * up to and including eot; eot_token < 0 disables early stop).  top_k == 1 (the reference script's setting,
+ * inference_mmu.py:81) is greedy; top_k <= 0 means None (no filter); otherwise logits / temperature, top-k filter,
+ * softmax and a categorical draw per token (:219-228) with Exp(1) noise from noise_expo_dev
+ * [max_new_tokens, B, vocab] (parity mode) or, when NULL, from the library's Philox stream keyed by `seed`. */
 SHOWO_API int showo_mmu_generate(showo_engine_t* e, const int64_t* ids_dev, const float* embeds_dev, int B, int L0,
                        const showo_seq_mask_t* masks_host, int max_new_tokens, int top_k, float temperature,
-                       int64_t eot_token, int64_t* out_tokens_dev, int32_t* out_lengths_dev, void* stream);
+                       int64_t eot_token, uint64_t seed, const float* noise_expo_dev, int64_t* out_tokens_dev,
+                       int32_t* out_lengths_dev, void* stream);
+
+/* The next-token draw of mmu_generate on its own (models/modeling_showo.py:219-228), for parity tests:
+ * logits_dev [B, ld >= V] fp32 -> out_tokens_dev [B] int64.  noise_expo_dev [B, V] or NULL (Philox(seed, step)). */
+SHOWO_API int showo_mmu_sample(const float* logits_dev, int64_t ld, int B, int V, float temperature, int top_k,
+                     const float* noise_expo_dev, uint64_t seed, uint32_t step, int64_t* out_tokens_dev, void* stream);
 
 /* model.showo.model.embed_tokens(ids) as called from outside (inference_mmu.py:134-136): out fp32 [n, hidden] */
 SHOWO_API int showo_embed_tokens(showo_engine_t* e, const int64_t* ids_dev, int64_t n, float* out_dev, void* stream);

@@ -534,11 +534,11 @@ int showo_sampler_step(const float* logits_cond_dev, const float* logits_uncond_
 
 int showo_mmu_generate(showo_engine_t* e, const int64_t* ids_dev, const float* embeds_dev, int B, int L0,
                        const showo_seq_mask_t* masks_host, int max_new_tokens, int top_k, float temperature,
-                       int64_t eot_token, int64_t* out_tokens_dev, int32_t* out_lengths_dev, void* stream) {
+                       int64_t eot_token, uint64_t seed, const float* noise_expo_dev, int64_t* out_tokens_dev,
+                       int32_t* out_lengths_dev, void* stream) {
     SHOWO_TRY(check_ready(e));
     SHOWO_CHECK((ids_dev != nullptr) != (embeds_dev != nullptr), "mmu_generate: exactly one of ids / embeds");
     SHOWO_CHECK(B > 0 && L0 > 0 && max_new_tokens > 0 && masks_host && out_tokens_dev, "mmu_generate: bad arguments");
-    SHOWO_CHECK(top_k == 1, "mmu_generate: only top_k == 1 (greedy, inference_mmu.py:81) is implemented");
     SHOWO_CHECK(temperature > 0.f, "mmu_generate: temperature must be positive");
     SHOWO_CHECK(L0 + max_new_tokens <= e->cfg.max_pos, "mmu_generate: sequence would exceed max_pos");
     cudaStream_t st = (cudaStream_t)stream;
@@ -561,9 +561,9 @@ int showo_mmu_generate(showo_engine_t* e, const int64_t* ids_dev, const float* e
         SHOWO_TRY(dev_alloc(&e->tok_ws, (size_t)B));
         e->tok_ws_cap = B;
     }
-    if (B <= 16 && D % 64 == 0) {
-        // decode fast path: greedy pick fused into the head GEMM (no logits tensor, no argmax pass), final LayerNorm fused
-        // into the head GEMM's input staging, per-layer LayerNorm fused into the projection GEMM (run_layers, decode)
+    const bool greedy = top_k == 1;              // a one-entry distribution: the draw is the argmax whatever the noise
+    if (greedy && B <= 16 && D % 64 == 0) {
+        // decode fast path: greedy pick fused into the head GEMM's epilogue (no logits tensor, no argmax pass)
         if (!e->argmax_keys) {
             SHOWO_TRY(dev_alloc(&e->argmax_keys, (size_t)16));
             SHOWO_CUDA_OK(cudaMemsetAsync(e->argmax_keys, 0, 16 * 8, st));
@@ -584,9 +584,18 @@ int showo_mmu_generate(showo_engine_t* e, const int64_t* ids_dev, const float* e
     } else {
     SHOWO_TRY(gemm_bf16(g, GEMM_BIAS_F32, st));
     for (int t = 0; t < max_new_tokens; ++t) {
-        SHOWO_TRY(argmax_rows(e->logits_ws, V, B, V, e->tok_ws, st));
-        SHOWO_CUDA_OK(cudaMemcpy2DAsync(out_tokens_dev + t, (size_t)max_new_tokens * 8, e->tok_ws, 8, 8, B,
-                                        cudaMemcpyDeviceToDevice, st));
+        if (greedy) {
+            SHOWO_TRY(argmax_rows(e->logits_ws, V, B, V, e->tok_ws, st));
+            SHOWO_CUDA_OK(cudaMemcpy2DAsync(out_tokens_dev + t, (size_t)max_new_tokens * 8, e->tok_ws, 8, 8, B,
+                                            cudaMemcpyDeviceToDevice, st));
+        } else {
+            MmuSampleArgs ms{};
+            ms.logits = e->logits_ws; ms.ld = V; ms.B = B; ms.V = V; ms.temperature = temperature; ms.top_k = top_k;
+            ms.noise_expo = noise_expo_dev ? noise_expo_dev + (size_t)t * B * V : nullptr;
+            ms.seed = seed; ms.step = (uint32_t)t;
+            ms.out = out_tokens_dev + t; ms.out_stride = max_new_tokens; ms.out_next = e->tok_ws;
+            SHOWO_TRY(mmu_sample(ms, st));
+        }
         if (t == max_new_tokens - 1) break;
         // ---- decode one token per row at position L0 + t
         SHOWO_TRY(embed_gather(e->tok_ws, 1, 0, e->embed, e->x, B, 1, D, V, st));
@@ -602,6 +611,16 @@ int showo_mmu_generate(showo_engine_t* e, const int64_t* ids_dev, const float* e
     }
     e->launches_last = launches_total() - l0;
     return 0;
+}
+
+int showo_mmu_sample(const float* logits_dev, int64_t ld, int B, int V, float temperature, int top_k,
+                     const float* noise_expo_dev, uint64_t seed, uint32_t step, int64_t* out_tokens_dev, void* stream) {
+    SHOWO_CHECK(logits_dev && out_tokens_dev && B > 0 && V > 0 && ld >= V, "mmu_sample: bad arguments");
+    SHOWO_CHECK(showo_device_count() > 0, "no sm_100 CUDA device visible: libshowo_b200 has no CPU fallback");
+    MmuSampleArgs ms{};
+    ms.logits = logits_dev; ms.ld = ld; ms.B = B; ms.V = V; ms.temperature = temperature; ms.top_k = top_k;
+    ms.noise_expo = noise_expo_dev; ms.seed = seed; ms.step = step; ms.out = out_tokens_dev; ms.out_stride = 1;
+    return mmu_sample(ms, (cudaStream_t)stream);
 }
 
 int64_t showo_kernel_launches(showo_engine_t* e) { return e ? e->launches_last : 0; }

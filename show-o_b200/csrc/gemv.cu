@@ -306,14 +306,14 @@ __global__ void __launch_bounds__(kSkThreads) skinny_gemm_kernel(SkinnyParams p)
 // tiles in CTA order -- deterministic.  The 16-row X chunk rides along with each weight chunk (TMA zero-fills rows
 // >= M; it is L2-resident), so there is no slab and no K limit.  Under programmatic dependent launch the producer
 // starts the weight stream BEFORE griddepcontrol.wait (weights never depend on the predecessor); only the X boxes wait.
-constexpr int kSk2Stages = 8;
+constexpr int kSk2MaxStages = 8;
 constexpr int kSk2ChunkK = 128;
 constexpr int kSk2WBytes = 64 * kSk2ChunkK * 2;                       // 16 KB: two [64 x 64] boxes
 constexpr int kSk2XBytes = 16 * kSk2ChunkK * 2;                       // 4 KB: two [16 x 64] boxes
 constexpr int kSk2StageBytes = kSk2WBytes + kSk2XBytes;               // 20 KB (multiple of 1024: swizzle atoms stay aligned)
 constexpr int kSk2PartStride = 72;                                    // floats per row of a warp's partial tile
 constexpr int kSk2Threads = 160;                                      // warps 0-3 consume, warp 4 produces
-constexpr size_t kSk2Smem = 1024 + (size_t)kSk2Stages * kSk2StageBytes + 4 * 16 * kSk2PartStride * 4 + 256;
+static inline size_t sk2_smem_bytes(int stages) { return 1024 + (size_t)stages * kSk2StageBytes + 4 * 16 * kSk2PartStride * 4 + 256; }
 
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
@@ -321,7 +321,7 @@ __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
 }
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-struct Skinny2Sched { int tiles, cpt, grid; long long total; };       // cpt = chunks per tile = K / 128
+struct Skinny2Sched { int tiles, cpt, grid, stages; long long total; };       // cpt = chunks per tile = K / 128
 __device__ __forceinline__ long long sk2_begin(const Skinny2Sched& sc, int cta) { return (long long)cta * sc.total / sc.grid; }
 __device__ __forceinline__ int sk2_cta_of(const Skinny2Sched& sc, long long chunk) {
     return (int)(((chunk + 1) * sc.grid - 1) / sc.total);
@@ -334,12 +334,13 @@ __global__ void __launch_bounds__(kSk2Threads, 1) skinny2_gemm_kernel(const __gr
     extern __shared__ uint8_t sk2_raw[];
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sk2_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* ring = base;
-    float* part = reinterpret_cast<float*>(base + (size_t)kSk2Stages * kSk2StageBytes);          // [4][16][72]
+    float* part = reinterpret_cast<float*>(base + (size_t)sc.stages * kSk2StageBytes);           // [4][16][72]
     uint64_t* full = reinterpret_cast<uint64_t*>(part + 4 * 16 * kSk2PartStride);
-    uint64_t* empty = full + kSk2Stages;
-    int* s_flag = reinterpret_cast<int*>(empty + kSk2Stages);
+    uint64_t* empty = full + kSk2MaxStages;
+    int* s_flag = reinterpret_cast<int*>(empty + kSk2MaxStages);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int kSk2Stages = sc.stages;               // ring depth (runtime: 8 = 160 KB in flight, 4 lets two kernels share an SM)
     const long long c_begin = sk2_begin(sc, blockIdx.x), c_end = sk2_begin(sc, blockIdx.x + 1);
     if (tid == 0) {
         for (int i = 0; i < kSk2Stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 4); }
@@ -483,6 +484,11 @@ __global__ void __launch_bounds__(kSk2Threads, 1) skinny2_gemm_kernel(const __gr
     }
 }
 
+static int skinny_stages() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SHOWO_SKINNY_STAGES"); v = e ? atoi(e) : 8; if (v < 2 || v > kSk2MaxStages) v = 8; }
+    return v;
+}
 // SHOWO_SKINNY=1 selects the register-prefetch kernel (A/B switch while tuning)
 static int skinny_variant() {
     static int v = -1;
@@ -516,6 +522,8 @@ static int gemm_skinny2(const GemmArgs& a, int epi, const QkvFuse* qf, int tiles
     Skinny2Sched sc{};
     sc.tiles = tiles; sc.cpt = a.K / kSk2ChunkK; sc.total = (long long)tiles * sc.cpt;
     sc.grid = (int)std::min<long long>(gemm_num_sms(), sc.total);
+    sc.stages = skinny_stages();
+    const size_t kSk2Smem = sk2_smem_bytes(sc.stages);
     SkinnyParams p{};
     p.X = a.A; p.lda = a.lda; p.W = a.B; p.ldb = a.ldb; p.M = a.M; p.N = a.N; p.K = a.K; p.splits = 1; p.kc = a.K;
     p.out = a.out; p.ldc = a.ldc; p.bias = a.bias; p.resid = a.resid; p.ldr = a.ldr; p.gelu_from = a.gelu_from;
@@ -531,7 +539,7 @@ static int gemm_skinny2(const GemmArgs& a, int epi, const QkvFuse* qf, int tiles
     do {                                                                                                          \
         static bool attr = false;                                                                                 \
         if (!attr) {                                                                                              \
-            SHOWO_CUDA_OK(cudaFuncSetAttribute(skinny2_gemm_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSk2Smem)); \
+            SHOWO_CUDA_OK(cudaFuncSetAttribute(skinny2_gemm_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sk2_smem_bytes(kSk2MaxStages))); \
             attr = true;                                                                                          \
         }                                                                                                         \
         SHOWO_CUDA_OK(launch_kernel(skinny2_gemm_kernel<E>, dim3(sc.grid), dim3(kSk2Threads), kSk2Smem, st, 1, mw, mx, p, sc)); \

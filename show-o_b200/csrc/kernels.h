@@ -120,5 +120,14 @@ struct SamplerArgs {
 int t2i_sampler_step(const SamplerArgs& a, cudaStream_t st);
 // greedy / top-k=1 next-token pick for MMU decode: out[b] = argmax_v logits[b, v]; appended to ids at position pos
 int argmax_rows(const float* logits, int64_t ld, int B, int V, int64_t* out, cudaStream_t st);
+// mmu_generate's next-token draw (modeling_showo.py:219-228): temperature, top-k filter (top_k <= 0: none), softmax,
+// categorical draw; Exp(1) noise [B, V] host-supplied (parity mode) or Philox(seed, step)
+struct MmuSampleArgs {
+    const float* logits; int64_t ld; int B, V; float temperature; int top_k;
+    const float* noise_expo; uint64_t seed; uint32_t step;
+    int64_t* out; int64_t out_stride;    // token of row b -> out[b * out_stride]
+    int64_t* out_next;                   // optional dense [B] copy (the next step's input ids)
+};
+int mmu_sample(const MmuSampleArgs& a, cudaStream_t st);
 
 }  // namespace showo

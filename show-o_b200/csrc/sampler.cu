@@ -251,4 +251,97 @@ int argmax_rows(const float* logits, int64_t ld, int B, int V, int64_t* out, cud
     return 0;
 }
 
+// ---------------------------------------------------------------------------------- mmu_generate next-token draw
+// modeling_showo.py:219-228: logits[:, -1] / temperature -> optional top-k filter (everything below the k-th largest
+// value becomes -inf, ties kept) -> softmax -> multinomial(probs, 1) (== argmax(p / Exp(1))).  One CTA per row; the row
+// (V = 58498 floats) stays in L2 across the passes.  The k-th largest value comes from a 4 x 8-bit radix select over
+// order-preserving integer keys, not a sort.
+__device__ __forceinline__ uint32_t float_order_key(float f) {
+    const uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+__global__ void __launch_bounds__(1024) mmu_sample_kernel(MmuSampleArgs a) {
+    __shared__ float red[32];
+    __shared__ ArgMax red_am[32];
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t s_prefix, s_remaining;
+    const int row = blockIdx.x, tid = threadIdx.x;
+    const float* lr = a.logits + (int64_t)row * a.ld;
+    float mx = -FLT_MAX;
+    for (int i = tid; i < a.V; i += 1024) mx = fmaxf(mx, __fdiv_rn(lr[i], a.temperature));
+    mx = block_reduce_max<1024>(mx, red);
+
+    uint32_t kth = 0u;                            // keep keys >= kth (0 keeps everything)
+    if (a.top_k > 0 && a.top_k < a.V) {
+        if (tid == 0) { s_prefix = 0u; s_remaining = (uint32_t)a.top_k; }
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            for (int i = tid; i < 256; i += 1024) hist[i] = 0u;
+            __syncthreads();
+            const uint32_t prefix = s_prefix;
+            const uint32_t hi_mask = shift == 24 ? 0u : (0xFFFFFFFFu << (shift + 8));
+            for (int i = tid; i < a.V; i += 1024) {
+                const uint32_t key = float_order_key(__fdiv_rn(lr[i], a.temperature));
+                if ((key & hi_mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                uint32_t cum = 0u, rem = s_remaining;
+                for (int b = 255; b >= 0; --b) {
+                    if (cum + hist[b] >= rem) { s_prefix = prefix | ((uint32_t)b << shift); s_remaining = rem - cum; break; }
+                    cum += hist[b];
+                }
+            }
+            __syncthreads();
+        }
+        kth = s_prefix;
+    }
+    float sum = 0.f;
+    for (int i = tid; i < a.V; i += 1024) {
+        const float l = __fdiv_rn(lr[i], a.temperature);
+        if (float_order_key(l) >= kth) sum += expf(l - mx);
+    }
+    sum = block_reduce_sum<1024>(sum, red);
+
+    ArgMax best{-1.f, 0x7fffffff, 0.f};
+    const float* ex = a.noise_expo ? a.noise_expo + (int64_t)row * a.V : nullptr;
+    const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+    for (int i = tid; i < a.V; i += 1024) {
+        const float l = __fdiv_rn(lr[i], a.temperature);
+        if (float_order_key(l) < kth) continue;   // filtered: p = 0 never wins against a kept entry
+        float q;
+        if (ex) q = ex[i];
+        else {
+            const uint4 r = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)row, a.step, 0xAu), key);
+            q = -logf(u01(r.x));
+        }
+        const float pr = __fdiv_rn(expf(l - mx), sum);
+        best = better(best, ArgMax{__fdiv_rn(pr, q), i, pr});
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ArgMax other;
+        other.v = __shfl_xor_sync(0xffffffffu, best.v, o);
+        other.i = __shfl_xor_sync(0xffffffffu, best.i, o);
+        other.p = 0.f;
+        best = better(best, other);
+    }
+    if ((tid & 31) == 0) red_am[tid >> 5] = best;
+    __syncthreads();
+    if (tid == 0) {
+        ArgMax r = red_am[0];
+        for (int i = 1; i < 32; ++i) r = better(r, red_am[i]);
+        a.out[(int64_t)row * a.out_stride] = r.i;
+        if (a.out_next) a.out_next[row] = r.i;
+    }
+}
+int mmu_sample(const MmuSampleArgs& a, cudaStream_t st) {
+    if (a.B == 0) return 0;
+    SHOWO_CHECK(a.temperature > 0.f && a.V > 0, "mmu_sample: temperature must be positive");
+    mmu_sample_kernel<<<a.B, 1024, 0, st>>>(a);
+    note_launch();
+    SHOWO_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace showo

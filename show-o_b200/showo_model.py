@@ -327,12 +327,15 @@ class Showo(nn.Module):
     # ------------------------------------------------------------------ mmu
     @torch.no_grad()
     def mmu_generate_batched(self, idx=None, input_embeddings=None, attention_mask=None, max_new_tokens=100,
-                             temperature=1.0, top_k=None, eot_token=None):
-        """Batched KV-cached decode: returns (tokens [B, max_new_tokens] int64, lengths [B] int32)."""
+                             temperature=1.0, top_k=None, eot_token=None, generator: torch.Generator = None):
+        """Batched KV-cached decode: returns (tokens [B, max_new_tokens] int64, lengths [B] int32).
+
+        top_k=1 is greedy (inference_mmu.py:81); top_k=None / k>1 draw from softmax(top-k-filtered logits / temperature)
+        (modeling_showo.py:219-228).  With `generator` the Exp(1) noise of torch.multinomial is drawn by torch
+        ([B, V] per token) and handed to the kernel; otherwise the kernel's Philox stream is seeded from torch's
+        global generator."""
         lib = _lib.require_gpu()
         eng = self._sync_engine()
-        if top_k != 1:
-            raise NotImplementedError("mmu_generate: only top_k=1 (greedy, as inference_mmu.py:81) is implemented")
         if input_embeddings is None:
             B, L0 = idx.shape
             ids, emb, dev = idx.contiguous(), None, idx.device
@@ -343,18 +346,28 @@ class Showo(nn.Module):
         toks = torch.zeros(B, max_new_tokens, dtype=torch.int64, device=dev)
         lens = torch.zeros(B, dtype=torch.int32, device=dev)
         eot = -1 if eot_token is None else int(eot_token)
+        k = 0 if top_k is None else int(top_k)
+        expo, seed = None, 0
+        if k != 1:
+            if generator is not None:
+                expo = torch.empty(max_new_tokens, B, self.config.vocab_size, dtype=torch.float32, device=dev)
+                for t in range(max_new_tokens):
+                    expo[t].exponential_(1, generator=generator)
+            else:
+                seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         with torch.cuda.device(dev):
             _lib.check(lib.showo_mmu_generate(eng, _lib.ptr(ids), _lib.ptr(emb), B, L0, _lib.masks_array(descs),
-                                              max_new_tokens, 1, float(temperature), eot, _lib.ptr(toks),
-                                              _lib.ptr(lens), _lib.current_stream_ptr()), "showo_mmu_generate")
+                                              max_new_tokens, k, float(temperature), eot, seed, _lib.ptr(expo),
+                                              _lib.ptr(toks), _lib.ptr(lens), _lib.current_stream_ptr()),
+                       "showo_mmu_generate")
         return toks, lens
 
     @torch.no_grad()
     def mmu_generate(self, idx=None, input_embeddings=None, attention_mask=None, max_new_tokens=100, temperature=1.0,
-                     top_k=None, eot_token=None):
+                     top_k=None, eot_token=None, generator: torch.Generator = None):
         """modeling_showo.py:183-240: list of 0-d LongTensors for batch row 0, cut after eot_token.  (The reference
         only works for B == 1; for B > 1 use mmu_generate_batched.)"""
         toks, lens = self.mmu_generate_batched(idx, input_embeddings, attention_mask, max_new_tokens, temperature,
-                                               top_k, eot_token)
+                                               top_k, eot_token, generator)
         n = int(lens[0].item())
         return [toks[0, i] for i in range(n)]

@@ -474,8 +474,69 @@ def test_mmu_generate_batched_equals_rowwise_reference(tiny, dev):
     lst = m.mmu_generate(mm[1:2].to(dev), attention_mask=O.create_attention_mask_for_mmu(mm[1:2]).to(dev), max_new_tokens=n_new,
                          top_k=1, eot_token=eot)
     assert len(lst) == first + 1 and int(lst[-1]) == eot and all(t.dim() == 0 and t.dtype == torch.int64 for t in lst)
-    with pytest.raises(NotImplementedError):
-        m.mmu_generate(mm[:1].to(dev), attention_mask=O.create_attention_mask_for_mmu(mm[:1]).to(dev), top_k=None)
+    # sampled decode (top_k=None / k>1, modeling_showo.py:219-228), noise drawn by torch in the reference's order: every
+    # drawn token must be what the oracle's draw gives on the engine's own teacher-forced logits with the same noise
+    for top_k, temp in ((None, 0.8), (5, 1.3)):
+        gen = torch.Generator(device=dev).manual_seed(11)
+        toks_s, _ = m.mmu_generate_batched(mm.to(dev), attention_mask=O.create_attention_mask_for_mmu(mm).to(dev),
+                                           max_new_tokens=4, temperature=temp, top_k=top_k, generator=gen)
+        gen = torch.Generator(device=dev).manual_seed(11)
+        V = dims.vocab_size
+        expo = torch.empty(4, 3, V, device=dev)
+        for t in range(4):
+            expo[t].exponential_(1, generator=gen)
+        ok = 0
+        for t in range(4):
+            seq = torch.cat([mm.to(dev), toks_s[:, :t]], 1)
+            desc = [(0, 0, 0, 0, 259)] * 3
+            lg = m(seq, attention_mask=desc)[:, -1] / temp                      # prefill-path logits (bf16-level noise)
+            if top_k is not None:
+                v, _ = torch.topk(lg, top_k)
+                assert (lg.gather(1, toks_s[:, t:t + 1]) >= v[:, [-1]] - 2 * TOL_TINY / temp).all()
+                lg = lg.masked_fill(lg < v[:, [-1]], -float("inf"))
+            pick = O.categorical_from_exponential(torch.softmax(lg, -1), expo[t])
+            ok += int((pick == toks_s[:, t]).sum())
+        assert ok >= 10, ok                                                     # 12 draws; near-ties may flip a few
+    # no generator: the library's own Philox stream, reproducible under torch.manual_seed
+    torch.manual_seed(3)
+    a1, _ = m.mmu_generate_batched(mm.to(dev), attention_mask=O.create_attention_mask_for_mmu(mm).to(dev), max_new_tokens=4, top_k=None)
+    torch.manual_seed(3)
+    a2, _ = m.mmu_generate_batched(mm.to(dev), attention_mask=O.create_attention_mask_for_mmu(mm).to(dev), max_new_tokens=4, top_k=None)
+    assert torch.equal(a1, a2) and int(a1.min()) >= 0 and int(a1.max()) < dims.vocab_size
+
+
+@pytest.mark.parametrize("V,top_k,temp", [(58498, 0, 1.0), (58498, 1, 0.7), (58498, 5, 0.7), (58498, 200, 1.5), (1000, 1000, 1.0),
+                                          (1000, 4000, 2.0), (777, 13, 0.3)])
+def test_mmu_next_token_draw_bit_exact(lib, dev, V, top_k, temp):
+    """showo_mmu_sample == the reference's temperature / top-k / softmax / multinomial (modeling_showo.py:219-228) on
+    the same logits and the same Exp(1) noise (torch.multinomial(p,1) == argmax(p/q)); ties in the k-th value are kept."""
+    B = 16
+    g = torch.Generator(device=dev).manual_seed(V + top_k)
+    logits = torch.randn(B, V, device=dev, generator=g) * 3.0
+    logits[:, 5] = logits[:, 9]                                # exact ties
+    if 1 < top_k < V:
+        kth = logits.topk(top_k).values[:, -1]
+        logits[:, 17] = kth                                    # a duplicate of the k-th largest value stays in
+    expo = torch.empty(B, V, device=dev).exponential_(1, generator=g)
+    out = torch.full((B,), -1, dtype=torch.int64, device=dev)
+    _lib.check(lib.showo_mmu_sample(_lib.ptr(logits), V, B, V, temp, top_k, _lib.ptr(expo), 0, 0, _lib.ptr(out), S()))
+    lg = logits.cpu() / temp
+    if top_k > 0:
+        v, _ = torch.topk(lg, min(top_k, V))
+        lg[lg < v[:, [-1]]] = -float("inf")
+    ref = O.categorical_from_exponential(torch.softmax(lg, -1), expo.cpu())
+    assert torch.equal(out.cpu(), ref)
+    # Philox mode: in range, deterministic in (seed, step), different across steps
+    o1, o2, o3 = (torch.empty(B, dtype=torch.int64, device=dev) for _ in range(3))
+    _lib.check(lib.showo_mmu_sample(_lib.ptr(logits), V, B, V, temp, top_k, None, 77, 0, _lib.ptr(o1), S()))
+    _lib.check(lib.showo_mmu_sample(_lib.ptr(logits), V, B, V, temp, top_k, None, 77, 0, _lib.ptr(o2), S()))
+    _lib.check(lib.showo_mmu_sample(_lib.ptr(logits), V, B, V, temp, top_k, None, 77, 1, _lib.ptr(o3), S()))
+    assert torch.equal(o1, o2) and int(o1.min()) >= 0 and int(o1.max()) < V
+    if top_k != 1:
+        assert not torch.equal(o1, o3)
+    if 0 < top_k < V:
+        kept = lg.gather(1, o1.cpu()[:, None])
+        assert torch.isfinite(kept).all()
 
 
 def test_full_size_model_against_reference_golden(dev):
