@@ -8,6 +8,8 @@
 //   4. omni_attention        softmax(q K^T / 8 + mask) V  -> overwrites the q block (so buf = k | v | attn | act)
 //   5. gemm  [M,D+F] x W2^T  W2 = [Wdense | Wfc2] ([D, D+F]), A = buf[:, 2D:], epilogue x += acc + (b_dense + b_fc2)
 // i.e. two GEMMs per layer instead of six, and the attention/MLP outputs never round-trip HBM separately.
+#include <math.h>
+
 #include <atomic>
 #include <map>
 #include <set>
@@ -98,6 +100,7 @@ struct showo_engine {
     // workspaces
     int cap_rows = 0, cap_seq = 0, cap_L = 0; int64_t cap_logit_elems = 0;
     float* x = nullptr; bf16* xh = nullptr; bf16* buf = nullptr;
+    bf16* w1_slab = nullptr; bf16* w2_slab = nullptr;    // all layers' W1 / W2 back to back (one tensor map each)
     bf16* kcache = nullptr; bf16* vtcache = nullptr;     // [NL][cap_seq][H][cap_L][64] each
     showo_seq_mask_t* d_masks = nullptr;
     float* logits_ws = nullptr; float* conf_ws = nullptr; int* sampled_ws = nullptr;
@@ -184,6 +187,69 @@ static int run_layers(showo_engine* e, int n_seq, int rows_per_seq, int pos0, in
     return 0;
 }
 
+// One decode step (one token per sequence at position pos0) through all layers + the final LayerNorm into e->xh:
+// the persistent megakernel when the geometry allows it, else the per-kernel path.
+static int decode_step_layers(showo_engine* e, int B, int pos0, int max_keys, cudaStream_t st) {
+    DecodeMegaDesc d{};
+    std::vector<DecodeMegaLayer> hl((size_t)e->NL);
+    for (int l = 0; l < e->NL; ++l) {
+        const LayerW& w = e->layers[l];
+        hl[l] = DecodeMegaLayer{w.w1, w.w2, w.b1, w.b2, w.ln_g, w.ln_b, w.qg, w.qb, w.kg, w.kb,
+                                e->kcache + (size_t)l * layer_cache_stride(e), e->vtcache + (size_t)l * layer_cache_stride(e)};
+    }
+    d.layers = hl.data(); d.w1_slab = e->w1_slab; d.w2_slab = e->w2_slab; d.NL = e->NL; d.M = B; d.D = e->D; d.F = e->F; d.H = e->H; d.W1N = e->W1N;
+    d.x = e->x; d.xh = e->xh; d.buf = e->buf; d.ln_eps = e->cfg.ln_eps; d.fln_g = e->fln_g; d.fln_b = e->fln_b;
+    d.cos_tab = e->cos_tab; d.sin_tab = e->sin_tab;
+    d.pos0 = pos0; d.n_keys = pos0 + 1; d.Lmax = e->cap_L; d.max_keys = max_keys; d.cache_seqs = e->cap_seq;
+    d.masks = e->d_masks; d.scale = 0.125f;
+    static int check = -1, nl_lim = 0;
+    if (check < 0) {
+        const char* c = getenv("SHOWO_MEGA_CHECK"); check = c ? atoi(c) : 0;
+        const char* n = getenv("SHOWO_MEGA_NL"); nl_lim = n ? atoi(n) : 0;
+    }
+    if (check && decode_mega_supported(d)) {
+        // debug: run the per-kernel path and the megakernel from the same state and report the differences
+        const int nl = nl_lim > 0 && nl_lim < e->NL ? nl_lim : e->NL;
+        const size_t nx = (size_t)B * e->D, nb = (size_t)B * e->W1N;
+        std::vector<float> x0(nx), xr(nx), xm(nx);
+        std::vector<bf16> hr(nx), hm(nx), br(nb), bm(nb);
+        SHOWO_CUDA_OK(cudaStreamSynchronize(st));
+        SHOWO_CUDA_OK(cudaMemcpy(x0.data(), e->x, nx * 4, cudaMemcpyDeviceToHost));
+        const int keep = e->NL; e->NL = nl;
+        int rc = run_layers(e, B, 1, pos0, pos0 + 1, true, st);
+        e->NL = keep;
+        SHOWO_TRY(rc);
+        SHOWO_TRY(layernorm_bf16(e->x, e->fln_g, e->fln_b, e->cfg.ln_eps, e->xh, B, e->D, B, B, 0, st));
+        SHOWO_CUDA_OK(cudaStreamSynchronize(st));
+        SHOWO_CUDA_OK(cudaMemcpy(xr.data(), e->x, nx * 4, cudaMemcpyDeviceToHost));
+        SHOWO_CUDA_OK(cudaMemcpy(hr.data(), e->xh, nx * 2, cudaMemcpyDeviceToHost));
+        SHOWO_CUDA_OK(cudaMemcpy(br.data(), e->buf, nb * 2, cudaMemcpyDeviceToHost));
+        SHOWO_CUDA_OK(cudaMemcpy(e->x, x0.data(), nx * 4, cudaMemcpyHostToDevice));
+        d.NL = nl;
+        SHOWO_TRY(decode_mega_step(d, st));
+        SHOWO_CUDA_OK(cudaStreamSynchronize(st));
+        SHOWO_CUDA_OK(cudaMemcpy(xm.data(), e->x, nx * 4, cudaMemcpyDeviceToHost));
+        SHOWO_CUDA_OK(cudaMemcpy(hm.data(), e->xh, nx * 2, cudaMemcpyDeviceToHost));
+        SHOWO_CUDA_OK(cudaMemcpy(bm.data(), e->buf, nb * 2, cudaMemcpyDeviceToHost));
+        double dx = 0, dh = 0, dq = 0, da = 0, ax = 0;
+        for (size_t i = 0; i < nx; ++i) {
+            dx = std::max(dx, (double)fabsf(xr[i] - xm[i])); ax = std::max(ax, (double)fabsf(xr[i]));
+            dh = std::max(dh, (double)fabsf(__bfloat162float(hr[i]) - __bfloat162float(hm[i])));
+        }
+        for (int r = 0; r < B; ++r)
+            for (int c = 2 * e->D; c < e->W1N; ++c) {
+                const double v = fabsf(__bfloat162float(br[(size_t)r * e->W1N + c]) - __bfloat162float(bm[(size_t)r * e->W1N + c]));
+                if (c < 3 * e->D) dq = std::max(dq, v); else da = std::max(da, v);
+            }
+        fprintf(stderr, "[mega check] pos %d layers %d: max|dx| %.3e (|x| %.3e)  |dxh| %.3e  |d attn_out| %.3e  |d fc1_act| %.3e\n",
+                pos0, nl, dx, ax, dh, dq, da);
+        return 0;
+    }
+    if (decode_mega_supported(d)) return decode_mega_step(d, st);
+    SHOWO_TRY(run_layers(e, B, 1, pos0, pos0 + 1, true, st));
+    return layernorm_bf16(e->x, e->fln_g, e->fln_b, e->cfg.ln_eps, e->xh, B, e->D, B, B, 0, st);
+}
+
 static int upload_masks(showo_engine* e, const showo_seq_mask_t* masks_host, int n, cudaStream_t st) {
     SHOWO_CUDA_OK(cudaMemcpyAsync(e->d_masks, masks_host, (size_t)n * sizeof(showo_seq_mask_t), cudaMemcpyHostToDevice, st));
     return 0;
@@ -230,10 +296,13 @@ int showo_engine_create(const showo_config_t* cfg, int device, showo_engine_t** 
     SHOWO_TRY(dev_alloc(&e->fln_g, (size_t)D));
     SHOWO_TRY(dev_alloc(&e->fln_b, (size_t)D));
     e->layers.resize(e->NL);
-    for (auto& w : e->layers) {
-        SHOWO_TRY(dev_alloc(&w.w1, (size_t)e->W1N * D));
+    SHOWO_TRY(dev_alloc(&e->w1_slab, (size_t)e->NL * e->W1N * D));
+    SHOWO_TRY(dev_alloc(&e->w2_slab, (size_t)e->NL * D * e->W2K));
+    for (size_t li = 0; li < e->layers.size(); ++li) {
+        LayerW& w = e->layers[li];
+        w.w1 = e->w1_slab + li * (size_t)e->W1N * D;
+        w.w2 = e->w2_slab + li * (size_t)D * e->W2K;
         SHOWO_TRY(dev_alloc(&w.b1, (size_t)e->W1N));
-        SHOWO_TRY(dev_alloc(&w.w2, (size_t)D * e->W2K));
         SHOWO_TRY(dev_alloc(&w.b2, (size_t)D));
         SHOWO_TRY(dev_alloc(&w.b_dense, (size_t)D));
         SHOWO_TRY(dev_alloc(&w.b_fc2, (size_t)D));
@@ -268,9 +337,10 @@ int showo_engine_destroy(showo_engine_t* e) {
     cudaDeviceSynchronize();
     dev_free(e->embed); dev_free(e->head_w); dev_free(e->head_b); dev_free(e->head_b_img); dev_free(e->fln_g); dev_free(e->fln_b);
     for (auto& w : e->layers) {
-        dev_free(w.w1); dev_free(w.b1); dev_free(w.w2); dev_free(w.b2); dev_free(w.b_dense); dev_free(w.b_fc2);
+        dev_free(w.b1); dev_free(w.b2); dev_free(w.b_dense); dev_free(w.b_fc2);
         dev_free(w.ln_g); dev_free(w.ln_b); dev_free(w.qg); dev_free(w.qb); dev_free(w.kg); dev_free(w.kb);
     }
+    dev_free(e->w1_slab); dev_free(e->w2_slab);
     dev_free(e->cos_tab); dev_free(e->sin_tab); dev_free(e->stage);
     dev_free(e->x); dev_free(e->xh); dev_free(e->buf); dev_free(e->kcache); dev_free(e->vtcache); dev_free(e->d_masks);
     dev_free(e->logits_ws); dev_free(e->conf_ws); dev_free(e->sampled_ws); dev_free(e->tok_ws); dev_free(e->argmax_keys);
@@ -577,8 +647,7 @@ int showo_mmu_generate(showo_engine_t* e, const int64_t* ids_dev, const float* e
             note_launch();
             if (t == max_new_tokens - 1) break;
             SHOWO_TRY(embed_gather(e->tok_ws, 1, 0, e->embed, e->x, B, 1, D, V, st));
-            SHOWO_TRY(run_layers(e, B, 1, L0 + t, L0 + t + 1, true, st));
-            SHOWO_TRY(layernorm_bf16(e->x, e->fln_g, e->fln_b, e->cfg.ln_eps, e->xh, B, D, B, B, 0, st));
+            SHOWO_TRY(decode_step_layers(e, B, L0 + t, Ltot, st));
             SHOWO_TRY(gemm_skinny(ga, 4 /*SK_ARGMAX*/, nullptr, st));
         }
     } else {
@@ -599,8 +668,7 @@ int showo_mmu_generate(showo_engine_t* e, const int64_t* ids_dev, const float* e
         if (t == max_new_tokens - 1) break;
         // ---- decode one token per row at position L0 + t
         SHOWO_TRY(embed_gather(e->tok_ws, 1, 0, e->embed, e->x, B, 1, D, V, st));
-        SHOWO_TRY(run_layers(e, B, 1, L0 + t, L0 + t + 1, true, st));
-        SHOWO_TRY(layernorm_bf16(e->x, e->fln_g, e->fln_b, e->cfg.ln_eps, e->xh, B, D, B, B, 0, st));
+        SHOWO_TRY(decode_step_layers(e, B, L0 + t, Ltot, st));
         SHOWO_TRY(gemm_bf16(g, GEMM_BIAS_F32, st));
     }
     }

@@ -38,6 +38,31 @@ struct QkvFuse {
 int gemm_qkv_bf16(const GemmArgs& a, const QkvFuse& f, cudaStream_t st);
 // weight-streaming path for M <= 16 rows (decode); epi: 0 bias->bf16(+gelu), 1 resid+bias->f32, 2 bias->f32, 3 fused qkv (gemv.cu)
 int gemm_skinny(const GemmArgs& a, int epi, const QkvFuse* qf, cudaStream_t st);
+// stream-K fix-up workspace shared by the streamed skinny GEMM and the decode megakernel: partial tiles [grid][2][16x64]
+// fp32 and self-resetting per-tile tickets
+int skinny_workspace(int grid, int tiles, float** partials, int** tickets, cudaStream_t st);
+
+// One decode step (one new token per sequence, M <= 16 rows) of ALL layers in one persistent kernel (decode_mega.cu):
+// LayerNorm -> GEMM1 (+ q/k-LN, rotary, KV scatter, gelu) -> attention -> GEMM2 (+ residual) per layer, then the
+// final LayerNorm into xh.  Buffers as in run_layers (engine.cu).
+struct DecodeMegaLayer {
+    const bf16* w1; const bf16* w2;
+    const float *b1, *b2, *ln_g, *ln_b, *qg, *qb, *kg, *kb;
+    bf16 *kc, *vc;
+};
+struct DecodeMegaDesc {
+    const DecodeMegaLayer* layers;       // host array [NL]
+    const bf16* w1_slab; const bf16* w2_slab;   // layers' W1 [NL * W1N, D] and W2 [NL * D, D + F] back to back
+    int NL, M, D, F, H, W1N;
+    float* x; bf16* xh; bf16* buf;
+    float ln_eps; const float* fln_g; const float* fln_b;
+    const float* cos_tab; const float* sin_tab;
+    int pos0, n_keys, Lmax, max_keys;    // max_keys: longest context of this generation
+    int cache_seqs;                      // sequences per layer slab of the KV cache ([NL][cache_seqs][H][Lmax][64])
+    const showo_seq_mask_t* masks; float scale;
+};
+bool decode_mega_supported(const DecodeMegaDesc& d);
+int decode_mega_step(const DecodeMegaDesc& d, cudaStream_t st);
 
 // implicit-GEMM convolution on NHWC bf16 (3x3 pad 1, or 1x1), stride 1.  cin multiple of 64, weights [Cout_pad, taps*cin].
 struct ConvArgs {

@@ -505,6 +505,21 @@ def test_mmu_generate_batched_equals_rowwise_reference(tiny, dev):
     assert torch.equal(a1, a2) and int(a1.min()) >= 0 and int(a1.max()) < dims.vocab_size
 
 
+def test_decode_megakernel_equals_per_kernel_path(tiny, dev, monkeypatch):
+    """The persistent decode kernel (SHOWO_DECODE_MEGA=1: all layers of a step in one launch, weights and KV chunks through
+    one TMA ring, grid barriers between phases) produces the same tokens as the per-kernel decode path."""
+    dims, W, m = tiny
+    mm = FX.tiny_mmu_inputs(VOC)
+    mk = O.create_attention_mask_for_mmu(mm).to(dev)
+    monkeypatch.setenv("SHOWO_DECODE_MEGA", "0")
+    ref, _ = m.mmu_generate_batched(mm.to(dev), attention_mask=mk, max_new_tokens=12, top_k=1)
+    n0 = m.kernel_launches()
+    monkeypatch.setenv("SHOWO_DECODE_MEGA", "1")
+    got, _ = m.mmu_generate_batched(mm.to(dev), attention_mask=mk, max_new_tokens=12, top_k=1)
+    assert m.kernel_launches() < n0                      # one launch per step instead of four per layer
+    assert torch.equal(ref, got)
+
+
 @pytest.mark.parametrize("V,top_k,temp", [(58498, 0, 1.0), (58498, 1, 0.7), (58498, 5, 0.7), (58498, 200, 1.5), (1000, 1000, 1.0),
                                           (1000, 4000, 2.0), (777, 13, 0.3)])
 def test_mmu_next_token_draw_bit_exact(lib, dev, V, top_k, temp):
