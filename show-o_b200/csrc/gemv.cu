@@ -193,6 +193,21 @@ __global__ void __launch_bounds__(kSk2Threads, 1) skinny2_gemm_kernel(const __gr
 
     if (warp == 4) {
         // ------------------------------------------------------------------------------------------------ producer
+        if (lane > 0 && c_end > c_begin && p.bias) {
+            // idle lanes: pull the bias slices of this CTA's tiles into L2 now, so that the epilogue at the tail of the
+            // stream does not start with a DRAM miss (weights: no need to wait for the predecessor)
+            const int t0 = c_begin / sc.cpt, t1 = (c_end - 1) / sc.cpt;
+            for (int t = t0 + (lane - 1) / 2; t <= t1; t += 16) {
+                const int n = t * 64 + ((lane - 1) & 1) * 32;
+                if (n < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.bias + n));
+            }
+            if constexpr (EPI == SK_QKV) {        // q / k LayerNorm affine terms and the rotary row of this position
+                const float* w4[4] = {p.qf.q_gamma, p.qf.q_beta, p.qf.k_gamma, p.qf.k_beta};
+                if (lane <= 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(w4[(lane - 1) >> 1] + ((lane - 1) & 1) * 32));
+                else if (lane == 9) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.qf.cos_tab + (int64_t)p.qf.pos0 * 32));
+                else if (lane == 10) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.qf.sin_tab + (int64_t)p.qf.pos0 * 32));
+            }
+        }
         if (lane == 0) {
             const int n = c_end - c_begin;
             const int pre = n < kSk2Stages ? n : kSk2Stages;
