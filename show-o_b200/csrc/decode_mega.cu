@@ -417,7 +417,13 @@ struct DecodeMega {
     const void* cache_k = nullptr;                // first / last layer K-cache pointers the layer block was filled with
     const void* cache_k_last = nullptr;
 };
-static DecodeMega g_mega;
+static DecodeMega g_mega_dev[64];                 // one per device
+static DecodeMega& cur_mega() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return g_mega_dev[dev & 63];
+}
+#define g_mega (cur_mega())
 
 // Opt-in (SHOWO_DECODE_MEGA=1): parity-green, but on B200 it measures 1.85 ms per decode step against 1.47 ms for the
 // per-kernel path -- every phase still pays ~5-7 us of unhidden latency (gated X boxes at its head, the stream-K hand-over

@@ -158,17 +158,15 @@ static int run_layers(showo_engine* e, int n_seq, int rows_per_seq, int pos0, in
     const int D = e->D, F = e->F;
     for (int l = 0; l < e->NL; ++l) {
         const LayerW& w = e->layers[l];
-        // The skinny GEMM can normalise its own 16-row slab (GemmArgs::ln_x), but measured slower than the stand-alone
-        // LayerNorm launch (224 CTAs each re-reading 16 x 8 KB three times: 2.81 vs 2.14 ms per decode step) -> off.
-        const bool fuse_ln = false;
-        if (!fuse_ln) SHOWO_TRY(layernorm_bf16(e->x, w.ln_g, w.ln_b, e->cfg.ln_eps, e->xh, M, D, M, M, 0, st));
+        // (normalising the 16-row slab inside the decode GEMM was measured slower than this stand-alone launch: every CTA
+        // re-reads 16 x 8 KB three times -- 2.81 vs 2.14 ms per decode step)
+        SHOWO_TRY(layernorm_bf16(e->x, w.ln_g, w.ln_b, e->cfg.ln_eps, e->xh, M, D, M, M, 0, st));
         bf16* kc = e->kcache + (size_t)l * layer_cache_stride(e);
         bf16* vc = e->vtcache + (size_t)l * layer_cache_stride(e);
         // GEMM1 + (q/k LayerNorm, partial rotary, K / V^T cache scatter, gelu_new) in one kernel
         GemmArgs g1{};
         g1.A = e->xh; g1.lda = D; g1.B = w.w1; g1.ldb = D; g1.M = M; g1.N = e->W1N; g1.K = D;
         g1.out = e->buf; g1.ldc = e->W1N; g1.bias = w.b1;
-        if (fuse_ln) { g1.ln_x = e->x; g1.ln_g = w.ln_g; g1.ln_b = w.ln_b; g1.ln_eps = e->cfg.ln_eps; }
         QkvFuse qf{};
         qf.D = D; qf.H = e->H; qf.rows_per_seq = rows_per_seq; qf.pos0 = pos0; qf.Lmax = e->cap_L;
         qf.q_gamma = w.qg; qf.q_beta = w.qb; qf.k_gamma = w.kg; qf.k_beta = w.kb; qf.eps = e->cfg.ln_eps;

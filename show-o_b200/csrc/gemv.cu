@@ -54,38 +54,6 @@ __global__ void __launch_bounds__(kSkThreads) skinny_gemm_kernel(SkinnyParams p)
         }
     }
     // ---- X slab -> smem (rows >= M are zero) while the first weight chunks are in flight
-    if (p.ln_x != nullptr) {
-        // fused LayerNorm of the fp32 residual rows (phi.py:776 / :1065): 8 threads per row, two passes over the L2-resident row
-        const int r = tid >> 3, sub = tid & 7;
-        const float* xr = p.ln_x + (int64_t)r * p.K;
-        const bool rv = r < p.M;                 // rows >= M run the same (predicated) code: the shuffles stay convergent
-        float s = 0.f;
-        for (int c = sub * 4; c < p.K; c += 32) {
-            const float4 v = rv ? *reinterpret_cast<const float4*>(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-            s += (v.x + v.y) + (v.z + v.w);
-        }
-        s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4);
-        const float mean = s / (float)p.K;
-        float q = 0.f;
-        for (int c = sub * 4; c < p.K; c += 32) {
-            const float4 v = rv ? *reinterpret_cast<const float4*>(xr + c) : make_float4(mean, mean, mean, mean);
-            const float a0 = v.x - mean, a1 = v.y - mean, a2 = v.z - mean, a3 = v.w - mean;
-            q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
-        }
-        q += __shfl_xor_sync(0xffffffffu, q, 1); q += __shfl_xor_sync(0xffffffffu, q, 2); q += __shfl_xor_sync(0xffffffffu, q, 4);
-        const float rstd = rsqrtf(q / (float)p.K + p.ln_eps);
-        for (int c = sub * 4; c < p.K; c += 32) {
-            uint32_t lo = 0u, hi = 0u;
-            if (rv) {
-                const float4 v = *reinterpret_cast<const float4*>(xr + c);
-                const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.ln_g + c)), b4 = __ldg(reinterpret_cast<const float4*>(p.ln_b + c));
-                lo = pack_bf16((v.x - mean) * rstd * g4.x + b4.x, (v.y - mean) * rstd * g4.y + b4.y);
-                hi = pack_bf16((v.z - mean) * rstd * g4.z + b4.z, (v.w - mean) * rstd * g4.w + b4.w);
-            }
-            uint32_t* d = reinterpret_cast<uint32_t*>(xs + r * xs_stride + c);
-            d[0] = lo; d[1] = hi;
-        }
-    } else
     for (int i = tid; i < 16 * (p.kc / 8); i += kSkThreads) {
         const int r = i / (p.kc / 8), c = (i % (p.kc / 8)) * 8;
         uint4 v = make_uint4(0, 0, 0, 0);
@@ -264,8 +232,18 @@ static int skinny_variant() {
     return v;
 }
 
-static float* g_partials = nullptr; static size_t g_partials_cap = 0;
-static int* g_tickets = nullptr; static size_t g_tickets_cap = 0;
+// Fix-up workspace, one per device (the library runs one stream of decode work per device; the tickets reset themselves)
+struct SkinnyWs { float* partials = nullptr; size_t partials_cap = 0; int* tickets = nullptr; size_t tickets_cap = 0; };
+static SkinnyWs g_ws[64];
+static SkinnyWs& cur_ws() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return g_ws[dev & 63];
+}
+#define g_partials (cur_ws().partials)
+#define g_partials_cap (cur_ws().partials_cap)
+#define g_tickets (cur_ws().tickets)
+#define g_tickets_cap (cur_ws().tickets_cap)
 
 static int ensure_skinny_ws(size_t partial_floats, size_t tiles, cudaStream_t st) {
     if (partial_floats > g_partials_cap) {
@@ -337,7 +315,7 @@ int gemm_skinny(const GemmArgs& a, int epi, const QkvFuse* qf, cudaStream_t st) 
     SHOWO_CHECK(a.M >= 1 && a.M <= 16, "gemm_skinny: M must be in [1,16]");
     SHOWO_CHECK(a.K % 64 == 0 && a.lda % 8 == 0 && a.ldb % 8 == 0, "gemm_skinny: K must be a multiple of 64, lda/ldb of 8");
     const int tiles = cdiv(a.N, kSkTileN);
-    if (skinny_variant() == 2 && a.K % kSk2ChunkK == 0 && a.ln_x == nullptr)
+    if (skinny_variant() == 2 && a.K % kSk2ChunkK == 0)
         return gemm_skinny2(a, epi, qf, tiles, st);
     // enough CTAs to cover the SMs a few times over, K per split a multiple of 64 and <= 2048 (X slab <= 64 KB of smem)
     int splits = 1;
@@ -350,8 +328,7 @@ int gemm_skinny(const GemmArgs& a, int epi, const QkvFuse* qf, cudaStream_t st) 
     p.X = a.A; p.lda = a.lda; p.W = a.B; p.ldb = a.ldb; p.M = a.M; p.N = a.N; p.K = a.K; p.splits = splits; p.kc = a.K / splits;
     p.out = a.out; p.ldc = a.ldc; p.bias = a.bias; p.resid = a.resid; p.ldr = a.ldr; p.gelu_from = a.gelu_from;
     if (qf) p.qf = *qf;
-    p.ln_x = a.ln_x; p.ln_g = a.ln_g; p.ln_b = a.ln_b; p.ln_eps = a.ln_eps; p.argmax_keys = a.argmax_keys;
-    if (a.ln_x) SHOWO_CHECK(splits == 1 && a.K % 32 == 0, "gemm_skinny: fused LayerNorm needs the whole row in one split");
+    p.argmax_keys = a.argmax_keys;
     if (epi == SK_ARGMAX) SHOWO_CHECK(a.argmax_keys != nullptr, "gemm_skinny: argmax epilogue needs a key buffer");
     if (splits > 1) {
         const size_t need = (size_t)tiles * splits * 16 * 64;

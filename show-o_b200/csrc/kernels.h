@@ -22,7 +22,6 @@ struct GemmArgs {
     int gelu_from;                    // GEMM_BIAS_BF16: gelu_new on columns >= gelu_from (N = none)
     int block_n;                      // 0 = auto, else 64 / 128 / 256
     // decode-path extras (gemm_skinny only): fused input LayerNorm of fp32 rows, greedy argmax epilogue
-    const float* ln_x = nullptr; const float* ln_g = nullptr; const float* ln_b = nullptr; float ln_eps = 0.f;
     unsigned long long* argmax_keys = nullptr;
 };
 int gemm_bf16(const GemmArgs& a, GemmEpi epi, cudaStream_t st);

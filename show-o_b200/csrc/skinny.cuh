@@ -13,8 +13,6 @@ struct SkinnyParams {
     void* out; int64_t ldc; const float* bias; const float* resid; int64_t ldr; int gelu_from;
     float* partials; int* tickets;
     QkvFuse qf;
-    // optional fused input LayerNorm (splits == 1, K == row width): X is ignored, the slab is LN(ln_x) computed per CTA
-    const float* ln_x; const float* ln_g; const float* ln_b; float ln_eps;
     unsigned long long* argmax_keys;     // SK_ARGMAX: per-row packed (orderable logit, ~index) maxima, atomicMax'ed
 };
 

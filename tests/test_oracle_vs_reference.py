@@ -71,6 +71,16 @@ def test_mmu_generate_equals_reference(tiny):
         r = model.mmu_generate(mm, attention_mask=mk, max_new_tokens=5, top_k=1)
         o = O.mmu_generate(W, dims, mm, mk, max_new_tokens=5, top_k=1)
     assert torch.equal(torch.stack(r), torch.stack(o))
+    # sampled decode (modeling_showo.py:219-228): temperature, top-k filter, softmax, torch.multinomial(p, 1) -- whose
+    # single-sample path is the exponential race the oracle (and the CUDA kernel) restate; both draw from the global RNG
+    for top_k, temp in ((None, 0.8), (5, 1.3), (1, 0.5)):
+        torch.manual_seed(17)
+        with torch.no_grad():
+            r = model.mmu_generate(mm, attention_mask=mk, max_new_tokens=4, temperature=temp, top_k=top_k)
+        torch.manual_seed(17)
+        with torch.no_grad():
+            o = O.mmu_generate(W, dims, mm, mk, max_new_tokens=4, temperature=temp, top_k=top_k)
+        assert torch.equal(torch.stack(r), torch.stack(o)), (top_k, temp)
 
 
 def test_magvit_equals_reference():
