@@ -337,16 +337,22 @@ __global__ void __launch_bounds__(128) omni_attention_decode_bulk_kernel(AttnArg
     if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
     __syncthreads();
     pdl_trigger();
-    pdl_wait();                                  // this step's K / V rows and q come from the predecessor GEMM
+    // Only the row / column of the current token (position n_keys - 1) comes from the predecessor GEMM; everything older was
+    // written by earlier decode steps, so those bytes are requested BEFORE griddepcontrol.wait and stream in while the
+    // predecessor drains.
     const bf16* kbase = a.kcache + ((int64_t)seq * a.H + h) * (int64_t)a.Lmax * 64;
     const bf16* vbase = a.vtcache + ((int64_t)seq * a.H + h) * 64 * (int64_t)a.Lmax;
+    const int old_keys = a.n_keys - 1, old_cols = n_pad - 8;
     if (tid == 0) {
         mbar_arrive_expect_tx(&bars[0], (uint32_t)a.n_keys * 128u);
-        bulk_g2s(Ks, kbase, (uint32_t)a.n_keys * 128u, &bars[0]);
+        if (old_keys > 0) bulk_g2s(Ks, kbase, (uint32_t)old_keys * 128u, &bars[0]);
         mbar_arrive_expect_tx(&bars[1], 64u * (uint32_t)n_pad * 2u);
     }
     __syncthreads();
-    if (tid < 64) bulk_g2s(Vs + (size_t)tid * vstride, vbase + (int64_t)tid * a.Lmax, (uint32_t)n_pad * 2u, &bars[1]);
+    if (tid < 64 && old_cols > 0) bulk_g2s(Vs + (size_t)tid * vstride, vbase + (int64_t)tid * a.Lmax, (uint32_t)old_cols * 2u, &bars[1]);
+    pdl_wait();
+    if (tid == 0) bulk_g2s(Ks + (size_t)old_keys * 64, kbase + (int64_t)old_keys * 64, 128u, &bars[0]);
+    if (tid < 64) bulk_g2s(Vs + (size_t)tid * vstride + (size_t)old_cols * 2, vbase + (int64_t)tid * a.Lmax + old_cols, 16u, &bars[1]);
 
     const showo_seq_mask_t msk = a.masks[seq];
     const int qpos = a.pos0;
@@ -428,7 +434,8 @@ int omni_attention_decode(const AttnArgs& a, cudaStream_t st) {
     const int n_pad = (a.n_keys + 7) & ~7;
     const int vstride = n_pad * 2 + 16;
     const size_t smem = (size_t)n_pad * 128 + (size_t)64 * vstride + (size_t)n_pad * 4;
-    if (variant == 2 && a.Lmax % 8 == 0 && n_pad <= a.Lmax && smem <= 200 * 1024 && a.ld % 8 == 0) {
+    if (variant == 2 && a.Lmax % 8 == 0 && n_pad <= a.Lmax && smem <= 200 * 1024 && a.ld % 8 == 0 && a.pos0 == a.n_keys - 1 &&
+        a.rows_per_seq == 1) {
         static bool attr = false;
         if (!attr) {
             SHOWO_CUDA_OK(cudaFuncSetAttribute(omni_attention_decode_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
