@@ -121,6 +121,13 @@ SHOWO_API int showo_mmu_generate(showo_engine_t* e, const int64_t* ids_dev, cons
                        int64_t eot_token, uint64_t seed, const float* noise_expo_dev, int64_t* out_tokens_dev,
                        int32_t* out_lengths_dev, void* stream);
 
+/* One F.cross_entropy(ignore_index) term of Showo.forward (models/modeling_showo.py:81-100) on fp32 logits [n_seq, L, V]:
+ * rows (b, t), b < nb, t < nt pair logits[b0 + b, t0 + t, :] with labels[b0 + b, t0 + t + shift] (labels int64
+ * [n_seq, L]).  t2i: (0, B_t2i, max_seq_length + 1, L - max_seq_length - 1, 0); lm / mmu: (first row, count, 0, L - 1, 1).
+ * out2_dev: {mean over the counted rows (NaN when none, like torch), number of counted rows}. */
+SHOWO_API int showo_cross_entropy(const float* logits_dev, const int64_t* labels_dev, int64_t L, int V, int b0, int nb, int t0,
+                        int nt, int shift, int64_t ignore_index, float* out2_dev, void* stream);
+
 /* The next-token draw of mmu_generate on its own (models/modeling_showo.py:219-228), for parity tests:
  * logits_dev [B, ld >= V] fp32 -> out_tokens_dev [B] int64.  noise_expo_dev [B, V] or NULL (Philox(seed, step)). */
 SHOWO_API int showo_mmu_sample(const float* logits_dev, int64_t ld, int B, int V, float temperature, int top_k,

@@ -48,6 +48,7 @@ _PROTOS = {
     "showo_sampler_step": (_I, [_P, _P, _I, _I, _I, _F, _P, _I64, _I, _I, _I, _I, _F, _P, _P, C.c_uint64,
                                 C.c_uint32, _P, _P, _P]),
     "showo_mmu_generate": (_I, [_P, _P, _P, _I, _I, C.POINTER(SeqMask), _I, _I, _F, _I64, C.c_uint64, _P, _P, _P, _P]),
+    "showo_cross_entropy": (_I, [_P, _P, _I64, _I, _I, _I, _I, _I, _I, _I64, _P, _P]),
     "showo_mmu_sample": (_I, [_P, _I64, _I, _I, _F, _I, _P, C.c_uint64, C.c_uint32, _P, _P]),
     "showo_embed_tokens": (_I, [_P, _P, _I64, _P, _P]),
     "showo_kernel_launches": (_I64, [_P]),

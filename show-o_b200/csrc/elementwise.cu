@@ -1,6 +1,8 @@
 // Memory-bound helper kernels of the backbone: LayerNorm, embedding gather, q/k LayerNorm + partial rotary + KV-cache
 // scatter, fp32 -> bf16 weight packing.  All are coalesced, vectorised (16 B per thread per access) and sized so that
 // every SM gets several CTAs.
+#include <float.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -240,6 +242,85 @@ int qk_norm_rope_scatter(const QkRopeArgs& a, cudaStream_t st) {
     dim3 grid(n_seq * cdiv(a.rows_per_seq, 32), a.H);
     qk_norm_rope_scatter_kernel<<<grid, 256, 0, st>>>(a);
     note_launch();
+    SHOWO_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ cross-entropy
+// The three F.cross_entropy(ignore_index=-100) terms of Showo.forward (modeling_showo.py:81-100) over fp32 logits
+// [n_seq, L, V]: row (b, t) of a term pairs logits[b0 + b, t0 + t, :] with labels[b0 + b, t0 + t + shift].  One CTA per row,
+// one pass over the row (per-thread online max / sum-exp, merged across the block), per-row losses to a buffer and a
+// single-CTA fixed-order reduction -> mean over the non-ignored rows (0/0 = NaN for an empty term, like torch).
+struct CeRowsArgs {
+    const float* logits; const int64_t* labels; int64_t L; int V;
+    int b0, nb, t0, nt, shift; int64_t ignore_index;
+    float* row_loss; float* row_valid;
+};
+
+__global__ void __launch_bounds__(256) ce_rows_kernel(CeRowsArgs a) {
+    __shared__ float sm_m[8], sm_s[8];
+    const int row = blockIdx.x, b = row / a.nt, t = row % a.nt;
+    const int64_t label = a.labels[(int64_t)(a.b0 + b) * a.L + a.t0 + t + a.shift];
+    const int tid = threadIdx.x;
+    if (label == a.ignore_index) {                // CTA-uniform
+        if (tid == 0) { a.row_loss[row] = 0.f; a.row_valid[row] = 0.f; }
+        return;
+    }
+    const float* x = a.logits + ((int64_t)(a.b0 + b) * a.L + a.t0 + t) * (int64_t)a.V;
+    float m = -FLT_MAX, sum = 0.f;
+    for (int i = tid; i < a.V; i += 256) {
+        const float v = x[i];
+        if (v > m) { sum = sum * expf(m - v) + 1.f; m = v; }
+        else sum += expf(v - m);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, m, o), os = __shfl_xor_sync(0xffffffffu, sum, o);
+        const float nm = fmaxf(m, om);
+        sum = sum * expf(m - nm) + os * expf(om - nm);
+        m = nm;
+    }
+    if ((tid & 31) == 0) { sm_m[tid >> 5] = m; sm_s[tid >> 5] = sum; }
+    __syncthreads();
+    if (tid == 0) {
+        float M = sm_m[0], S = sm_s[0];
+        for (int w = 1; w < 8; ++w) {
+            const float nm = fmaxf(M, sm_m[w]);
+            S = S * expf(M - nm) + sm_s[w] * expf(sm_m[w] - nm);
+            M = nm;
+        }
+        const bool in_range = label >= 0 && label < a.V;
+        a.row_loss[row] = in_range ? (M + logf(S)) - x[label] : __int_as_float(0x7fc00000);
+        a.row_valid[row] = 1.f;
+    }
+}
+
+__global__ void __launch_bounds__(1024) ce_reduce_kernel(const float* row_loss, const float* row_valid, int n, float* out) {
+    __shared__ float s_l[1024], s_v[1024];
+    float l = 0.f, v = 0.f;
+    for (int i = threadIdx.x; i < n; i += 1024) { l += row_loss[i]; v += row_valid[i]; }
+    s_l[threadIdx.x] = l; s_v[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) { s_l[threadIdx.x] += s_l[threadIdx.x + o]; s_v[threadIdx.x] += s_v[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out[0] = s_l[0] / s_v[0]; out[1] = s_v[0]; }
+}
+
+int cross_entropy_mean(const float* logits, const int64_t* labels, int64_t L, int V, int b0, int nb, int t0, int nt, int shift,
+                       int64_t ignore_index, float* ws, float* out2, cudaStream_t st) {
+    const int n = nb * nt;
+    if (n <= 0) {                                 // empty slice: torch's mean over nothing is NaN
+        const float h[2] = {__builtin_nanf(""), 0.f};
+        SHOWO_CUDA_OK(cudaMemcpyAsync(out2, h, 8, cudaMemcpyHostToDevice, st));
+        SHOWO_CUDA_OK(cudaStreamSynchronize(st));
+        return 0;
+    }
+    CeRowsArgs a{logits, labels, L, V, b0, nb, t0, nt, shift, ignore_index, ws, ws + n};
+    ce_rows_kernel<<<n, 256, 0, st>>>(a);
+    ce_reduce_kernel<<<1, 1024, 0, st>>>(ws, ws + n, n, out2);
+    note_launch(); note_launch();
     SHOWO_CUDA_OK(cudaGetLastError());
     return 0;
 }

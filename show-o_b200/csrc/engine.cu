@@ -679,6 +679,19 @@ int showo_mmu_generate(showo_engine_t* e, const int64_t* ids_dev, const float* e
     return 0;
 }
 
+int showo_cross_entropy(const float* logits_dev, const int64_t* labels_dev, int64_t L, int V, int b0, int nb, int t0, int nt,
+                        int shift, int64_t ignore_index, float* out2_dev, void* stream) {
+    SHOWO_CHECK(logits_dev && labels_dev && out2_dev && V > 0 && L > 0 && nb >= 0 && nt >= 0, "cross_entropy: bad arguments");
+    SHOWO_CHECK(showo_device_count() > 0, "no sm_100 CUDA device visible: libshowo_b200 has no CPU fallback");
+    cudaStream_t st = (cudaStream_t)stream;
+    float* ws = nullptr;
+    const size_t n = (size_t)nb * nt;
+    if (n > 0) SHOWO_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&ws), 2 * n * 4, st));
+    const int rc = cross_entropy_mean(logits_dev, labels_dev, L, V, b0, nb, t0, nt, shift, ignore_index, ws, out2_dev, st);
+    if (ws) cudaFreeAsync(ws, st);
+    return rc;
+}
+
 int showo_mmu_sample(const float* logits_dev, int64_t ld, int B, int V, float temperature, int top_k,
                      const float* noise_expo_dev, uint64_t seed, uint32_t step, int64_t* out_tokens_dev, void* stream) {
     SHOWO_CHECK(logits_dev && out_tokens_dev && B > 0 && V > 0 && ld >= V, "mmu_sample: bad arguments");

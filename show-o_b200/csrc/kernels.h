@@ -87,6 +87,10 @@ int layernorm_bf16(const float* x, const float* gamma, const float* beta, float 
 int embed_gather(const int64_t* ids, int64_t ids_stride, int pos0, const bf16* table, float* x, int n_rows,
                  int rows_per_seq, int D, int vocab, cudaStream_t st);
 int f32_to_bf16(const float* src, bf16* dst, int64_t n, cudaStream_t st);
+// mean cross-entropy (ignore_index rows skipped) of logits[b0 + b, t0 + t, :] vs labels[b0 + b, t0 + t + shift], b < nb, t < nt;
+// ws: 2 * nb * nt floats of scratch; out2: {mean loss, number of counted rows}
+int cross_entropy_mean(const float* logits, const int64_t* labels, int64_t L, int V, int b0, int nb, int t0, int nt, int shift,
+                       int64_t ignore_index, float* ws, float* out2, cudaStream_t st);
 int copy_f32_to_f32_rows(const float* src, int64_t src_ld, float* dst, int64_t dst_ld, int rows, int cols, cudaStream_t st);
 // dst[r, c0 + c] = bf16(src[r, c])  -- packs weight blocks into the fused weight matrices
 int pack_block_bf16(const float* src, int64_t src_ld, bf16* dst, int64_t dst_ld, int rows, int cols, cudaStream_t st);

@@ -241,14 +241,22 @@ class Showo(nn.Module):
             _lib.check(lib.showo_forward(eng, _lib.ptr(ids), _lib.ptr(emb), B, L, _lib.masks_array(descs),
                                          _lib.ptr(logits), _lib.current_stream_ptr()), "showo_forward")
         if labels is not None:
-            import torch.nn.functional as F
             V = self.output_size
-            loss_t2i = F.cross_entropy(logits[:batch_size_t2i, max_seq_length + 1:].reshape(-1, V),
-                                       labels[:batch_size_t2i, max_seq_length + 1:].reshape(-1), ignore_index=-100)
-            sl = slice(batch_size_t2i, batch_size_t2i + batch_size_lm)
-            loss_lm = F.cross_entropy(logits[sl, :-1].reshape(-1, V), labels[sl, 1:].reshape(-1), ignore_index=-100)
-            loss_mmu = F.cross_entropy(logits[-batch_size_mmu:, :-1].reshape(-1, V),
-                                       labels[-batch_size_mmu:, 1:].reshape(-1), ignore_index=-100)
+            lab = labels.to(dev).long().contiguous()
+            out = torch.empty(3, 2, dtype=torch.float32, device=dev)
+            P = max_seq_length + 1
+            # the same row ranges as the reference's slices, quirks included: logits[-batch_size_mmu:] is the WHOLE batch when
+            # batch_size_mmu == 0 (python's -0), while an empty t2i / lm slice gives a NaN mean
+            bt = min(max(batch_size_t2i, 0), B)
+            lm0 = min(batch_size_t2i, B)
+            lm1 = min(batch_size_t2i + batch_size_lm, B)
+            mmu0 = B - batch_size_mmu if 0 < batch_size_mmu <= B else 0
+            terms = ((0, bt, P, L - P, 0), (lm0, max(lm1 - lm0, 0), 0, L - 1, 1), (mmu0, B - mmu0, 0, L - 1, 1))
+            with torch.cuda.device(dev):
+                for i, (b0, nb, t0, nt, shift) in enumerate(terms):
+                    _lib.check(lib.showo_cross_entropy(_lib.ptr(logits), _lib.ptr(lab), L, V, b0, nb, t0, max(nt, 0), shift, -100,
+                                                       _lib.ptr(out[i]), _lib.current_stream_ptr()), "showo_cross_entropy")
+            loss_t2i, loss_lm, loss_mmu = out[0, 0], out[1, 0], out[2, 0]
             return logits, loss_t2i, loss_lm, loss_mmu
         return logits
 

@@ -96,3 +96,41 @@ def magvit_inputs():
     codes = torch.from_numpy(r.integers(0, 8192, size=(1, 256)).astype("int64"))
     pixels = torch.from_numpy(r.random(size=(1, 3, 256, 256), dtype=np.float32)) * 2 - 1
     return codes, pixels
+
+
+TRAIN_COEFF = (1.0, 0.1, 1.0)          # loss = c0 * loss_t2i + c1 * loss_lm + c2 * loss_mmu (train.py:603-606 shape)
+
+
+def train_batch(voc):
+    """A mixed training batch the way training/train.py assembles it (2 t2i + 1 lm + 2 mmu rows, L = 387):
+    ids, additive mask [5,1,L,L], labels (-100 = ignored), and the three batch sizes.
+    t2i rows: image codes with ~60 % of the positions replaced by the mask token, labels = the true image-token ids there
+    (mask_or_random_replace_tokens semantics, training/utils.py:77-154); lm row: next-token labels over a full text row;
+    mmu rows: [mmu, soi, 256 codes, eoi, bos, text]: labels only on the text part."""
+    r = rng(21)
+    L = 387
+    cond, _ = O.make_t2i_prompts(2, voc, seed=22)
+    codes = torch.from_numpy(r.integers(0, 8192, size=(2, 256)).astype("int64")) + voc.image_offset
+    masked = torch.from_numpy(r.random(size=(2, 256), dtype=np.float32) < 0.6)
+    t2i = cond.clone()
+    t2i[:, 130:386] = torch.where(masked, torch.full_like(codes, voc.mask_token_id), codes)
+    lab_t2i = torch.full((2, L), -100, dtype=torch.int64)
+    lab_t2i[:, 130:386] = torch.where(masked, codes, torch.full_like(codes, -100))
+    lm = torch.from_numpy(r.integers(0, 50257, size=(1, L)).astype("int64"))
+    lm[0, 0] = O.BOS
+    lm[0, -1] = O.EOS
+    lab_lm = lm.clone()
+    mcodes = torch.from_numpy(r.integers(0, 8192, size=(2, 256)).astype("int64"))
+    mmu = O.make_mmu_prompts(2, voc, mcodes, q_len=L - 260, seed=23)
+    assert mmu.shape[1] == L
+    lab_mmu = mmu.clone()
+    lab_mmu[:, :260] = -100
+    ids = torch.cat([t2i, lm, mmu])
+    labels = torch.cat([lab_t2i, lab_lm, lab_mmu])
+    mask = torch.cat([O.create_attention_mask_predict_next(torch.cat([t2i, lm])), O.create_attention_mask_for_mmu(mmu)])
+    return ids, mask, labels, (2, 1, 2)
+
+
+TRAIN_GRAD_PROBES = ["showo.model.layers.0.self_attn.q_proj.weight", "showo.model.layers.0.self_attn.k_layernorm.weight",
+                     "showo.model.layers.1.mlp.fc2.bias", "showo.model.layers.1.self_attn.dense.weight",
+                     "showo.model.final_layernorm.weight", "showo.lm_head.bias"]

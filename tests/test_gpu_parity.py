@@ -505,6 +505,48 @@ def test_mmu_generate_batched_equals_rowwise_reference(tiny, dev):
     assert torch.equal(a1, a2) and int(a1.min()) >= 0 and int(a1.max()) < dims.vocab_size
 
 
+def test_cross_entropy_terms_against_torch(lib, dev):
+    """showo_cross_entropy == F.cross_entropy(ignore_index=-100) on the reference's three slices (modeling_showo.py:81-100),
+    including an empty slice (NaN) and a slice whose rows are all ignored."""
+    import torch.nn.functional as F
+    B, L, V, P = 4, 37, 58498, 9
+    g = torch.Generator(device=dev).manual_seed(3)
+    logits = torch.randn(B, L, V, device=dev, generator=g) * 2.0
+    labels = torch.randint(0, V, (B, L), device=dev, generator=g)
+    labels[torch.rand(B, L, device=dev, generator=g) < 0.3] = -100
+    labels[3] = -100
+    out = torch.zeros(2, device=dev)
+
+    def ce(b0, nb, t0, nt, shift):
+        _lib.check(lib.showo_cross_entropy(_lib.ptr(logits), _lib.ptr(labels), L, V, b0, nb, t0, nt, shift, -100, _lib.ptr(out), S()))
+        return out.clone().cpu()
+
+    got = ce(0, 2, P, L - P, 0)
+    ref = F.cross_entropy(logits[:2, P:].reshape(-1, V), labels[:2, P:].reshape(-1), ignore_index=-100)
+    assert abs(got[0].item() - ref.item()) < 2e-5 and int(got[1]) == int((labels[:2, P:] != -100).sum())
+    got = ce(2, 1, 0, L - 1, 1)
+    ref = F.cross_entropy(logits[2:3, :-1].reshape(-1, V), labels[2:3, 1:].reshape(-1), ignore_index=-100)
+    assert abs(got[0].item() - ref.item()) < 2e-5
+    assert torch.isnan(ce(2, 0, 0, L - 1, 1)[0])                      # empty slice: mean over nothing
+    assert torch.isnan(ce(3, 1, 0, L - 1, 1)[0])                      # every row ignored: 0 / 0
+    a, b2 = ce(0, B, 0, L - 1, 1), ce(0, B, 0, L - 1, 1)
+    assert torch.equal(a, b2)                                         # fixed-order reduction
+
+
+def test_forward_with_labels_losses_against_reference_golden(tiny, dev):
+    """Showo.forward(labels=...) on the mixed t2i / lm / mmu training batch (modeling_showo.py:81-100): logits from the CUDA
+    engine (three different mask kinds in one batch), the three cross-entropies against the reference's values."""
+    dims, W, m = tiny
+    z = FX.load("train_step.npz")
+    ids, mask, labels, (bt, bl, bm) = FX.train_batch(VOC)
+    logits, l1, l2, l3 = m(ids.to(dev), attention_mask=mask.to(dev), labels=labels.to(dev), batch_size_t2i=bt, batch_size_lm=bl,
+                           batch_size_mmu=bm, max_seq_length=128)
+    assert logits.shape == (5, 387, dims.vocab_size) and logits.dtype == torch.float32
+    assert np.abs(logits[:, ::32, ::997].cpu().numpy() - z["logits_slice"]).max() < TOL_TINY
+    got = np.array([l1.item(), l2.item(), l3.item()])
+    assert np.abs(got - z["losses"]).max() < TOL_TINY, (got, z["losses"])
+
+
 def test_decode_megakernel_equals_per_kernel_path(tiny, dev, monkeypatch):
     """The persistent decode kernel (SHOWO_DECODE_MEGA=1: all layers of a step in one launch, weights and KV chunks through
     one TMA ring, grid barriers between phases) produces the same tokens as the per-kernel decode path."""

@@ -174,3 +174,28 @@ def test_full_size_slice_matches_reference_golden():
     with torch.no_grad():
         lg = O.showo_logits(W, dims, input_ids=ids, add_mask=mask)[:, 130:386, VOC.image_offset:-1]
     assert np.abs(lg[:, ::16].numpy() - z["logits_slice"]).max() < 1e-4
+
+
+def test_train_step_losses_and_gradients_match_reference_golden():
+    """Showo.forward with labels (modeling_showo.py:81-100) and the gradients of the weighted loss on a mixed t2i / lm / mmu
+    batch: the oracle's restated forward, differentiated by autograd, against what the unmodified reference produced
+    (tests/golden/make_golden_train.py).  This is the pin the CUDA backward of the next round is tested against."""
+    z = FX.load("train_step.npz")
+    dims = O.PhiDims(**FX.TINY)
+    W = {k: v.clone().requires_grad_(True) for k, v in O.make_showo_weights(dims, seed=3).items()}
+    ids, mask, labels, (bt, bl, bm) = FX.train_batch(VOC)
+    logits = O.showo_logits(W, dims, input_ids=ids, add_mask=mask)
+    l1, l2, l3 = O.showo_losses(logits, labels, bt, bl, bm, 128)
+    assert np.allclose([l1.item(), l2.item(), l3.item()], z["losses"], rtol=2e-6, atol=0)
+    assert np.abs(logits[:, ::32, ::997].detach().numpy() - z["logits_slice"]).max() < 2e-5
+    c = FX.TRAIN_COEFF
+    (c[0] * l1 + c[1] * l2 + c[2] * l3).backward()
+    names = [str(n) for n in z["grad_names"]]
+    assert sorted(W.keys()) == names                                  # every parameter receives a gradient
+    norms = np.array([W[k].grad.double().norm().item() for k in names])
+    assert np.allclose(norms, z["grad_norms"], rtol=2e-4, atol=1e-9), np.abs(norms / z["grad_norms"] - 1).max()
+    for k in FX.TRAIN_GRAD_PROBES:
+        g = W[k].grad
+        got = (g[:8, :8] if g.dim() == 2 else g[:64]).numpy()
+        ref = z["grad:" + k]
+        assert np.abs(got - ref).max() <= 1e-4 * np.abs(ref).max() + 1e-9, k
