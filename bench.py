@@ -273,7 +273,8 @@ def run_ours(args):
         #      [mmu][soi] 256 codes [eoi][bos] 16 question ids, greedy 100-token decode, batch 16, KV cache)
         mmu = mmu_decode_bench(torch, model, vq, dev, peaks)
         # ---- CPU baseline: the oracle (port of the reference) on the host cores, bounded sample
-        cpu = None if os.environ.get("SHOWO_BENCH_SKIP_CPU") else cpu_reference_sample(steps=1, warmup=1, quiet=True)
+        # (rank 0 at N = 1 only: at N > 1 the other ranks are waiting in the closing barrier)
+        cpu = None if (world > 1 or os.environ.get("SHOWO_BENCH_SKIP_CPU")) else cpu_reference_sample(steps=1, warmup=1, quiet=True)
         clocks = sampler.summary()
         out = {
             "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
