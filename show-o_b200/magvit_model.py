@@ -108,15 +108,18 @@ class MAGVITv2(nn.Module):
 
     @classmethod
     def from_pretrained(cls, path, **kw):
-        import os
+        """Weights of `showlab/magvitv2` as laid out by save_pretrained (inference_t2i.py:61): single file or sharded."""
+        from . import checkpoint
         model = cls()
-        binp = os.path.join(path, "pytorch_model.bin")
-        sd = torch.load(binp, map_location="cpu") if os.path.exists(binp) else None
-        if sd is None:
-            from safetensors.torch import load_file
-            sd = load_file(os.path.join(path, "diffusion_pytorch_model.safetensors"))
-        model.load_state_dict(sd, strict=False)
+        sd = checkpoint.read_state_dict(path)
+        missing, _ = model.load_state_dict(sd, strict=False)
+        if missing:
+            raise KeyError(f"MAGVITv2.from_pretrained({path}): missing keys {missing[:5]}{'...' if len(missing) > 5 else ''}")
         return model
+
+    def save_pretrained(self, path, max_shard_bytes: int = 5 << 30):
+        from . import checkpoint
+        checkpoint.write_checkpoint(path, self.state_dict(), {"_class_name": "MAGVITv2"}, max_shard_bytes)
 
     @property
     def device(self):

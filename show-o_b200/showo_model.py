@@ -129,19 +129,24 @@ class Showo(nn.Module):
 
     @classmethod
     def from_pretrained(cls, path, **kwargs):
-        """Load `config.json` + `pytorch_model.bin` / safetensors written by the reference's save_pretrained."""
-        import json
-        import os
-        cfg = json.load(open(os.path.join(path, "config.json")))
-        model = cls(**{k: v for k, v in cfg.items() if not k.startswith("_")}, **kwargs)
-        binp = os.path.join(path, "pytorch_model.bin")
-        if os.path.exists(binp):
-            sd = torch.load(binp, map_location="cpu")
-        else:
-            from safetensors.torch import load_file
-            sd = load_file(os.path.join(path, "diffusion_pytorch_model.safetensors"))
-        model.load_state_dict(sd, strict=False)
+        """`config.json` + weights written by the reference's save_pretrained / the hub layout (single file or sharded
+        safetensors / .bin; inference_t2i.py:67).  The checkpoint must carry every parameter of the model."""
+        from . import checkpoint
+        cfg = checkpoint.read_config(path)
+        cfg.update(kwargs)
+        model = cls(**cfg)
+        sd = checkpoint.read_state_dict(path)
+        checkpoint.check_keys(model.state_dict().keys(), sd.keys(), f"Showo.from_pretrained({path})")
+        model.load_state_dict({k: v for k, v in sd.items() if "rotary_emb.inv_freq" not in k}, strict=True)
         return model
+
+    def save_pretrained(self, path, max_shard_bytes: int = 5 << 30):
+        """config.json + safetensors in the layout `from_pretrained` (and the reference's ModelMixin) reads back."""
+        from . import checkpoint
+        cfg = {"_class_name": "Showo", "w_clip_vit": bool(self.config.w_clip_vit), "vocab_size": int(self.vocab_size),
+               "llm_vocab_size": int(self.config.llm_vocab_size), "llm_model_path": "", "codebook_size": int(self.config.codebook_size),
+               "num_vq_tokens": int(self.config.num_vq_tokens), "load_from_showo": False}
+        checkpoint.write_checkpoint(path, self.state_dict(), cfg, max_shard_bytes)
 
     # ------------------------------------------------------------------ engine plumbing
     @property

@@ -141,3 +141,62 @@ def test_bench_reference_arm_contract_offline():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                         "--warmup", "0"], capture_output=True, text=True, env=env, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_from_pretrained_reads_single_sharded_and_bin_checkpoints(tmp_path):
+    """Showo / MAGVITv2.from_pretrained on the layouts save_pretrained and the hub produce (inference_t2i.py:61-68): one
+    safetensors file, a sharded safetensors set with an index, a torch .bin; a checkpoint that lacks a parameter is refused."""
+    import json
+    from safetensors.torch import save_file
+    kw = dict(hidden=128, n_layers=2, n_heads=2, ffn=256)
+    m = showo_b200.Showo(False, 58498, 50295, phi_dims=kw)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    cfg = {"_class_name": "Showo", "_diffusers_version": "0.30.1", "w_clip_vit": False, "vocab_size": 58498, "llm_vocab_size": 50295,
+           "llm_model_path": "microsoft/phi-1_5", "codebook_size": 8192, "num_vq_tokens": 256, "load_from_showo": False}
+
+    def check(d):
+        m2 = showo_b200.Showo.from_pretrained(str(d), phi_dims=kw)
+        sd2 = m2.state_dict()
+        assert sd2.keys() == sd.keys() and all(torch.equal(sd[k], sd2[k]) for k in sd)
+        assert m2.config.mask_token_id == 58497
+
+    d1 = tmp_path / "single"; d1.mkdir()
+    json.dump(cfg, open(d1 / "config.json", "w"))
+    save_file({**sd, "showo.model.layers.0.self_attn.rotary_emb.inv_freq": torch.ones(16)}, str(d1 / "diffusion_pytorch_model.safetensors"))
+    check(d1)
+    d2 = tmp_path / "sharded"; d2.mkdir()
+    json.dump(cfg, open(d2 / "config.json", "w"))
+    names = sorted(sd)
+    shards = {"diffusion_pytorch_model-00001-of-00002.safetensors": names[: len(names) // 2],
+              "diffusion_pytorch_model-00002-of-00002.safetensors": names[len(names) // 2:]}
+    for fn, ks in shards.items():
+        save_file({k: sd[k] for k in ks}, str(d2 / fn))
+    json.dump({"metadata": {}, "weight_map": {k: fn for fn, ks in shards.items() for k in ks}},
+              open(d2 / "diffusion_pytorch_model.safetensors.index.json", "w"))
+    check(d2)
+    d3 = tmp_path / "bin"; d3.mkdir()
+    json.dump(cfg, open(d3 / "config.json", "w"))
+    torch.save(sd, str(d3 / "pytorch_model.bin"))
+    check(d3)
+    d4 = tmp_path / "broken"; d4.mkdir()
+    json.dump(cfg, open(d4 / "config.json", "w"))
+    save_file({k: v for k, v in sd.items() if k != "showo.lm_head.bias"}, str(d4 / "diffusion_pytorch_model.safetensors"))
+    with pytest.raises(KeyError, match="lm_head.bias"):
+        showo_b200.Showo.from_pretrained(str(d4), phi_dims=kw)
+    # MAGVIT-v2
+    vq = showo_b200.MAGVITv2()
+    vsd = {k: v.detach().clone() for k, v in vq.state_dict().items()}
+    dv = tmp_path / "vq"; dv.mkdir()
+    save_file(vsd, str(dv / "diffusion_pytorch_model.safetensors"))
+    vq2 = showo_b200.MAGVITv2.from_pretrained(str(dv))
+    assert all(torch.equal(vsd[k], v) for k, v in vq2.state_dict().items())
+    first = sorted(vsd)[0]
+    save_file({k: v for k, v in vsd.items() if k != first}, str(dv / "diffusion_pytorch_model.safetensors"))
+    with pytest.raises(KeyError):
+        showo_b200.MAGVITv2.from_pretrained(str(dv))
+    # save_pretrained -> from_pretrained round trip, single file and forced sharding
+    for shard_bytes in (5 << 30, 200_000):
+        dr = tmp_path / f"rt{shard_bytes}"
+        m.save_pretrained(str(dr), max_shard_bytes=shard_bytes)
+        assert (shard_bytes > 10 ** 6) == os.path.exists(dr / "diffusion_pytorch_model.safetensors")
+        check(dr)
