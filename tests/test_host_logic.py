@@ -200,3 +200,20 @@ def test_from_pretrained_reads_single_sharded_and_bin_checkpoints(tmp_path):
         m.save_pretrained(str(dr), max_shard_bytes=shard_bytes)
         assert (shard_bytes > 10 ** 6) == os.path.exists(dr / "diffusion_pytorch_model.safetensors")
         check(dr)
+
+
+def test_clip_vision_tower_delegate_selects_penultimate_patch_features():
+    """`from models import ... CLIPVisionTower` surface (models/clip_encoder.py:39-51): penultimate layer, CLS dropped."""
+    from transformers import CLIPVisionConfig
+    from showo_b200 import CLIPVisionTower
+    cfg = CLIPVisionConfig(hidden_size=32, intermediate_size=64, num_hidden_layers=3, num_attention_heads=2, image_size=28, patch_size=14)
+    torch.manual_seed(0)
+    tower = CLIPVisionTower(cfg)
+    x = torch.randn(2, 3, 28, 28)
+    f = tower(x)
+    assert f.shape == (2, 4, 32) and tower.num_patches == 4 and tower.hidden_size == 32
+    ref = tower.vision_tower(x, output_hidden_states=True).hidden_states[-2][:, 1:]
+    assert torch.equal(f, ref)
+    assert all(not p.requires_grad for p in tower.parameters())
+    fl = tower([x[0], x[1]])
+    assert torch.allclose(torch.cat(fl), f, atol=1e-6)
