@@ -92,3 +92,18 @@ def test_magvit_equals_reference():
     with torch.no_grad():
         assert torch.equal(vq.get_code(x), MO.get_code(x, W))
         assert (vq.decode_code(ids) - MO.decode_code(ids, W)).abs().max().item() < 1e-5
+
+
+def test_mask_schedules_equal_reference(tiny):
+    """get_mask_chedule (sic) and every schedule it hands out, bit for bit on the fp32 grid the sampler evaluates them on
+    (models/sampling.py:39-78)."""
+    import showo_b200
+    _, _, _, mods = tiny
+    ts = [torch.tensor(float(i) / 18) for i in range(19)] + [torch.rand(7, generator=torch.Generator().manual_seed(1))]
+    for method, kw in (("cosine", {}), ("linear", {}), ("pow2", {}), ("pow0.5", {}), ("pow3", {}), ("sigmoid", {}),
+                       ("sigmoid", dict(start=-2, end=4, tau=0.7))):
+        ref, ours = mods.sampling.get_mask_chedule(method, **kw), showo_b200.get_mask_chedule(method, **kw)
+        for t in ts:
+            assert torch.equal(ref(t), ours(t)), (method, t)
+    with pytest.raises(ValueError):
+        showo_b200.get_mask_chedule("nope")
