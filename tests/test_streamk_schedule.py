@@ -76,3 +76,74 @@ def test_engine_shapes(tiles, cpt, grid):
 def test_sweep_small_shapes():
     for tiles, cpt, grid in itertools.product(range(1, 14), range(1, 12), (1, 2, 3, 5, 8, 13, 148)):
         simulate(tiles, cpt, grid)
+
+
+# ------------------------------------------------------------------------------------------------ decode megakernel
+def mega_items(cta, launch_grid, NL, W1N, D, F, M, H, n_keys):
+    """The ring items of one CTA of decode_mega_kernel in CONSUMPTION order (show-o_b200/csrc/decode_mega.cu): per layer the
+    GEMM1 chunks of its stream-K range, the 64-key chunks of its attention units, the GEMM2 chunks."""
+    t1, c1 = W1N // 64, D // 128
+    t2, c2 = D // 64, (D + F) // 128
+    g1, g2 = min(launch_grid, t1 * c1), min(launch_grid, t2 * c2)
+    b1, e1 = sk2_begin(t1 * c1, g1, cta), sk2_begin(t1 * c1, g1, cta + 1)
+    b2, e2 = sk2_begin(t2 * c2, g2, cta), sk2_begin(t2 * c2, g2, cta + 1)
+    units = list(range(cta, M * H, launch_grid))
+    n_chunks = (n_keys + 63) // 64
+    out = []
+    for l in range(NL):
+        out += [(l, 0, c // c1, c % c1) for c in range(b1, e1)]
+        out += [(l, 1, u, j) for u in units for j in range(n_chunks)]
+        out += [(l, 2, c // c2, c % c2) for c in range(b2, e2)]
+    return out, (b1, e1, c1, b2, e2, c2, len(units), n_chunks)
+
+
+def producer_sequence(cta, launch_grid, NL, geo):
+    """The producer's cursor walk (enter / advance lambdas of the kernel), re-stated with the same state variables."""
+    b1, e1, c1, b2, e2, c2, my_units, n_chunks = geo
+    cnt = [e1 - b1, my_units * n_chunks, e2 - b2]
+    if sum(cnt) == 0:
+        return []
+    st = dict(layer=0, ph=0, idx=0, tile=0, kc=0)
+
+    def enter():
+        while st["layer"] < NL and cnt[st["ph"]] == 0:
+            st["ph"] += 1
+            if st["ph"] == 3:
+                st["ph"], st["layer"] = 0, st["layer"] + 1
+        st["idx"] = 0
+        if st["ph"] == 0:
+            st["tile"], st["kc"] = b1 // c1, b1 % c1
+        elif st["ph"] == 2:
+            st["tile"], st["kc"] = b2 // c2, b2 % c2
+        else:
+            st["tile"], st["kc"] = 0, 0
+
+    seq = []
+    enter()
+    while st["layer"] < NL:
+        tile = cta + st["tile"] * launch_grid if st["ph"] == 1 else st["tile"]
+        seq.append((st["layer"], st["ph"], tile, st["kc"]))
+        lim = c1 if st["ph"] == 0 else (c2 if st["ph"] == 2 else n_chunks)
+        st["kc"] += 1
+        if st["kc"] == lim:
+            st["kc"], st["tile"] = 0, st["tile"] + 1
+        st["idx"] += 1
+        if st["idx"] == cnt[st["ph"]]:
+            st["ph"] += 1
+            if st["ph"] == 3:
+                st["ph"], st["layer"] = 0, st["layer"] + 1
+            enter()
+    return seq
+
+
+@pytest.mark.parametrize("geom", [dict(NL=24, W1N=14336, D=2048, F=8192, M=16, H=32, n_keys=289),
+                                  dict(NL=2, W1N=1792, D=256, F=1024, M=3, H=4, n_keys=271),
+                                  dict(NL=3, W1N=1792, D=256, F=1024, M=1, H=4, n_keys=64)])
+def test_megakernel_producer_issues_items_in_the_consumers_order(geom):
+    grid = 148
+    for cta in range(grid):
+        items, geo = mega_items(cta, grid, **geom)
+        assert producer_sequence(cta, grid, geom["NL"], geo) == items
+    # the gated attention chunk (the one holding the current token) is the last chunk of every unit
+    n_chunks = (geom["n_keys"] + 63) // 64
+    assert (geom["n_keys"] - 1) // 64 == n_chunks - 1
