@@ -119,6 +119,22 @@ def synth_prompts(torch, batch, seed):
     return cond, unc, descs_c + descs_u
 
 
+def dense_mask_like_reference(torch, ids, pad_id=50295, soi_id=50296, eoi_id=50297):
+    """What the reference's caller does before every t2i_generate (inference_t2i.py:300 -> create_attention_mask_predict_next,
+    training/prompting_utils.py:466-511, rm_pad_in_image=True): dense additive fp32 [2B, 1, L, L] on the device."""
+    n, L = ids.shape
+    is_pad = ids == pad_id
+    is_soi, is_eoi = ids == soi_id, ids == eoi_id
+    in_img = (torch.cumsum(is_soi, 1) - torch.cumsum(is_eoi, 1)) > 0
+    in_img = in_img | is_eoi
+    causal = torch.tril(torch.ones(L, L, dtype=torch.bool, device=ids.device))
+    allowed = causal[None] | in_img[:, :, None]
+    allowed = allowed & ~(is_pad[:, None, :] & ~is_pad[:, :, None])
+    add = torch.zeros(n, 1, L, L, dtype=torch.float32, device=ids.device)
+    add.masked_fill_(~allowed[:, None], float(torch.iinfo(torch.int64).min))
+    return add
+
+
 def gpu_random_weights(torch, dev, seed=0):
     """Random-init Phi-1.5-sized state_dict generated on the device (N(0,0.02) matrices, zero biases, LN 1/0 --
     PhiPreTrainedModel._init_weights, phi.py:833-842).  Yields (name, tensor) one at a time to bound memory."""
@@ -200,9 +216,14 @@ def run_ours(args):
         if e2e:
             ids_d.copy_(cond_pin, non_blocking=True)           # H2D of this step's prompts (pinned)
             unc_d.copy_(unc_pin, non_blocking=True)
+            # the reference's call shape (inference_t2i.py:300,321): the caller builds the DENSE [2B,1,L,L] mask and hands it to
+            # t2i_generate; the shim recovers + verifies the closed-form descriptors from it (showo_mask_descriptors, one
+            # kernel + a 24 B/sequence read-back) -- all inside the timed region
+            mask = dense_mask_like_reference(torch, torch.cat([ids_d, unc_d]))
         else:
             ids_d.copy_(cond_d0)                               # device-resident inputs
-        codes = model.t2i_generate(ids_d, unc_d, descs, guidance_scale=CFG_W, timesteps=T_STEPS, config=cfg)
+            mask = descs
+        codes = model.t2i_generate(ids_d, unc_d, mask, guidance_scale=CFG_W, timesteps=T_STEPS, config=cfg)
         imgs = vq.decode_code_uint8(torch.clamp(codes, 0, CODEBOOK - 1))
         if world > 1:
             dist.all_gather_into_tensor(gather_buf, imgs)
@@ -236,6 +257,20 @@ def run_ours(args):
     ms_e2e = timed(True, args.steps)
     sampler.stop_flag = True
     sampler.join(timeout=2)
+
+    # ---- secondaries run on EVERY rank (weak scaling like the headline) and are aggregated below
+    mmu_local = mmu_decode_bench(torch, model, vq, dev, measured_peaks(), seed=5 + rank)
+    mmu_agg = torch.tensor([mmu_local["ms_per_decode_step"], mmu_local["value"]], device=dev, dtype=torch.float64)
+    t512 = t2i512_bench(torch, dist, model, vq, dev, world, rank)
+    if world > 1:
+        mx = mmu_agg.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(mmu_agg, op=dist.ReduceOp.SUM)
+        mmu_local["ms_per_decode_step_max_over_ranks"] = round(float(mx[0]), 4)
+        mmu_local["value_rank0"] = mmu_local["value"]
+        # whole-job tokens/s: every rank decodes its own 16 sequences; time = the slowest rank's step
+        mmu_local["value"] = round(world * 16 * 1000.0 / float(mx[0]), 1)
+        mmu_local["n_gpus"] = world
 
     n_img = world * B_PER_GPU * args.steps
     value = n_img / (ms_dev / 1e3)
@@ -271,7 +306,9 @@ def run_ours(args):
         kern_tflops = tot_f / tot_ms / 1e9
         # ---- second half of BASELINE.json's metric: MMU decode tokens/s (configs[2]: 256x256 image -> get_code ->
         #      [mmu][soi] 256 codes [eoi][bos] 16 question ids, greedy 100-token decode, batch 16, KV cache)
-        mmu = mmu_decode_bench(torch, model, vq, dev, peaks)
+        mmu = mmu_local
+        if world == 1 and not os.environ.get("SHOWO_BENCH_SKIP_CPU"):
+            mmu["cpu_baseline"] = cpu_mmu_sample()
         # ---- CPU baseline: the oracle (port of the reference) on the host cores, bounded sample
         # (rank 0 at N = 1 only: at N > 1 the other ranks are waiting in the closing barrier)
         cpu = None if (world > 1 or os.environ.get("SHOWO_BENCH_SKIP_CPU")) else cpu_reference_sample(steps=1, warmup=1, quiet=True)
@@ -289,7 +326,9 @@ def run_ours(args):
             "gpu_launches": int(launches * args.steps),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": round(kern_tflops, 1), "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
-                         "frac": round(kern_tflops / peaks["bf16_burst"], 4), "traffic": ncu_traffic(),
+                         "frac": round(kern_tflops / peaks["bf16_burst"], 4),
+                         "job_frac": round((F_IMG + F_DEC) * value / world / 1e12 / peaks["bf16_sustained"], 4),
+                         "traffic": ncu_traffic(),
                          "kernel": "gemm_tcgen05_kernel (FLOP-weighted over the 24x2 layer GEMMs + image-vocab head of one "
                                    "denoise step, each shape timed alone with CUDA events)", "peak_source": peaks["source"],
                          "per_shape": per_shape},
@@ -298,6 +337,7 @@ def run_ours(args):
                              "unit": "TFLOP/s per GPU", "frac": round((F_IMG + F_DEC) * value / world / 1e12 / peaks["bf16_sustained"], 4)},
             "cpu_baseline": cpu,
             "secondary": mmu,
+            "secondary_t2i512": t512,
         }
         print(json.dumps(out), flush=True)
     if world > 1:
@@ -306,10 +346,96 @@ def run_ours(args):
     return out
 
 
-def mmu_decode_bench(torch, model, vq, dev, peaks, B=16, q_len=16, n_new=100):
+def t2i512_bench(torch, dist, model, vq, dev, world, rank, warm=1, steps=2):
+    """BASELINE.json configs[3]: showo_demo_512x512.yaml t2i, N = 1024 image tokens (L = 1155), 18 steps, CFG 5, 8 images per GPU
+    (batch 64 over 8 GPUs), decode_code -> uint8 [8,512,512,3], NCCL all-gather of the images for N > 1.  Device-resident ids."""
+    N5, L5, B5 = 1024, P_TXT + 1 + 1024 + 1, B_PER_GPU
+    g = torch.Generator().manual_seed(4321 + rank)
+    PAD, SOI, EOI, T2I, BOS = 50295, 50296, 50297, 50300, 50256
+    cond = torch.full((B5, L5), PAD, dtype=torch.int64)
+    unc = torch.full((B5, L5), PAD, dtype=torch.int64)
+    descs_c, descs_u = [], []
+    for b in range(B5):
+        n = int(torch.randint(8, 65, (1,), generator=g))
+        row = torch.cat([torch.tensor([T2I, BOS]), torch.randint(0, 50257, (n,), generator=g), torch.tensor([BOS])])
+        cond[b, P_TXT - row.numel():P_TXT] = row
+        unc[b, P_TXT - 3:P_TXT] = torch.tensor([T2I, BOS, BOS])
+        for r in (cond, unc):
+            r[b, P_TXT] = SOI
+            r[b, P_TXT + 1:P_TXT + 1 + N5] = V - 1
+            r[b, P_TXT + 1 + N5] = EOI
+        descs_c.append((P_TXT - row.numel(), P_TXT, L5, 0, 0))
+        descs_u.append((P_TXT - 3, P_TXT, L5, 0, 0))
+    descs = descs_c + descs_u
+    cfg5 = NS(model=NS(showo=NS(num_vq_tokens=N5, num_new_special_tokens=10, llm_vocab_size=50295)),
+              dataset=NS(preprocessing=NS(max_seq_length=P_TXT - 1)))
+    cond_d0, unc_d = cond.to(dev), unc.to(dev)
+    ids_d = torch.empty_like(cond_d0)
+    gather = torch.empty(world * B5, 512, 512, 3, dtype=torch.uint8, device=dev) if world > 1 else None
+
+    def step():
+        ids_d.copy_(cond_d0)
+        codes = model.t2i_generate(ids_d, unc_d, descs, guidance_scale=CFG_W, timesteps=T_STEPS, config=cfg5)
+        imgs = vq.decode_code_uint8(torch.clamp(codes, 0, CODEBOOK - 1), shape=(32, 32))
+        if world > 1:
+            dist.all_gather_into_tensor(gather, imgs)
+        return imgs
+    for _ in range(warm):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        imgs = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    assert tuple(imgs.shape) == (B5, 512, 512, 3)
+    f_img = T_STEPS * 2 * ((N5 + 2) * (G_TOK + A_PAIR * L5) + N5 * 2 * D * CODEBOOK) + 2 * P_TXT * (G_TOK + A_PAIR * P_TXT / 2) + 1205e9
+    value = world * B5 * steps / (ms / 1e3)
+    peaks = measured_peaks()
+    return {"metric": "t2i_512x512_images_per_sec_18steps_cfg5", "value": round(value, 3), "unit": UNIT, "n_gpus": world,
+            "ms_per_step": round(ms / steps, 2), "steps": steps, "warmup": warm,
+            "config": {"workload": "showo_demo_512x512.yaml t2i 512x512 (N=1024, L=1155), 18 steps, CFG 5, 8 images per GPU, "
+                                   "t2i_generate + decode_code + uint8 (+ all-gather)", "global_batch": world * B5, "seq_len": L5},
+            "roofline": {"bound": "tensor", "achieved": round(f_img * value / world / 1e12, 1), "peak": peaks["bf16_sustained"],
+                         "unit": "TFLOP/s per GPU", "frac": round(f_img * value / world / 1e12 / peaks["bf16_sustained"], 4),
+                         "algorithmic_tflop_per_image": round(f_img / 1e12, 2), "kernel": "whole job (SURVEY 8d F_img at N=1024 + decode)"}}
+
+
+def cpu_mmu_sample(n_tokens=2):
+    """The reference's MMU path on the host cores (modeling_showo.py:183-240: B = 1, NO KV cache, the whole sequence is
+    re-run for every new token; 16 prompts are processed one after the other): bounded sample = `n_tokens` greedy tokens of ONE
+    L0 = 276 row through the oracle port; tokens/s = 1 / (seconds per token), linear extrapolation to 16 x 100 tokens."""
+    import torch
+    from oracle import showo_oracle as O
+    cores = host_cores()
+    torch.set_num_threads(cores)
+    dims = O.PhiDims()
+    W = cpu_random_weights(torch, dims)
+    voc = O.ShowoVocab()
+    g = torch.Generator().manual_seed(5)
+    codes = torch.randint(0, CODEBOOK, (1, N_TOK), generator=g)
+    row = O.make_mmu_prompts(1, voc, codes, q_len=16, seed=6)
+    mk = O.create_attention_mask_for_mmu(row)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        O.mmu_generate(W, dims, row, mk, max_new_tokens=n_tokens, top_k=1)
+    dt = (time.perf_counter() - t0) / n_tokens
+    return {"value": round(1.0 / dt, 4), "unit": "tokens/s", "cores": cores, "kind": "port",
+            "sample": f"{n_tokens} greedy tokens of 1 row (L0=276, full re-forward per token, fp32) = {dt:.2f} s per token; "
+                      f"the reference decodes its 16 prompts sequentially, so tokens/s = 1 / t_token (extrapolated to 16 x 100 tokens)"}
+
+
+def mmu_decode_bench(torch, model, vq, dev, peaks, B=16, q_len=16, n_new=100, seed=5):
     """MMU decode tokens/s on rank 0.  decode time = t(100 tokens) - t(1 token), i.e. 99
     KV-cached decode steps of 16 sequences; prefill and get_code are reported separately."""
-    g = torch.Generator().manual_seed(5)
+    g = torch.Generator().manual_seed(seed)
     pixels = (torch.rand(B, 3, 256, 256, generator=g) * 2 - 1).to(dev)
 
     def ev():
@@ -349,29 +475,25 @@ def mmu_decode_bench(torch, model, vq, dev, peaks, B=16, q_len=16, n_new=100):
 
 
 # ======================================================================================================= reference arm (CPU)
-def cpu_reference_sample(steps: int, warmup: int, quiet: bool = False):
-    """Times the oracle (CPU port of the reference's fp32 path; the Python reference itself cannot travel to the GPU box)
-    on the host cores.  One sample = ONE of the 18 denoise-step forwards of ONE image as the reference executes it
-    (cond + uncond rows, L = 387, full 58498-way head) ; MAGVIT decode of one image is timed once; images/s is the
-    extrapolation 1 / (18 * t_step + t_decode)."""
-    import torch
-    from oracle import magvit_oracle as MO
-    from oracle import showo_oracle as O
+def host_cores():
+    """threads the process can actually use: the affinity mask, capped by the container's CPU quota (cgroup v2 cpu.max) -- on the
+    round-1 GPU box the mask showed 128 CPUs but the quota was 16 cores, and 128 threads ran 3x slower than 16."""
     try:
         cores = len(os.sched_getaffinity(0))
     except Exception:
         cores = os.cpu_count() or 1
-    # the container's CPU quota (cgroup v2 cpu.max) is what the process can actually use: on the round-1 GPU box the
-    # affinity mask showed 128 CPUs but the quota was 16 cores, and 128 threads ran 3x slower than 16 (tests/cpu_probe.py)
     try:
         quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
         if quota != "max":
             cores = max(1, min(cores, int(math.ceil(int(quota) / int(period)))))
     except Exception:
         pass
-    torch.set_num_threads(cores)
-    dims = O.PhiDims()
-    g = torch.Generator().manual_seed(0)
+    return cores
+
+
+def cpu_random_weights(torch, dims, seed=0):
+    """Random-init state_dict with the initialisation the tests use (N(0, 0.02) matrices, zero biases, LayerNorm 1 / 0)."""
+    g = torch.Generator().manual_seed(seed)
     W = {}
     Dd, Ff, Vv = dims.hidden, dims.ffn, dims.vocab_size
     W["showo.model.embed_tokens.weight"] = torch.randn(Vv, Dd, generator=g) * 0.02
@@ -388,10 +510,39 @@ def cpu_reference_sample(steps: int, warmup: int, quiet: bool = False):
     W["showo.model.final_layernorm.bias"] = torch.zeros(Dd)
     W["showo.lm_head.weight"] = torch.randn(Vv, Dd, generator=g) * 0.02
     W["showo.lm_head.bias"] = torch.zeros(Vv)
+    return W
+
+
+def cpu_reference_sample(steps: int, warmup: int, quiet: bool = False, full: bool = False):
+    """Times the oracle (CPU port of the reference's fp32 path; the Python reference itself cannot travel to the GPU box)
+    on the host cores.  Bounded mode: one sample = ONE of the 18 denoise-step forwards of ONE image as the reference executes
+    it (cond + uncond rows, L = 387, full 58498-way head), MAGVIT decode of one image timed once, images/s EXTRAPOLATED as
+    1 / (18 * t_step + t_decode).  full=True: one COMPLETE image (t2i_generate: 18 forwards + sampler, then decode_code)."""
+    import torch
+    from oracle import magvit_oracle as MO
+    from oracle import showo_oracle as O
+    cores = host_cores()
+    torch.set_num_threads(cores)
+    dims = O.PhiDims()
+    W = cpu_random_weights(torch, dims)
     voc = O.ShowoVocab()
     cond, unc = O.make_t2i_prompts(1, voc, seed=1234)
     ids = torch.cat([cond, unc])
     mask = O.create_attention_mask_predict_next(ids)
+    g = torch.Generator().manual_seed(0)
+    Wm = MO.make_magvit_weights(1)
+    if full:
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            codes = O.t2i_generate(W, dims, voc, cond.clone(), unc.clone(), mask, guidance_scale=CFG_W, timesteps=T_STEPS, generator=g)
+            t_gen = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            MO.decode_code(torch.clamp(codes, 0, CODEBOOK - 1), Wm)
+            t_dec = time.perf_counter() - t0
+        return {"value": round(1.0 / (t_gen + t_dec), 6), "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": f"1 complete image: t2i_generate (18 denoise steps, CFG 5, fp32, sampler included) = {t_gen:.1f} s + "
+                          f"decode_code = {t_dec:.2f} s; no extrapolation",
+                "t_step_s": round(t_gen / T_STEPS, 3), "t_decode_s": round(t_dec, 3), "extrapolated": False}
     times = []
     with torch.no_grad():
         for it in range(warmup + steps):
@@ -402,7 +553,6 @@ def cpu_reference_sample(steps: int, warmup: int, quiet: bool = False):
             dt = time.perf_counter() - t0
             if it >= warmup:
                 times.append(dt)
-        Wm = MO.make_magvit_weights(1)
         codes = torch.randint(0, CODEBOOK, (1, N_TOK), generator=g)
         t0 = time.perf_counter()
         MO.decode_code(codes, Wm)
@@ -411,21 +561,25 @@ def cpu_reference_sample(steps: int, warmup: int, quiet: bool = False):
     value = 1.0 / (T_STEPS * t_step + t_dec)
     return {"value": round(value, 6), "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{len(times)} x (1 of 18 denoise-step forwards of 1 image: cond+uncond rows, L=387, fp32, full head) "
-                      f"= {t_step:.2f} s each + 1 MAGVIT decode = {t_dec:.2f} s; images/s = 1/(18*t_step + t_decode)",
-            "t_step_s": round(t_step, 3), "t_decode_s": round(t_dec, 3)}
+                      f"= {t_step:.2f} s each + 1 MAGVIT decode = {t_dec:.2f} s; images/s EXTRAPOLATED = 1/(18*t_step + t_decode)",
+            "t_step_s": round(t_step, 3), "t_decode_s": round(t_dec, 3), "extrapolated": True}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cpu = cpu_reference_sample(steps=max(1, args.steps), warmup=min(args.warmup, 1))
-    t_step, t_dec = cpu["t_step_s"], cpu["t_decode_s"]
+    # --steps >= 18: one COMPLETE 18-step image (about a minute on 16 cores); fewer: bounded sample, extrapolated
+    full = args.steps >= T_STEPS
+    cpu = cpu_reference_sample(steps=max(1, args.steps), warmup=min(args.warmup, 1), full=full)
+    t_step = cpu["t_step_s"]
+    how = ("one complete image (18 steps + sampler + decode)" if full
+           else "bounded sample, EXTRAPOLATED: each step = 1 of 18 denoise-step forwards of 1 image")
     out = {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * t_step, 1), "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "showo_demo.yaml t2i 256x256, 18 denoise steps, CFG 5 -- reference fp32 CPU path (oracle port), "
-                                  "bounded sample: each step = 1 of 18 denoise-step forwards of 1 image", "parallelism": "cpu"},
+           "config": {"workload": "showo_demo.yaml t2i 256x256, 18 denoise steps, CFG 5 -- reference fp32 CPU path (oracle port), " + how,
+                      "parallelism": "cpu"},
            "cpu_baseline": cpu,
            "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)

@@ -76,6 +76,14 @@ SHOWO_API int showo_load_weight(showo_engine_t* e, const char* name, const float
 /* returns 0 when every tensor of the model has been loaded, else sets last_error to the first missing key */
 SHOWO_API int showo_weights_complete(showo_engine_t* e);
 
+/* The caller's dense attention mask (training/prompting_utils.py:466-511 create_attention_mask_predict_next, :591-624
+ * create_attention_mask_for_mmu[_vit]; inference_t2i.py:300, inference_mmu.py:146,166) -> closed form: one kernel derives the
+ * five integers per sequence from mask_dev [B, L, L] (elem_bytes 4: additive fp32, 0 = attend; 1: bool / uint8, non-zero =
+ * attend; batch stride in elements) and checks them against every non-pad query row.  mismatches_host[b] != 0 means the
+ * tensor is not an omni mask and must not be used with the descriptor.  Synchronises the stream. */
+SHOWO_API int showo_mask_descriptors(const void* mask_dev, int elem_bytes, int B, int L, int64_t batch_stride_elems,
+                           showo_seq_mask_t* out_host, int32_t* mismatches_host, void* stream);
+
 /* models/modeling_showo.py:59-79  Showo.forward (labels=None): logits fp32 [B, L, vocab].
  * Exactly one of ids_dev [B,L] (int64) / embeds_dev [B,L,hidden] (fp32) is non-NULL.  masks_host: B descriptors. */
 SHOWO_API int showo_forward(showo_engine_t* e, const int64_t* ids_dev, const float* embeds_dev, int B, int L,
@@ -136,6 +144,22 @@ SHOWO_API int showo_mmu_sample(const float* logits_dev, int64_t ld, int B, int V
 /* model.showo.model.embed_tokens(ids) as called from outside (inference_mmu.py:134-136): out fp32 [n, hidden] */
 SHOWO_API int showo_embed_tokens(showo_engine_t* e, const int64_t* ids_dev, int64_t n, float* out_dev, void* stream);
 
+/* ---------------------------------------------------------------- training step (training/train.py:589-612)
+ * Showo.forward with labels under autograd (models/modeling_showo.py:59-102): the same logits and cross-entropy terms as
+ * showo_forward + showo_cross_entropy, with every layer's activations kept in engine-owned buffers for showo_backward.
+ * terms_host: 3 x {b0, nb, t0, nt, shift} (t2i, lm, mmu) exactly as in showo_cross_entropy.  logits_out_dev [B, L, vocab]
+ * fp32 may be NULL (the logits then stay in an engine buffer).  losses_out_dev: float[3][2] = {mean, counted rows}. */
+SHOWO_API int showo_train_forward(showo_engine_t* e, const int64_t* ids_dev, const float* embeds_dev, int B, int L,
+                        const showo_seq_mask_t* masks_host, const int64_t* labels_dev, const int32_t* terms_host,
+                        int64_t ignore_index, float* logits_out_dev, float* losses_out_dev, void* stream);
+/* loss.backward() (training/train.py:612) for loss = sum_i loss_grads[i] * loss_i of the last showo_train_forward:
+ * gradients of every parameter go to an engine-owned fp32 buffer (read with showo_read_grad); dembeds_out_dev, optional
+ * [B, L, hidden] fp32, receives the gradient wrt the input embeddings (the mm_projector / embed_tokens side of
+ * train_w_clip_vit.py).  loss_grads_dev: float[3] on the device. */
+SHOWO_API int showo_backward(showo_engine_t* e, const float* loss_grads_dev, float* dembeds_out_dev, void* stream);
+/* gradient of one parameter of the reference state_dict (same names as showo_load_weight) -> out_dev (fp32, contiguous) */
+SHOWO_API int showo_read_grad(showo_engine_t* e, const char* name, float* out_dev, int64_t numel, void* stream);
+
 /* seconds spent / kernels launched by the last generate call (for bench.py's gpu_launches) */
 SHOWO_API int64_t showo_kernel_launches(showo_engine_t* e);
 
@@ -168,6 +192,11 @@ SHOWO_API int showo_attention_test(void* qkv_dev, int64_t ld, int n_seq, int row
                          const float* qg, const float* qb, const float* kg, const float* kb, float eps,
                          float rope_theta, int rotary_dim, void* kcache_dev, void* vtcache_dev, int Lmax, int n_keys,
                          const showo_seq_mask_t* masks_host, void* stream);
+/* backward of the omni-mask attention on its own: q/k (rotated), v, o, d_o bf16 [n_seq*L, H*64], lse fp32 [n_seq*L, H] in the
+ * exp2 domain (max*scale*log2e + log2(sum)); outputs dq, dk, dv bf16 [n_seq*L, H*64].  scale = 1/8. */
+SHOWO_API int showo_attention_bwd_test(const void* q_dev, const void* k_dev, const void* v_dev, const void* o_dev, const void* do_dev,
+                             const float* lse_dev, void* dq_dev, void* dk_dev, void* dv_dev, int n_seq, int L, int H,
+                             const showo_seq_mask_t* masks_host, void* stream);
 SHOWO_API int showo_layernorm_test(const float* x_dev, const float* gamma_dev, const float* beta_dev, float eps, void* out_bf16_dev,
                          int rows, int D, void* stream);
 /* NHWC bf16 3x3 (taps=9) or 1x1 (taps=1) convolution, stride 1, same padding; w [cout_pad, taps*cin] bf16 */

@@ -50,6 +50,11 @@ _PROTOS = {
     "showo_mmu_generate": (_I, [_P, _P, _P, _I, _I, C.POINTER(SeqMask), _I, _I, _F, _I64, C.c_uint64, _P, _P, _P, _P]),
     "showo_cross_entropy": (_I, [_P, _P, _I64, _I, _I, _I, _I, _I, _I, _I64, _P, _P]),
     "showo_mmu_sample": (_I, [_P, _I64, _I, _I, _F, _I, _P, C.c_uint64, C.c_uint32, _P, _P]),
+    "showo_mask_descriptors": (_I, [_P, _I, _I, _I, _I64, C.POINTER(SeqMask), C.POINTER(C.c_int32), _P]),
+    "showo_train_forward": (_I, [_P, _P, _P, _I, _I, C.POINTER(SeqMask), _P, C.POINTER(C.c_int32), _I64, _P, _P, _P]),
+    "showo_backward": (_I, [_P, _P, _P, _P]),
+    "showo_read_grad": (_I, [_P, C.c_char_p, _P, _I64, _P]),
+    "showo_attention_bwd_test": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, C.POINTER(SeqMask), _P]),
     "showo_embed_tokens": (_I, [_P, _P, _I64, _P, _P]),
     "showo_kernel_launches": (_I64, [_P]),
     "magvit_engine_create": (_I, [_I, C.POINTER(_P)]),

@@ -9,55 +9,9 @@
 // Attention is ~3 % of the step FLOPs at L=387, the tcgen05 GEMMs carry the rest.
 //
 // Decode kernel: one query per sequence against the KV cache (mmu_generate), HBM-bound, CUDA cores.
-#include "common.cuh"
-#include "kernels.h"
+#include "attn_common.cuh"
 
 namespace showo {
-
-__device__ __forceinline__ bool omni_allowed(const showo_seq_mask_t& m, int q, int k) {
-    const bool ok = (k <= q) | ((q >= m.full_begin) & (q < m.full_end)) | ((k >= m.win_begin) & (k < m.win_end));
-    return ok & !((k < m.pad_end) & (q >= m.pad_end));
-}
-// conservative: can ANY (q in [q_lo,q_hi], k in [k_lo,k_hi)) pair be allowed?
-__device__ __forceinline__ bool omni_tile_possible(const showo_seq_mask_t& m, int q_lo, int q_hi, int k_lo, int k_hi) {
-    if (k_hi <= m.pad_end && q_lo >= m.pad_end) return false;
-    const bool causal = k_lo <= q_hi;
-    const bool full = (q_hi >= m.full_begin) && (q_lo < m.full_end);
-    const bool win = (k_lo < m.win_end) && (k_hi > m.win_begin);
-    return causal || full || win;
-}
-
-// is EVERY (q in [q_lo,q_hi], k in [k_lo,k_hi)) pair allowed (so the per-element predicate can be skipped)?
-__device__ __forceinline__ bool omni_tile_all_allowed(const showo_seq_mask_t& m, int q_lo, int q_hi, int k_lo, int k_hi,
-                                                      int n_keys) {
-    if (k_hi > n_keys) return false;
-    if (k_lo < m.pad_end && q_hi >= m.pad_end) return false;       // some pad column x some row past the pads
-    const bool causal = (k_hi - 1) <= q_lo;
-    const bool full = (q_lo >= m.full_begin) && (q_hi < m.full_end);
-    const bool win = (k_lo >= m.win_begin) && (k_hi <= m.win_end);
-    return causal || full || win;
-}
-__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_row) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-                 : "r"(smem_u32(smem_row)));
-}
-__device__ __forceinline__ float ex2_approx(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
-__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile(
-        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
-constexpr int kTileK = 64;     // keys per smem tile
-constexpr int kPad = 72;       // padded smem row (elements) -> conflict-free 32-bit fragment loads
-constexpr float kNegBig = -1.0e30f;
 
 __global__ void __launch_bounds__(128) omni_attention_kernel(AttnArgs a) {
     __shared__ __align__(16) bf16 Ks[2][kTileK][kPad];
@@ -216,11 +170,17 @@ __global__ void __launch_bounds__(128) omni_attention_kernel(AttnArgs a) {
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
     const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;
+    bf16* orow0 = a.out ? a.out + ((int64_t)seq * a.rows_per_seq + r0) * a.out_ld + h * 64 : qrow0;
+    bf16* orow1 = a.out ? a.out + ((int64_t)seq * a.rows_per_seq + r1) * a.out_ld + h * 64 : qrow1;
 #pragma unroll
     for (int nd = 0; nd < 8; ++nd) {
         const int c = nd * 8 + t4 * 2;
-        if (r0_ok) *reinterpret_cast<uint32_t*>(qrow0 + c) = pack_bf16(o[nd][0] * i0, o[nd][1] * i0);
-        if (r1_ok) *reinterpret_cast<uint32_t*>(qrow1 + c) = pack_bf16(o[nd][2] * i1, o[nd][3] * i1);
+        if (r0_ok) *reinterpret_cast<uint32_t*>(orow0 + c) = pack_bf16(o[nd][0] * i0, o[nd][1] * i0);
+        if (r1_ok) *reinterpret_cast<uint32_t*>(orow1 + c) = pack_bf16(o[nd][2] * i1, o[nd][3] * i1);
+    }
+    if (a.lse != nullptr && t4 == 0) {          // exp2-domain log-sum-exp; a row without any allowed key gets +big (p = 0)
+        if (r0_ok) a.lse[((int64_t)seq * a.rows_per_seq + r0) * a.H + h] = l0 > 0.f ? m0 * sc + log2f(l0) : 1.0e30f;
+        if (r1_ok) a.lse[((int64_t)seq * a.rows_per_seq + r1) * a.H + h] = l1 > 0.f ? m1 * sc + log2f(l1) : 1.0e30f;
     }
 }
 
@@ -228,7 +188,7 @@ int omni_attention(const AttnArgs& a, cudaStream_t st) {
     if (a.n_seq == 0 || a.rows_per_seq == 0) return 0;
     SHOWO_CHECK(a.Lmax % 64 == 0, "attention: Lmax must be a multiple of 64");
     SHOWO_CHECK(a.n_keys <= a.Lmax, "attention: n_keys exceeds the cache length");
-    if (attention_tc_supported(a)) return omni_attention_tc(a, st);      // whole score row fits in TMEM: tcgen05 path
+    if (a.out == nullptr && attention_tc_supported(a)) return omni_attention_tc(a, st);      // whole score row fits in TMEM: tcgen05 path
     dim3 grid(cdiv(a.rows_per_seq, 64), a.H, a.n_seq);
     SHOWO_CUDA_OK(launch_kernel(omni_attention_kernel, grid, dim3(128), 0, st, 1, a));
     note_launch();

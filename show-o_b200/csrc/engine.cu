@@ -16,8 +16,7 @@
 #include <string>
 #include <vector>
 
-#include "common.cuh"
-#include "kernels.h"
+#include "engine_state.h"
 
 namespace showo {
 
@@ -57,57 +56,9 @@ __global__ void mmu_lengths_kernel(const int64_t* toks, int max_new, int64_t eot
     lens[b] = n;
 }
 
-template <class T>
-static int dev_alloc(T** p, size_t n) {
-    *p = nullptr;
-    if (n == 0) return 0;
-    SHOWO_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
-    return 0;
-}
-template <class T>
-static void dev_free(T*& p) {
-    if (p) cudaFree(p);
-    p = nullptr;
-}
-
 }  // namespace showo
 
 using namespace showo;
-
-struct LayerW {
-    bf16* w1 = nullptr;   // [3D+F, D]
-    float* b1 = nullptr;  // [3D+F]
-    bf16* w2 = nullptr;   // [D, D+F]
-    float* b2 = nullptr;  // [D]  (= dense.bias + fc2.bias)
-    float* b_dense = nullptr; float* b_fc2 = nullptr;
-    float* ln_g = nullptr; float* ln_b = nullptr;
-    float* qg = nullptr; float* qb = nullptr; float* kg = nullptr; float* kb = nullptr;
-};
-
-struct showo_engine {
-    showo_config_t cfg{};
-    int device = 0;
-    int D = 0, H = 0, F = 0, NL = 0, V = 0, W1N = 0, W2K = 0;
-    bf16* embed = nullptr;
-    bf16* head_w = nullptr; float* head_b = nullptr;
-    float* head_b_img = nullptr;                         // 16B-aligned copy of head_b[image_offset : image_offset + C]
-    float* fln_g = nullptr; float* fln_b = nullptr;
-    std::vector<LayerW> layers;
-    float* cos_tab = nullptr; float* sin_tab = nullptr;
-    std::set<std::string> loaded;
-    bool finalized = false;
-    float* stage = nullptr; size_t stage_cap = 0;       // fp32 staging for weight uploads
-    // workspaces
-    int cap_rows = 0, cap_seq = 0, cap_L = 0; int64_t cap_logit_elems = 0;
-    float* x = nullptr; bf16* xh = nullptr; bf16* buf = nullptr;
-    bf16* w1_slab = nullptr; bf16* w2_slab = nullptr;    // all layers' W1 / W2 back to back (one tensor map each)
-    bf16* kcache = nullptr; bf16* vtcache = nullptr;     // [NL][cap_seq][H][cap_L][64] each
-    showo_seq_mask_t* d_masks = nullptr;
-    float* logits_ws = nullptr; float* conf_ws = nullptr; int* sampled_ws = nullptr;
-    int64_t* tok_ws = nullptr; int64_t tok_ws_cap = 0;
-    unsigned long long* argmax_keys = nullptr;            // [16] packed (logit, ~index) maxima of the fused greedy head
-    int64_t launches_last = 0;
-};
 
 static int engine_set_device(showo_engine* e) {
     SHOWO_CUDA_OK(cudaSetDevice(e->device));
@@ -260,6 +211,10 @@ static int check_ready(showo_engine* e) {
     return 0;
 }
 
+int engine_check_ready(showo_engine* e) { return check_ready(e); }
+int engine_upload_masks(showo_engine* e, const showo_seq_mask_t* masks_host, int n, cudaStream_t st) { return upload_masks(e, masks_host, n, st); }
+int engine_ensure_ws(showo_engine* e, int rows, int n_seq, int L, int64_t logit_elems, cudaStream_t st) { return ensure_ws(e, rows, n_seq, L, logit_elems, st); }
+
 extern "C" {
 
 const char* showo_last_error(void) { return last_error_cstr(); }
@@ -342,6 +297,7 @@ int showo_engine_destroy(showo_engine_t* e) {
     dev_free(e->cos_tab); dev_free(e->sin_tab); dev_free(e->stage);
     dev_free(e->x); dev_free(e->xh); dev_free(e->buf); dev_free(e->kcache); dev_free(e->vtcache); dev_free(e->d_masks);
     dev_free(e->logits_ws); dev_free(e->conf_ws); dev_free(e->sampled_ws); dev_free(e->tok_ws); dev_free(e->argmax_keys);
+    if (e->train) train_state_destroy(e->train);
     delete e;
     return 0;
 }
@@ -419,6 +375,7 @@ int showo_load_weight(showo_engine_t* e, const char* name_c, const float* data, 
     SHOWO_CUDA_OK(cudaStreamSynchronize(st));
     e->loaded.insert(name);
     e->finalized = false;
+    ++e->weights_version;
     return 0;
 }
 

@@ -1,0 +1,73 @@
+// Engine state shared by the inference orchestration (engine.cu) and the training step (train.cu).
+#pragma once
+#include <set>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace showo {
+template <class T>
+inline int dev_alloc(T** p, size_t n) {
+    *p = nullptr;
+    if (n == 0) return 0;
+    SHOWO_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
+    return 0;
+}
+template <class T>
+inline void dev_free(T*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+
+int64_t launches_total();
+struct TrainState;
+void train_state_destroy(TrainState* t);
+}  // namespace showo
+
+using showo::bf16;
+
+struct LayerW {
+    bf16* w1 = nullptr;   // [3D+F, D]
+    float* b1 = nullptr;  // [3D+F]
+    bf16* w2 = nullptr;   // [D, D+F]
+    float* b2 = nullptr;  // [D]  (= dense.bias + fc2.bias)
+    float* b_dense = nullptr; float* b_fc2 = nullptr;
+    float* ln_g = nullptr; float* ln_b = nullptr;
+    float* qg = nullptr; float* qb = nullptr; float* kg = nullptr; float* kb = nullptr;
+};
+
+struct showo_engine {
+    showo_config_t cfg{};
+    int device = 0;
+    int D = 0, H = 0, F = 0, NL = 0, V = 0, W1N = 0, W2K = 0;
+    bf16* embed = nullptr;
+    bf16* head_w = nullptr; float* head_b = nullptr;
+    float* head_b_img = nullptr;                         // 16B-aligned copy of head_b[image_offset : image_offset + C]
+    float* fln_g = nullptr; float* fln_b = nullptr;
+    std::vector<LayerW> layers;
+    float* cos_tab = nullptr; float* sin_tab = nullptr;
+    std::set<std::string> loaded;
+    bool finalized = false;
+    int64_t weights_version = 0;                         // bumped by every showo_load_weight (train.cu re-derives its transposed copies)
+    float* stage = nullptr; size_t stage_cap = 0;       // fp32 staging for weight uploads
+    // workspaces
+    int cap_rows = 0, cap_seq = 0, cap_L = 0; int64_t cap_logit_elems = 0;
+    float* x = nullptr; bf16* xh = nullptr; bf16* buf = nullptr;
+    bf16* w1_slab = nullptr; bf16* w2_slab = nullptr;    // all layers' W1 / W2 back to back (one tensor map each)
+    bf16* kcache = nullptr; bf16* vtcache = nullptr;     // [NL][cap_seq][H][cap_L][64] each
+    showo_seq_mask_t* d_masks = nullptr;
+    float* logits_ws = nullptr; float* conf_ws = nullptr; int* sampled_ws = nullptr;
+    int64_t* tok_ws = nullptr; int64_t tok_ws_cap = 0;
+    unsigned long long* argmax_keys = nullptr;            // [16] packed (logit, ~index) maxima of the fused greedy head
+    int64_t launches_last = 0;
+    showo::TrainState* train = nullptr;                  // training-step buffers (train.cu), allocated on first use
+};
+
+
+// helpers defined in engine.cu
+int engine_check_ready(showo_engine* e);
+int engine_upload_masks(showo_engine* e, const showo_seq_mask_t* masks_host, int n, cudaStream_t st);
+int engine_ensure_ws(showo_engine* e, int rows, int n_seq, int L, int64_t logit_elems, cudaStream_t st);

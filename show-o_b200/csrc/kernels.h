@@ -117,6 +117,10 @@ struct AttnArgs {
     int n_keys;                          // keys [0, n_keys) are valid in the cache
     const showo_seq_mask_t* masks;       // device array [n_seq]
     float scale;                         // 1/sqrt(head_dim)
+    // training step (train.cu): output rows go to `out` (row stride out_ld) instead of overwriting q, and the row's
+    // log-sum-exp in the exp2 domain (max * scale * log2e + log2(sum)) is saved at lse[row * H + head]
+    bf16* out = nullptr; int64_t out_ld = 0;
+    float* lse = nullptr;
 };
 int omni_attention(const AttnArgs& a, cudaStream_t st);
 // tcgen05/TMEM/TMA variant for n_keys <= 448 (attention_tc.cu); omni_attention() dispatches to it when supported
@@ -124,6 +128,26 @@ bool attention_tc_supported(const AttnArgs& a);
 int omni_attention_tc(const AttnArgs& a, cudaStream_t st);
 // single-query (decode) variant: one query row per sequence at position n_keys-1
 int omni_attention_decode(const AttnArgs& a, cudaStream_t st);
+
+// backward of the omni-mask attention (attention_bwd.cu), flash-style: the scores are recomputed per 64 x 64 tile from the
+// rotated q / k rows, P = exp2(S * scale * log2e - lse), dS = P o (dP - delta); dK / dV by key block, dQ by query block
+// (two passes, no atomics, deterministic).  All operands row-major bf16 [n_seq * L, ld] with head h at columns [64h, 64h+64).
+struct AttnBwdArgs {
+    const bf16* q; int64_t q_ld;
+    const bf16* k; int64_t k_ld;
+    const bf16* v; int64_t v_ld;
+    const bf16* o; int64_t o_ld;         // forward output
+    const bf16* d_o; int64_t do_ld;      // gradient of the loss wrt the forward output
+    const float* lse;                    // [n_seq * L, H] from the forward (exp2 domain)
+    float* delta;                        // [n_seq * L, H] workspace: rowsum(dO o O)
+    bf16* dq; int64_t dq_ld;
+    bf16* dk; int64_t dk_ld;
+    bf16* dv; int64_t dv_ld;
+    int n_seq, H, L;
+    const showo_seq_mask_t* masks;       // device array [n_seq]
+    float scale;
+};
+int omni_attention_backward(const AttnBwdArgs& a, cudaStream_t st);
 
 // ------------------------------------------------------------------ sampler (sampler.cu)
 struct SamplerArgs {

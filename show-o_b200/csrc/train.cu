@@ -1,0 +1,843 @@
+// Training step of the Show-o backbone behind the C ABI: Showo.forward with labels under autograd + loss.backward()
+// (models/modeling_showo.py:59-102, training/train.py:589-612; PhiDecoderLayer phi.py:774-790 differentiated).
+//
+// Forward (activations kept for the backward, per layer l, M = B * L token rows):
+//   xs[l] fp32 residual stream -> LN (+ row mean / rstd) -> xh[l] bf16 -> GEMM1 (tcgen05, + bias) -> pre[l] = k | v | q | fc1 (raw, bf16)
+//   -> q/k LayerNorm(64) + partial rotary -> qrot[l], krot[l] (+ the K / V^T tiles the forward attention kernel reads)
+//   -> gelu_new(fc1) and omni attention (+ row log-sum-exp) -> a2[l] = attn | act -> GEMM2 (+ bias + residual) -> xs[l+1];
+//   final LN -> head GEMM -> logits -> the three cross-entropy means.
+// Backward, all contractions on the tcgen05 GEMM of gemm_tcgen05.cuh (bf16 operands, fp32 accumulate, fp32 gradients):
+//   dgrad  dX = dY W        : A = dY [M, N] row-major, B = W^T kept as a second bf16 copy (w1t / w2t / head_wt), so both operands
+//                             stay K-contiguous for TMA / UMMA (cost: 2.9 GB of HBM and one transpose per weight update);
+//   wgrad  dW = dY^T A      : both operands transposed into [features, M] scratch (token dimension = K) by a tiled transpose;
+//                             bias gradients are row sums of the transposed dY;
+//   attention              : attention_bwd.cu (recompute S per tile, dK/dV by key block, dQ by query block);
+//   elementwise            : d gelu_new, rotary^T + LayerNorm(64) backward, LayerNorm(D) backward (+ two-stage deterministic
+//                             column reductions for all LayerNorm weights), softmax - onehot for the three loss terms, embedding
+//                             scatter-add.
+// Gradients land in one engine-owned fp32 buffer in the packed layout of the weights (W1 = [Wk; Wv; Wq; Wfc1], W2 = [Wdense | Wfc2])
+// and are read back per reference parameter name with showo_read_grad.
+#include <float.h>
+
+#include "engine_state.h"
+
+namespace showo {
+
+// ------------------------------------------------------------------------------------------------ LayerNorm (training)
+template <int kMaxVec>
+__global__ void __launch_bounds__(256) layernorm_train_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, float eps, bf16* __restrict__ out,
+                                                              float2* __restrict__ stats, int n_rows, int D) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n_rows) return;
+    const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)warp * D);
+    const int nvec = D >> 7;
+    float4 v[kMaxVec];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i)
+        if (i < nvec) { v[i] = xr[i * 32 + lane]; s += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
+    const float mean = warp_sum(s) / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i)
+        if (i < nvec) {
+            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+            q += (a * a + b * b) + (c * c + d * d);
+        }
+    const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+    if (lane == 0) stats[warp] = make_float2(mean, rstd);
+    uint2* orow = reinterpret_cast<uint2*>(out + (int64_t)warp * D);
+    const float4* g4 = reinterpret_cast<const float4*>(gamma);
+    const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i)
+        if (i < nvec) {
+            const float4 g = __ldg(g4 + i * 32 + lane), b = __ldg(b4 + i * 32 + lane);
+            uint2 pk;
+            pk.x = pack_bf16((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
+            pk.y = pack_bf16((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+            orow[i * 32 + lane] = pk;
+        }
+}
+
+// dx_io[r] (+)= rstd * (g o dy - mean(g o dy) - xhat * mean(g o dy o xhat))        (one warp per row)
+template <int kMaxVec>
+__global__ void __launch_bounds__(256) ln_bwd_dx_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                        const float2* __restrict__ stats, const float* __restrict__ gamma,
+                                                        float* __restrict__ dx_io, int accumulate, int n_rows, int D) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n_rows) return;
+    const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)warp * D);
+    const float4* dr = reinterpret_cast<const float4*>(dy + (int64_t)warp * D);
+    const float4* g4 = reinterpret_cast<const float4*>(gamma);
+    const float2 st = stats[warp];
+    const int nvec = D >> 7;
+    float4 xh[kMaxVec], gd[kMaxVec];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i)
+        if (i < nvec) {
+            const float4 xv = xr[i * 32 + lane], dv = dr[i * 32 + lane], g = __ldg(g4 + i * 32 + lane);
+            xh[i] = make_float4((xv.x - st.x) * st.y, (xv.y - st.x) * st.y, (xv.z - st.x) * st.y, (xv.w - st.x) * st.y);
+            gd[i] = make_float4(dv.x * g.x, dv.y * g.y, dv.z * g.z, dv.w * g.w);
+            s1 += (gd[i].x + gd[i].y) + (gd[i].z + gd[i].w);
+            s2 += (gd[i].x * xh[i].x + gd[i].y * xh[i].y) + (gd[i].z * xh[i].z + gd[i].w * xh[i].w);
+        }
+    const float m1 = warp_sum(s1) / (float)D, m2 = warp_sum(s2) / (float)D;
+    float4* orow = reinterpret_cast<float4*>(dx_io + (int64_t)warp * D);
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i)
+        if (i < nvec) {
+            float4 o = make_float4(st.y * (gd[i].x - m1 - xh[i].x * m2), st.y * (gd[i].y - m1 - xh[i].y * m2),
+                                   st.y * (gd[i].z - m1 - xh[i].z * m2), st.y * (gd[i].w - m1 - xh[i].w * m2));
+            if (accumulate) {
+                const float4 p = orow[i * 32 + lane];
+                o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+            }
+            orow[i * 32 + lane] = o;
+        }
+}
+
+// partial[blockIdx.y][0][c] = sum_r dy[r,c] * xhat[r,c], partial[blockIdx.y][1][c] = sum_r dy[r,c] over this block's rows
+__global__ void __launch_bounds__(256) ln_bwd_param_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                           const float2* __restrict__ stats, int n_rows, int D,
+                                                           float* __restrict__ partial) {
+    __shared__ float sg[8][33], sb[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
+    float ag = 0.f, ab = 0.f;
+    if (c < D)
+        for (int r = blockIdx.y * 8 + ty; r < n_rows; r += 8 * gridDim.y) {
+            const float2 st = stats[r];
+            const float d = dy[(int64_t)r * D + c];
+            ag += d * (x[(int64_t)r * D + c] - st.x) * st.y;
+            ab += d;
+        }
+    sg[ty][tx] = ag; sb[ty][tx] = ab;
+    __syncthreads();
+    if (ty == 0 && c < D) {
+#pragma unroll
+        for (int j = 1; j < 8; ++j) { ag += sg[j][tx]; ab += sb[j][tx]; }
+        partial[((int64_t)blockIdx.y * 2 + 0) * D + c] = ag;
+        partial[((int64_t)blockIdx.y * 2 + 1) * D + c] = ab;
+    }
+}
+// out[i] = sum_s partial[s][i]   (fixed order -> deterministic)
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, int S, int n, float* __restrict__ out) {
+    __shared__ float sm[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + tx;
+    float a = 0.f;
+    if (i < n)
+        for (int s = ty; s < S; s += 8) a += partial[(int64_t)s * n + i];
+    sm[ty][tx] = a;
+    __syncthreads();
+    if (ty == 0 && i < n) {
+#pragma unroll
+        for (int j = 1; j < 8; ++j) a += sm[j][tx];
+        out[i] = a;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ q/k LayerNorm(64) + rotary
+struct QkTrainArgs {
+    const bf16* pre; int64_t ld;          // [M, ld]: k at col 0, v at col D, q at col 2D (raw projections + bias)
+    int n_seq, L, H, D;
+    const float *qg, *qb, *kg, *kb; float eps;
+    const float* cos_tab; const float* sin_tab;
+    bf16* qrot; bf16* krot;               // [M, D] row-major
+    bf16* kcache; bf16* vtcache; int Lmax;   // forward attention operands ([seq][H][Lmax][64], [seq][H][64][Lmax])
+    // backward
+    const bf16* dq; const bf16* dk;       // [M, D] gradients wrt the rotated q / k
+    bf16* dpre;                           // [M, ld]: receives d k_raw at col 0 and d q_raw at col 2D
+    float* partial;                       // [gridDim.x][4][64]: q gamma, q beta, k gamma, k beta
+};
+
+__global__ void __launch_bounds__(256) qk_rope_train_kernel(QkTrainArgs a) {
+    __shared__ bf16 vs[32][66];
+    const int blocks_per_seq = (a.L + 31) >> 5;
+    const int seq = blockIdx.x / blocks_per_seq, rb = blockIdx.x % blocks_per_seq, h = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int D = a.D;
+    const float2 qg = reinterpret_cast<const float2*>(a.qg)[lane], qb = reinterpret_cast<const float2*>(a.qb)[lane];
+    const float2 kg = reinterpret_cast<const float2*>(a.kg)[lane], kb = reinterpret_cast<const float2*>(a.kb)[lane];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int rl = warp * 4 + i, pos = rb * 32 + rl;
+        if (pos >= a.L) continue;
+        const int64_t m = (int64_t)seq * a.L + pos;
+        const bf16* row = a.pre + m * a.ld + h * 64;
+        const __nv_bfloat162 k2 = reinterpret_cast<const __nv_bfloat162*>(row)[lane];
+        const __nv_bfloat162 v2 = reinterpret_cast<const __nv_bfloat162*>(row + D)[lane];
+        const __nv_bfloat162 q2 = reinterpret_cast<const __nv_bfloat162*>(row + 2 * D)[lane];
+        *reinterpret_cast<__nv_bfloat162*>(&vs[rl][2 * lane]) = v2;
+        float2 kf = __bfloat1622float2(k2), qf = __bfloat1622float2(q2);
+        const float mk = warp_sum(kf.x + kf.y) * (1.f / 64.f), mq = warp_sum(qf.x + qf.y) * (1.f / 64.f);
+        kf.x -= mk; kf.y -= mk; qf.x -= mq; qf.y -= mq;
+        const float rk = rsqrtf(warp_sum(kf.x * kf.x + kf.y * kf.y) * (1.f / 64.f) + a.eps);
+        const float rq = rsqrtf(warp_sum(qf.x * qf.x + qf.y * qf.y) * (1.f / 64.f) + a.eps);
+        kf.x = kf.x * rk * kg.x + kb.x; kf.y = kf.y * rk * kg.y + kb.y;
+        qf.x = qf.x * rq * qg.x + qb.x; qf.y = qf.y * rq * qg.y + qb.y;
+        const float pkx = __shfl_xor_sync(0xffffffffu, kf.x, 8), pky = __shfl_xor_sync(0xffffffffu, kf.y, 8);
+        const float pqx = __shfl_xor_sync(0xffffffffu, qf.x, 8), pqy = __shfl_xor_sync(0xffffffffu, qf.y, 8);
+        if (lane < 16) {
+            const float2 c = reinterpret_cast<const float2*>(a.cos_tab + (int64_t)pos * 32)[lane];
+            const float2 s = reinterpret_cast<const float2*>(a.sin_tab + (int64_t)pos * 32)[lane];
+            const float sgn = lane < 8 ? -1.f : 1.f;
+            kf.x = kf.x * c.x + sgn * pkx * s.x; kf.y = kf.y * c.y + sgn * pky * s.y;
+            qf.x = qf.x * c.x + sgn * pqx * s.x; qf.y = qf.y * c.y + sgn * pqy * s.y;
+        }
+        const __nv_bfloat162 qo = __floats2bfloat162_rn(qf.x, qf.y), ko = __floats2bfloat162_rn(kf.x, kf.y);
+        reinterpret_cast<__nv_bfloat162*>(a.qrot + m * D + h * 64)[lane] = qo;
+        reinterpret_cast<__nv_bfloat162*>(a.krot + m * D + h * 64)[lane] = ko;
+        reinterpret_cast<__nv_bfloat162*>(a.kcache + (((int64_t)seq * a.H + h) * a.Lmax + pos) * 64)[lane] = ko;
+    }
+    __syncthreads();
+    const int pos = rb * 32 + lane;
+    if (pos < a.L) {
+        bf16* vt = a.vtcache + ((int64_t)seq * a.H + h) * 64 * (int64_t)a.Lmax + pos;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int d = warp + 8 * i;
+            vt[(int64_t)d * a.Lmax] = vs[lane][d];
+        }
+    }
+}
+
+// backward of rotary (transpose of the rotation) and of LayerNorm(64); one warp per (row, head), the block walks all heads
+__global__ void __launch_bounds__(256) qk_rope_bwd_kernel(QkTrainArgs a) {
+    __shared__ float red[8][8][32];
+    const int blocks_per_seq = (a.L + 31) >> 5;
+    const int seq = blockIdx.x / blocks_per_seq, rb = blockIdx.x % blocks_per_seq;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int D = a.D;
+    const float2 qg = reinterpret_cast<const float2*>(a.qg)[lane], kg = reinterpret_cast<const float2*>(a.kg)[lane];
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int h = 0; h < a.H; ++h) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int pos = rb * 32 + warp * 4 + i;
+            if (pos >= a.L) continue;
+            const int64_t m = (int64_t)seq * a.L + pos;
+            float2 c = make_float2(1.f, 1.f), s = make_float2(0.f, 0.f);
+            if (lane < 16) {
+                c = reinterpret_cast<const float2*>(a.cos_tab + (int64_t)pos * 32)[lane];
+                s = reinterpret_cast<const float2*>(a.sin_tab + (int64_t)pos * 32)[lane];
+            }
+            const float sgn = lane < 8 ? 1.f : -1.f;          // transpose of the forward rotation
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {                     // t = 0: q, t = 1: k
+                const bf16* gsrc = (t == 0 ? a.dq : a.dk) + m * D + h * 64;
+                const bf16* raw = a.pre + m * a.ld + (t == 0 ? 2 * D : 0) + h * 64;
+                float2 dz = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(gsrc)[lane]);
+                const float px = __shfl_xor_sync(0xffffffffu, dz.x, 8), py = __shfl_xor_sync(0xffffffffu, dz.y, 8);
+                if (lane < 16) { dz.x = dz.x * c.x + sgn * px * s.x; dz.y = dz.y * c.y + sgn * py * s.y; }
+                float2 xr = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(raw)[lane]);
+                const float mu = warp_sum(xr.x + xr.y) * (1.f / 64.f);
+                xr.x -= mu; xr.y -= mu;
+                const float rstd = rsqrtf(warp_sum(xr.x * xr.x + xr.y * xr.y) * (1.f / 64.f) + a.eps);
+                const float2 xh = make_float2(xr.x * rstd, xr.y * rstd);
+                acc[4 * t + 0] += dz.x * xh.x; acc[4 * t + 1] += dz.y * xh.y;      // d gamma (dims 2l, 2l+1)
+                acc[4 * t + 2] += dz.x; acc[4 * t + 3] += dz.y;                    // d beta
+                const float2 gm = t == 0 ? qg : kg;
+                const float2 gd = make_float2(dz.x * gm.x, dz.y * gm.y);
+                const float m1 = warp_sum(gd.x + gd.y) * (1.f / 64.f);
+                const float m2 = warp_sum(gd.x * xh.x + gd.y * xh.y) * (1.f / 64.f);
+                const float ox = rstd * (gd.x - m1 - xh.x * m2), oy = rstd * (gd.y - m1 - xh.y * m2);
+                reinterpret_cast<__nv_bfloat162*>(a.dpre + m * a.ld + (t == 0 ? 2 * D : 0) + h * 64)[lane] = __floats2bfloat162_rn(ox, oy);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[warp][j][lane] = acc[j];
+    __syncthreads();
+    // partial[block][tensor][dim]: tensors q gamma, q beta, k gamma, k beta; dim 2l / 2l+1 from accumulators (0,1) / (2,3)
+    const int t = threadIdx.x;                 // 256 threads = 4 tensors x 64 dims
+    const int tensor = t >> 6, dim = t & 63, ln = dim >> 1, odd = dim & 1;
+    const int j = (tensor >> 1) * 4 + (tensor & 1) * 2 + odd;
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += red[w][j][ln];
+    a.partial[(int64_t)blockIdx.x * 256 + t] = v;
+}
+
+// ------------------------------------------------------------------------------------------------ gelu_new forward / backward
+__global__ void __launch_bounds__(256) gelu_fwd_kernel(const bf16* __restrict__ src, int64_t ld_s, bf16* __restrict__ dst, int64_t ld_d,
+                                                       int64_t rows, int cols) {
+    const int cv = cols >> 3;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows * cv; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / cv; const int c = (int)(i % cv) * 8;
+        const uint4 u = *reinterpret_cast<const uint4*>(src + r * ld_s + c);
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+        uint4 o; uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(h2[j]); ow[j] = pack_bf16(gelu_new_f(f.x), gelu_new_f(f.y)); }
+        *reinterpret_cast<uint4*>(dst + r * ld_d + c) = o;
+    }
+}
+__device__ __forceinline__ float gelu_new_grad(float x) {
+    const float c = 0.7978845608028654f, k = 0.044715f;
+    const float t = tanhf(c * (x + k * x * x * x));
+    return 0.5f * (1.f + t) + 0.5f * x * (1.f - t * t) * c * (1.f + 3.f * k * x * x);
+}
+__global__ void __launch_bounds__(256) gelu_bwd_kernel(const bf16* __restrict__ dact, int64_t ld_a, const bf16* __restrict__ pre, int64_t ld_p,
+                                                       bf16* __restrict__ dst, int64_t ld_d, int64_t rows, int cols) {
+    const int cv = cols >> 3;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows * cv; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / cv; const int c = (int)(i % cv) * 8;
+        const uint4 ua = *reinterpret_cast<const uint4*>(dact + r * ld_a + c);
+        const uint4 up = *reinterpret_cast<const uint4*>(pre + r * ld_p + c);
+        const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&ua);
+        const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&up);
+        uint4 o; uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 g = __bfloat1622float2(a2[j]), x = __bfloat1622float2(p2[j]);
+            ow[j] = pack_bf16(g.x * gelu_new_grad(x.x), g.y * gelu_new_grad(x.y));
+        }
+        *reinterpret_cast<uint4*>(dst + r * ld_d + c) = o;
+    }
+}
+// dst[r, c] = src[r, c] for a column block (bf16, 16-byte vectors)
+__global__ void __launch_bounds__(256) copy_cols_bf16_kernel(const bf16* __restrict__ src, int64_t ld_s, bf16* __restrict__ dst, int64_t ld_d,
+                                                             int64_t rows, int cols) {
+    const int cv = cols >> 3;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows * cv; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / cv; const int c = (int)(i % cv) * 8;
+        *reinterpret_cast<uint4*>(dst + r * ld_d + c) = *reinterpret_cast<const uint4*>(src + r * ld_s + c);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ transposes / row sums
+// dst[c, r] = bf16(src[r, c]) over 64 x 64 tiles (R, C even); optional row-major bf16 copy of the source (fp32 -> bf16)
+template <class TSrc>
+__global__ void __launch_bounds__(256) transpose_to_bf16_kernel(const TSrc* __restrict__ src, int64_t ld_s, int R, int C,
+                                                                bf16* __restrict__ dst, int64_t ld_d, bf16* __restrict__ copy, int64_t ld_c) {
+    __shared__ bf16 tile[64][66];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int r = r0 + ty + 8 * j, c = c0 + 2 * tx;
+        __nv_bfloat162 v = __floats2bfloat162_rn(0.f, 0.f);
+        if (r < R && c < C) {
+            if constexpr (sizeof(TSrc) == 4) {
+                const float2 f = *reinterpret_cast<const float2*>(src + (int64_t)r * ld_s + c);
+                v = __floats2bfloat162_rn(f.x, f.y);
+            } else {
+                v = *reinterpret_cast<const __nv_bfloat162*>(src + (int64_t)r * ld_s + c);
+            }
+            if (copy != nullptr) *reinterpret_cast<__nv_bfloat162*>(copy + (int64_t)r * ld_c + c) = v;
+        }
+        *reinterpret_cast<__nv_bfloat162*>(&tile[ty + 8 * j][2 * tx]) = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = c0 + ty + 8 * j, r = r0 + 2 * tx;          // dst row c, dst columns r, r + 1
+        if (c < C && r < R) {
+            __nv_bfloat162 v;
+            v.x = tile[2 * tx][ty + 8 * j];
+            v.y = tile[2 * tx + 1][ty + 8 * j];
+            *reinterpret_cast<__nv_bfloat162*>(dst + (int64_t)c * ld_d + r) = v;
+        }
+    }
+}
+// out[r] = sum_c src[r, c]  (one warp per row, fixed order)
+__global__ void __launch_bounds__(256) rowsum_bf16_kernel(const bf16* __restrict__ src, int64_t ld, int R, int C, float* __restrict__ out) {
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (r >= R) return;
+    const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(src + (int64_t)r * ld);
+    float s = 0.f;
+    for (int i = lane; i < (C >> 1); i += 32) { const float2 f = __bfloat1622float2(p[i]); s += f.x + f.y; }
+    if ((C & 1) && lane == 0) s += __bfloat162float(src[(int64_t)r * ld + C - 1]);
+    s = warp_sum(s);
+    if (lane == 0) out[r] = s;
+}
+
+// ------------------------------------------------------------------------------------------------ cross-entropy backward
+struct CeBwdArgs {
+    const float* logits; const int64_t* labels; int L, V; int64_t Vp;
+    int b0[3], nb[3], t0[3], nt[3], shift[3];
+    int64_t ignore_index;
+    const float* loss_grads;      // [3] upstream gradients of the three mean losses (device)
+    const float* counts;          // [3][2] {mean, count} written by the forward (device)
+    bf16* dlogits;                // [B * L, Vp]
+};
+// dlogits[r, :] = sum_i w_i (softmax(logits[r]) - onehot(label_i)),  w_i = loss_grads[i] / count_i for every loss term i that
+// counts row r (modeling_showo.py:81-100); rows no term counts get zeros.
+__global__ void __launch_bounds__(256) ce_bwd_kernel(CeBwdArgs a) {
+    __shared__ float sm_m[8], sm_s[8];
+    __shared__ float s_lse;
+    const int r = blockIdx.x, b = r / a.L, t = r % a.L, tid = threadIdx.x;
+    float w[3]; int lab[3];
+    float wsum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        w[i] = 0.f; lab[i] = -1;
+        if (b >= a.b0[i] && b < a.b0[i] + a.nb[i] && t >= a.t0[i] && t < a.t0[i] + a.nt[i]) {
+            const int64_t l = a.labels[(int64_t)b * a.L + t + a.shift[i]];
+            if (l != a.ignore_index) { w[i] = a.loss_grads[i] / a.counts[2 * i + 1]; lab[i] = (int)l; wsum += w[i]; }
+        }
+    }
+    bf16* out = a.dlogits + (int64_t)r * a.Vp;
+    if (lab[0] < 0 && lab[1] < 0 && lab[2] < 0) {
+        for (int i = tid; i < a.Vp; i += 256) out[i] = __float2bfloat16(0.f);
+        return;
+    }
+    const float* x = a.logits + (int64_t)r * a.V;
+    float m = -FLT_MAX, sum = 0.f;
+    for (int i = tid; i < a.V; i += 256) {
+        const float v = x[i];
+        if (v > m) { sum = sum * expf(m - v) + 1.f; m = v; }
+        else sum += expf(v - m);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, m, o), os = __shfl_xor_sync(0xffffffffu, sum, o);
+        const float nm = fmaxf(m, om);
+        sum = sum * expf(m - nm) + os * expf(om - nm);
+        m = nm;
+    }
+    if ((tid & 31) == 0) { sm_m[tid >> 5] = m; sm_s[tid >> 5] = sum; }
+    __syncthreads();
+    if (tid == 0) {
+        float M = sm_m[0], S = sm_s[0];
+        for (int q = 1; q < 8; ++q) {
+            const float nm = fmaxf(M, sm_m[q]);
+            S = S * expf(M - nm) + sm_s[q] * expf(sm_m[q] - nm);
+            M = nm;
+        }
+        s_lse = M + logf(S);
+    }
+    __syncthreads();
+    const float lse = s_lse;
+    for (int i = tid; i < a.Vp; i += 256) {
+        float v = 0.f;
+        if (i < a.V) {
+            v = wsum * expf(x[i] - lse);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) if (i == lab[q]) v -= w[q];
+        }
+        out[i] = __float2bfloat16(v);
+    }
+}
+
+// g[ids[r], :] += dx[r, :]   (fp32 atomics; rows sharing a token id -- pads, the mask token -- collide on purpose)
+__global__ void __launch_bounds__(128) embed_scatter_add_kernel(const int64_t* __restrict__ ids, const float* __restrict__ dx,
+                                                                float* __restrict__ g, int n_rows, int D, int vocab) {
+    const int r = blockIdx.x;
+    if (r >= n_rows) return;
+    int64_t id = ids[r];
+    if (id < 0 || id >= vocab) return;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) atomicAdd(g + id * D + d, dx[(int64_t)r * D + d]);
+}
+
+// ================================================================================================ host side
+struct TrainState {
+    int cap_M = 0;
+    int64_t Vp = 0;
+    bf16 *w1t = nullptr, *w2t = nullptr, *head_wt = nullptr;
+    int64_t wt_version = -1;
+    float* xs = nullptr; float2* stats = nullptr; bf16* xh = nullptr; bf16* pre = nullptr; bf16* a2 = nullptr;
+    bf16 *qrot = nullptr, *krot = nullptr; float* lse = nullptr;
+    float *dx = nullptr, *dxh = nullptr; bf16 *dxb = nullptr, *dA2 = nullptr, *dpre = nullptr, *dqk = nullptr;
+    float* delta = nullptr; bf16 *tA = nullptr, *tB = nullptr, *dlogits = nullptr;
+    float* partials = nullptr; size_t partials_cap = 0;
+    float* logits = nullptr; int64_t logits_cap = 0;
+    float* grads = nullptr; int64_t n_grads = 0;
+    int64_t* ids = nullptr; int64_t* labels = nullptr; float* losses = nullptr;   // device copies for the backward
+    // what the last forward ran
+    int B = 0, L = 0, M = 0; bool from_ids = false, have_forward = false;
+    const float* logits_used = nullptr;
+    int terms[15] = {0}; int64_t ignore_index = -100;
+};
+
+void train_state_destroy(TrainState* t) {
+    if (!t) return;
+    dev_free(t->w1t); dev_free(t->w2t); dev_free(t->head_wt);
+    dev_free(t->xs); dev_free(t->stats); dev_free(t->xh); dev_free(t->pre); dev_free(t->a2); dev_free(t->qrot); dev_free(t->krot);
+    dev_free(t->lse); dev_free(t->dx); dev_free(t->dxh); dev_free(t->dxb); dev_free(t->dA2); dev_free(t->dpre); dev_free(t->dqk);
+    dev_free(t->delta); dev_free(t->tA); dev_free(t->tB); dev_free(t->dlogits); dev_free(t->partials); dev_free(t->logits);
+    dev_free(t->grads); dev_free(t->ids); dev_free(t->labels); dev_free(t->losses);
+    delete t;
+}
+
+// ---- gradient buffer layout (fp32, packed like the weights)
+struct GradLayout {
+    int64_t per_layer, w1, b1, w2, b2, ln_g, ln_b, qg, qb, kg, kb;      // offsets inside a layer block
+    int64_t head_w, head_b, fln_g, fln_b, embed, total;
+};
+static GradLayout grad_layout(const showo_engine* e) {
+    GradLayout g{};
+    const int64_t D = e->D, W1N = e->W1N, W2K = e->W2K, V = e->V;
+    int64_t o = 0;
+    g.w1 = o; o += W1N * D; g.b1 = o; o += W1N; g.w2 = o; o += D * W2K; g.b2 = o; o += D;
+    g.ln_g = o; o += D; g.ln_b = o; o += D; g.qg = o; o += 64; g.qb = o; o += 64; g.kg = o; o += 64; g.kb = o; o += 64;
+    g.per_layer = o;
+    o = g.per_layer * e->NL;
+    g.head_w = o; o += V * D; g.head_b = o; o += (V + 3) / 4 * 4; g.fln_g = o; o += D; g.fln_b = o; o += D; g.embed = o; o += V * D;
+    g.total = o;
+    return g;
+}
+
+static int launch_grid(int64_t work_items, int threads) {
+    const int64_t b = (work_items + threads - 1) / threads;
+    return (int)(b < 148 * 16 ? (b < 1 ? 1 : b) : 148 * 16);
+}
+static int layernorm_train(const float* x, const float* g, const float* b, float eps, bf16* out, float2* stats, int rows, int D, cudaStream_t st) {
+    const int grid = cdiv(rows, 8);
+    if (D <= 512) layernorm_train_kernel<4><<<grid, 256, 0, st>>>(x, g, b, eps, out, stats, rows, D);
+    else layernorm_train_kernel<16><<<grid, 256, 0, st>>>(x, g, b, eps, out, stats, rows, D);
+    note_launch();
+    SHOWO_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+static int ensure_partials(TrainState* t, size_t n) {
+    if (n > t->partials_cap) {
+        dev_free(t->partials);
+        SHOWO_TRY(dev_alloc(&t->partials, n));
+        t->partials_cap = n;
+    }
+    return 0;
+}
+// LayerNorm(D) backward: dx_io (+)= ..., d gamma / d beta -> gg / gb
+static int layernorm_backward(TrainState* t, const float* dy, const float* x, const float2* stats, const float* gamma, float* dx_io,
+                              bool accumulate, float* gg, float* gb, int rows, int D, cudaStream_t st) {
+    const int S = 32;
+    SHOWO_TRY(ensure_partials(t, (size_t)S * 2 * D + 2 * D));
+    ln_bwd_param_kernel<<<dim3(cdiv(D, 32), S), 256, 0, st>>>(dy, x, stats, rows, D, t->partials);
+    // partial layout [S][2][D]: reduced as one vector of 2 * D (gamma | beta) behind the partials, then copied out
+    reduce_partials_kernel<<<cdiv(2 * D, 32), 256, 0, st>>>(t->partials, S, 2 * D, t->partials + (size_t)S * 2 * D);
+    SHOWO_CUDA_OK(cudaMemcpyAsync(gg, t->partials + (size_t)S * 2 * D, (size_t)D * 4, cudaMemcpyDeviceToDevice, st));
+    SHOWO_CUDA_OK(cudaMemcpyAsync(gb, t->partials + (size_t)S * 2 * D + D, (size_t)D * 4, cudaMemcpyDeviceToDevice, st));
+    const int grid = cdiv(rows, 8);
+    if (D <= 512) ln_bwd_dx_kernel<4><<<grid, 256, 0, st>>>(dy, x, stats, gamma, dx_io, accumulate ? 1 : 0, rows, D);
+    else ln_bwd_dx_kernel<16><<<grid, 256, 0, st>>>(dy, x, stats, gamma, dx_io, accumulate ? 1 : 0, rows, D);
+    note_launch(3);
+    SHOWO_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+template <class TSrc>
+static int transpose_to_bf16(const TSrc* src, int64_t ld_s, int R, int C, bf16* dst, int64_t ld_d, bf16* copy, int64_t ld_c, cudaStream_t st) {
+    SHOWO_CHECK(C % 2 == 0 && ld_s % 2 == 0 && ld_d % 2 == 0, "transpose: even sizes expected");
+    transpose_to_bf16_kernel<TSrc><<<dim3(cdiv(C, 64), cdiv(R, 64)), 256, 0, st>>>(src, ld_s, R, C, dst, ld_d, copy, ld_c);
+    note_launch();
+    SHOWO_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+static int rowsum_bf16(const bf16* src, int64_t ld, int R, int C, float* out, cudaStream_t st) {
+    rowsum_bf16_kernel<<<cdiv(R, 8), 256, 0, st>>>(src, ld, R, C, out);
+    note_launch();
+    SHOWO_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+static int gemm_plain(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, int M, int N, int K, void* out, int64_t ldc, bool f32_out,
+                      cudaStream_t st) {
+    GemmArgs g{};
+    g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.M = M; g.N = N; g.K = K; g.out = out; g.ldc = ldc; g.gelu_from = N;
+    if (M <= 16) g.block_n = 64;          // keep the training path on the tcgen05 kernel whatever the row count
+    return gemm_bf16(g, f32_out ? GEMM_BIAS_F32 : GEMM_BIAS_BF16, st);
+}
+
+static int ensure_train(showo_engine* e, int M, cudaStream_t st) {
+    if (!e->train) e->train = new TrainState();
+    TrainState* t = e->train;
+    const int64_t D = e->D, W1N = e->W1N, W2K = e->W2K, V = e->V, NL = e->NL, H = e->H;
+    t->Vp = (V + 7) / 8 * 8;
+    if (!t->w1t) {
+        SHOWO_TRY(dev_alloc(&t->w1t, (size_t)(NL * D * W1N)));
+        SHOWO_TRY(dev_alloc(&t->w2t, (size_t)(NL * W2K * D)));
+        SHOWO_TRY(dev_alloc(&t->head_wt, (size_t)(D * t->Vp)));
+        SHOWO_CUDA_OK(cudaMemsetAsync(t->head_wt, 0, (size_t)(D * t->Vp) * 2, st));
+        const GradLayout gl = grad_layout(e);
+        SHOWO_TRY(dev_alloc(&t->grads, (size_t)gl.total));
+        t->n_grads = gl.total;
+        SHOWO_TRY(dev_alloc(&t->losses, 8));
+    }
+    if (t->wt_version != e->weights_version) {
+        for (int l = 0; l < NL; ++l) {
+            SHOWO_TRY(transpose_to_bf16<bf16>(e->layers[l].w1, D, (int)W1N, (int)D, t->w1t + (size_t)l * D * W1N, W1N, nullptr, 0, st));
+            SHOWO_TRY(transpose_to_bf16<bf16>(e->layers[l].w2, W2K, (int)D, (int)W2K, t->w2t + (size_t)l * W2K * D, D, nullptr, 0, st));
+        }
+        SHOWO_TRY(transpose_to_bf16<bf16>(e->head_w, D, (int)V, (int)D, t->head_wt, t->Vp, nullptr, 0, st));
+        t->wt_version = e->weights_version;
+    }
+    if (M > t->cap_M) {
+        SHOWO_CUDA_OK(cudaStreamSynchronize(st));
+        dev_free(t->xs); dev_free(t->stats); dev_free(t->xh); dev_free(t->pre); dev_free(t->a2); dev_free(t->qrot); dev_free(t->krot);
+        dev_free(t->lse); dev_free(t->dx); dev_free(t->dxh); dev_free(t->dxb); dev_free(t->dA2); dev_free(t->dpre); dev_free(t->dqk);
+        dev_free(t->delta); dev_free(t->tA); dev_free(t->tB); dev_free(t->dlogits); dev_free(t->ids); dev_free(t->labels);
+        const size_t m = (size_t)M, Mp = (size_t)(M + 7) / 8 * 8;
+        SHOWO_TRY(dev_alloc(&t->xs, (size_t)(NL + 1) * m * D));
+        SHOWO_TRY(dev_alloc(&t->stats, (size_t)(NL + 1) * m));
+        SHOWO_TRY(dev_alloc(&t->xh, (size_t)(NL + 1) * m * D));
+        SHOWO_TRY(dev_alloc(&t->pre, (size_t)NL * m * W1N));
+        SHOWO_TRY(dev_alloc(&t->a2, (size_t)NL * m * W2K));
+        SHOWO_TRY(dev_alloc(&t->qrot, (size_t)NL * m * D));
+        SHOWO_TRY(dev_alloc(&t->krot, (size_t)NL * m * D));
+        SHOWO_TRY(dev_alloc(&t->lse, (size_t)NL * m * H));
+        SHOWO_TRY(dev_alloc(&t->dx, m * D));
+        SHOWO_TRY(dev_alloc(&t->dxh, m * D));
+        SHOWO_TRY(dev_alloc(&t->dxb, m * D));
+        SHOWO_TRY(dev_alloc(&t->dA2, m * W2K));
+        SHOWO_TRY(dev_alloc(&t->dpre, m * W1N));
+        SHOWO_TRY(dev_alloc(&t->dqk, 2 * m * D));
+        SHOWO_TRY(dev_alloc(&t->delta, m * H));
+        const size_t ra = (size_t)(t->Vp > W1N ? t->Vp : W1N), rbm = (size_t)(W2K > D ? W2K : D);
+        SHOWO_TRY(dev_alloc(&t->tA, ra * Mp));
+        SHOWO_TRY(dev_alloc(&t->tB, rbm * Mp));
+        SHOWO_TRY(dev_alloc(&t->dlogits, m * (size_t)t->Vp));
+        SHOWO_TRY(dev_alloc(&t->ids, m));
+        SHOWO_TRY(dev_alloc(&t->labels, m));
+        t->cap_M = M;
+    }
+    return 0;
+}
+
+static int named_grad(showo_engine* e, const std::string& name, float** ptr, int64_t* rows, int64_t* cols, int64_t* ld) {
+    const GradLayout g = grad_layout(e);
+    TrainState* t = e->train;
+    const int64_t D = e->D, F = e->F, V = e->V, W2K = e->W2K;
+    auto set = [&](int64_t off, int64_t r, int64_t c, int64_t l) { *ptr = t->grads + off; *rows = r; *cols = c; *ld = l; return 0; };
+    if (name == "showo.model.embed_tokens.weight") return set(g.embed, V, D, D);
+    if (name == "showo.lm_head.weight") return set(g.head_w, V, D, D);
+    if (name == "showo.lm_head.bias") return set(g.head_b, 1, V, V);
+    if (name == "showo.model.final_layernorm.weight") return set(g.fln_g, 1, D, D);
+    if (name == "showo.model.final_layernorm.bias") return set(g.fln_b, 1, D, D);
+    const std::string lp = "showo.model.layers.";
+    SHOWO_CHECK(name.compare(0, lp.size(), lp) == 0, "read_grad: unknown parameter " + name);
+    const size_t dot = name.find('.', lp.size());
+    SHOWO_CHECK(dot != std::string::npos, "read_grad: bad parameter name " + name);
+    const int l = atoi(name.substr(lp.size(), dot - lp.size()).c_str());
+    SHOWO_CHECK(l >= 0 && l < e->NL, "read_grad: layer index out of range in " + name);
+    const int64_t base = g.per_layer * l;
+    const std::string k = name.substr(dot + 1);
+    if (k == "self_attn.k_proj.weight") return set(base + g.w1, D, D, D);
+    if (k == "self_attn.v_proj.weight") return set(base + g.w1 + D * D, D, D, D);
+    if (k == "self_attn.q_proj.weight") return set(base + g.w1 + 2 * D * D, D, D, D);
+    if (k == "mlp.fc1.weight") return set(base + g.w1 + 3 * D * D, F, D, D);
+    if (k == "self_attn.k_proj.bias") return set(base + g.b1, 1, D, D);
+    if (k == "self_attn.v_proj.bias") return set(base + g.b1 + D, 1, D, D);
+    if (k == "self_attn.q_proj.bias") return set(base + g.b1 + 2 * D, 1, D, D);
+    if (k == "mlp.fc1.bias") return set(base + g.b1 + 3 * D, 1, F, F);
+    if (k == "self_attn.dense.weight") return set(base + g.w2, D, D, W2K);
+    if (k == "mlp.fc2.weight") return set(base + g.w2 + D, D, F, W2K);
+    if (k == "self_attn.dense.bias" || k == "mlp.fc2.bias") return set(base + g.b2, 1, D, D);
+    if (k == "input_layernorm.weight") return set(base + g.ln_g, 1, D, D);
+    if (k == "input_layernorm.bias") return set(base + g.ln_b, 1, D, D);
+    if (k == "self_attn.q_layernorm.weight") return set(base + g.qg, 1, 64, 64);
+    if (k == "self_attn.q_layernorm.bias") return set(base + g.qb, 1, 64, 64);
+    if (k == "self_attn.k_layernorm.weight") return set(base + g.kg, 1, 64, 64);
+    if (k == "self_attn.k_layernorm.bias") return set(base + g.kb, 1, 64, 64);
+    SHOWO_CHECK(false, "read_grad: unknown parameter " + name);
+    return -2;
+}
+
+}  // namespace showo
+
+using namespace showo;
+
+extern "C" {
+
+int showo_train_forward(showo_engine_t* e, const int64_t* ids_dev, const float* embeds_dev, int B, int L,
+                        const showo_seq_mask_t* masks_host, const int64_t* labels_dev, const int32_t* terms_host,
+                        int64_t ignore_index, float* logits_out_dev, float* losses_out_dev, void* stream) {
+    SHOWO_TRY(engine_check_ready(e));
+    SHOWO_CHECK((ids_dev != nullptr) != (embeds_dev != nullptr), "train_forward: exactly one of ids / embeds");
+    SHOWO_CHECK(B > 0 && L > 0 && L <= e->cfg.max_pos && masks_host && labels_dev && terms_host && losses_out_dev,
+                "train_forward: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t l0 = launches_total();
+    const int M = B * L, D = e->D, H = e->H, W1N = e->W1N, W2K = e->W2K, V = e->V, NL = e->NL;
+    SHOWO_TRY(engine_ensure_ws(e, 0, B, L, 0, st));         // K / V^T tiles of one layer + the mask descriptors
+    SHOWO_TRY(engine_upload_masks(e, masks_host, B, st));
+    SHOWO_TRY(ensure_train(e, M, st));
+    TrainState* t = e->train;
+    t->B = B; t->L = L; t->M = M; t->from_ids = ids_dev != nullptr; t->ignore_index = ignore_index;
+    for (int i = 0; i < 15; ++i) t->terms[i] = terms_host[i];
+    SHOWO_CUDA_OK(cudaMemcpyAsync(t->labels, labels_dev, (size_t)M * 8, cudaMemcpyDeviceToDevice, st));
+    const size_t mD = (size_t)M * D;
+    if (ids_dev) {
+        SHOWO_CUDA_OK(cudaMemcpyAsync(t->ids, ids_dev, (size_t)M * 8, cudaMemcpyDeviceToDevice, st));
+        SHOWO_TRY(embed_gather(ids_dev, L, 0, e->embed, t->xs, M, L, D, V, st));
+    } else {
+        SHOWO_CUDA_OK(cudaMemcpyAsync(t->xs, embeds_dev, mD * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    for (int l = 0; l < NL; ++l) {
+        const LayerW& w = e->layers[l];
+        float* x = t->xs + (size_t)l * mD;
+        bf16* xh = t->xh + (size_t)l * mD;
+        bf16* pre = t->pre + (size_t)l * M * W1N;
+        bf16* a2 = t->a2 + (size_t)l * M * W2K;
+        SHOWO_TRY(layernorm_train(x, w.ln_g, w.ln_b, e->cfg.ln_eps, xh, t->stats + (size_t)l * M, M, D, st));
+        GemmArgs g1{};
+        g1.A = xh; g1.lda = D; g1.B = w.w1; g1.ldb = D; g1.M = M; g1.N = W1N; g1.K = D; g1.out = pre; g1.ldc = W1N; g1.bias = w.b1;
+        g1.gelu_from = W1N; if (M <= 16) g1.block_n = 64;
+        SHOWO_TRY(gemm_bf16(g1, GEMM_BIAS_BF16, st));
+        QkTrainArgs q{};
+        q.pre = pre; q.ld = W1N; q.n_seq = B; q.L = L; q.H = H; q.D = D; q.qg = w.qg; q.qb = w.qb; q.kg = w.kg; q.kb = w.kb;
+        q.eps = e->cfg.ln_eps; q.cos_tab = e->cos_tab; q.sin_tab = e->sin_tab;
+        q.qrot = t->qrot + (size_t)l * mD; q.krot = t->krot + (size_t)l * mD; q.kcache = e->kcache; q.vtcache = e->vtcache; q.Lmax = e->cap_L;
+        qk_rope_train_kernel<<<dim3(B * cdiv(L, 32), H), 256, 0, st>>>(q);
+        gelu_fwd_kernel<<<launch_grid((int64_t)M * (e->F / 8), 256), 256, 0, st>>>(pre + 3 * D, W1N, a2 + D, W2K, M, e->F);
+        note_launch(2);
+        SHOWO_CUDA_OK(cudaGetLastError());
+        AttnArgs a{};
+        a.q = t->qrot + (size_t)l * mD; a.ld = D; a.n_seq = B; a.H = H; a.rows_per_seq = L; a.pos0 = 0;
+        a.kcache = e->kcache; a.vtcache = e->vtcache; a.Lmax = e->cap_L; a.n_keys = L; a.masks = e->d_masks; a.scale = 0.125f;
+        a.out = a2; a.out_ld = W2K; a.lse = t->lse + (size_t)l * M * H;
+        SHOWO_TRY(omni_attention(a, st));
+        GemmArgs g2{};
+        g2.A = a2; g2.lda = W2K; g2.B = w.w2; g2.ldb = W2K; g2.M = M; g2.N = D; g2.K = W2K;
+        g2.out = t->xs + (size_t)(l + 1) * mD; g2.ldc = D; g2.bias = w.b2; g2.resid = x; g2.ldr = D; if (M <= 16) g2.block_n = 64;
+        SHOWO_TRY(gemm_bf16(g2, GEMM_RESID_F32, st));
+    }
+    SHOWO_TRY(layernorm_train(t->xs + (size_t)NL * mD, e->fln_g, e->fln_b, e->cfg.ln_eps, t->xh + (size_t)NL * mD, t->stats + (size_t)NL * M, M, D, st));
+    float* logits = logits_out_dev;
+    if (!logits) {
+        if ((int64_t)M * V > t->logits_cap) {
+            SHOWO_CUDA_OK(cudaStreamSynchronize(st));
+            dev_free(t->logits);
+            SHOWO_TRY(dev_alloc(&t->logits, (size_t)M * V));
+            t->logits_cap = (int64_t)M * V;
+        }
+        logits = t->logits;
+    }
+    t->logits_used = logits;
+    GemmArgs gh{};
+    gh.A = t->xh + (size_t)NL * mD; gh.lda = D; gh.B = e->head_w; gh.ldb = D; gh.M = M; gh.N = V; gh.K = D;
+    gh.out = logits; gh.ldc = V; gh.bias = e->head_b; if (M <= 16) gh.block_n = 64;
+    SHOWO_TRY(gemm_bf16(gh, GEMM_BIAS_F32, st));
+    // the three cross-entropy means (modeling_showo.py:81-100); {mean, count} pairs are kept on the device for the backward
+    SHOWO_TRY(ensure_partials(t, (size_t)2 * M + 64));
+    for (int i = 0; i < 3; ++i) {
+        const int* tm = t->terms + 5 * i;
+        SHOWO_TRY(cross_entropy_mean(logits, labels_dev, L, V, tm[0], tm[1], tm[2], tm[3], tm[4], ignore_index, t->partials, t->losses + 2 * i, st));
+    }
+    SHOWO_CUDA_OK(cudaMemcpyAsync(losses_out_dev, t->losses, 6 * 4, cudaMemcpyDeviceToDevice, st));
+    t->have_forward = true;
+    e->launches_last = launches_total() - l0;
+    return 0;
+}
+
+int showo_backward(showo_engine_t* e, const float* loss_grads_dev, float* dembeds_out_dev, void* stream) {
+    SHOWO_TRY(engine_check_ready(e));
+    SHOWO_CHECK(e->train && e->train->have_forward, "backward: call showo_train_forward first");
+    SHOWO_CHECK(loss_grads_dev != nullptr, "backward: null loss gradients");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t l0 = launches_total();
+    TrainState* t = e->train;
+    const int M = t->M, B = t->B, L = t->L, D = e->D, H = e->H, W1N = e->W1N, W2K = e->W2K, V = e->V, NL = e->NL, F = e->F;
+    const int64_t Mp = (int64_t)(M + 7) / 8 * 8, Vp = t->Vp;
+    const size_t mD = (size_t)M * D;
+    const GradLayout gl = grad_layout(e);
+    float* G = t->grads;
+    // ---- loss -> dlogits (bf16) -> head
+    CeBwdArgs c{};
+    c.logits = t->logits_used; c.labels = t->labels; c.L = L; c.V = V; c.Vp = Vp; c.ignore_index = t->ignore_index;
+    for (int i = 0; i < 3; ++i) { c.b0[i] = t->terms[5 * i]; c.nb[i] = t->terms[5 * i + 1]; c.t0[i] = t->terms[5 * i + 2]; c.nt[i] = t->terms[5 * i + 3]; c.shift[i] = t->terms[5 * i + 4]; }
+    c.loss_grads = loss_grads_dev; c.counts = t->losses; c.dlogits = t->dlogits;
+    ce_bwd_kernel<<<M, 256, 0, st>>>(c);
+    note_launch();
+    SHOWO_CUDA_OK(cudaGetLastError());
+    // d xh_f = dlogits * Wh                                     [M, D] fp32
+    SHOWO_TRY(gemm_plain(t->dlogits, Vp, t->head_wt, Vp, M, D, (int)Vp, t->dxh, D, true, st));
+    // d Wh = dlogits^T * xh_f, d bh = column sums of dlogits
+    SHOWO_TRY(transpose_to_bf16<bf16>(t->dlogits, Vp, M, (int)Vp, t->tA, Mp, nullptr, 0, st));
+    SHOWO_TRY(transpose_to_bf16<bf16>(t->xh + (size_t)NL * mD, D, M, D, t->tB, Mp, nullptr, 0, st));
+    SHOWO_TRY(gemm_plain(t->tA, Mp, t->tB, Mp, V, D, M, G + gl.head_w, D, true, st));
+    SHOWO_TRY(rowsum_bf16(t->tA, Mp, V, M, G + gl.head_b, st));
+    // final LayerNorm
+    SHOWO_TRY(layernorm_backward(t, t->dxh, t->xs + (size_t)NL * mD, t->stats + (size_t)NL * M, e->fln_g, t->dx, false, G + gl.fln_g,
+                                 G + gl.fln_b, M, D, st));
+    for (int l = NL - 1; l >= 0; --l) {
+        const LayerW& w = e->layers[l];
+        float* GL = G + gl.per_layer * l;
+        const bf16* pre = t->pre + (size_t)l * M * W1N;
+        const bf16* a2 = t->a2 + (size_t)l * M * W2K;
+        // dx (fp32) -> bf16 row-major + transposed; d b2 = column sums
+        SHOWO_TRY(transpose_to_bf16<float>(t->dx, D, M, D, t->tA, Mp, t->dxb, D, st));
+        SHOWO_TRY(rowsum_bf16(t->tA, Mp, D, M, GL + gl.b2, st));
+        // d W2 = dx^T * [attn | act]
+        SHOWO_TRY(transpose_to_bf16<bf16>(a2, W2K, M, W2K, t->tB, Mp, nullptr, 0, st));
+        SHOWO_TRY(gemm_plain(t->tA, Mp, t->tB, Mp, D, W2K, M, GL + gl.w2, W2K, true, st));
+        // d [attn | act] = dx * W2
+        SHOWO_TRY(gemm_plain(t->dxb, D, t->w2t + (size_t)l * W2K * D, D, M, W2K, D, t->dA2, W2K, false, st));
+        // attention backward: d q_rot, d k_rot -> dqk, d v -> dpre[:, D:2D]
+        AttnBwdArgs ab{};
+        ab.q = t->qrot + (size_t)l * mD; ab.q_ld = D; ab.k = t->krot + (size_t)l * mD; ab.k_ld = D; ab.v = pre + D; ab.v_ld = W1N;
+        ab.o = a2; ab.o_ld = W2K; ab.d_o = t->dA2; ab.do_ld = W2K; ab.lse = t->lse + (size_t)l * M * H; ab.delta = t->delta;
+        ab.dq = t->dqk; ab.dq_ld = D; ab.dk = t->dqk + mD; ab.dk_ld = D; ab.dv = t->dpre + D; ab.dv_ld = W1N;
+        ab.n_seq = B; ab.H = H; ab.L = L; ab.masks = e->d_masks; ab.scale = 0.125f;
+        SHOWO_TRY(omni_attention_backward(ab, st));
+        // rotary^T + LayerNorm(64) backward -> d q_raw / d k_raw; gelu' -> d fc1
+        QkTrainArgs q{};
+        q.pre = pre; q.ld = W1N; q.n_seq = B; q.L = L; q.H = H; q.D = D; q.qg = w.qg; q.qb = w.qb; q.kg = w.kg; q.kb = w.kb;
+        q.eps = e->cfg.ln_eps; q.cos_tab = e->cos_tab; q.sin_tab = e->sin_tab; q.dq = t->dqk; q.dk = t->dqk + mD; q.dpre = t->dpre;
+        const int nblk = B * cdiv(L, 32);
+        SHOWO_TRY(ensure_partials(t, (size_t)nblk * 256 + 256));
+        q.partial = t->partials;
+        qk_rope_bwd_kernel<<<nblk, 256, 0, st>>>(q);
+        reduce_partials_kernel<<<cdiv(256, 32), 256, 0, st>>>(t->partials, nblk, 256, GL + gl.qg);      // qg | qb | kg | kb are adjacent
+        gelu_bwd_kernel<<<launch_grid((int64_t)M * (F / 8), 256), 256, 0, st>>>(t->dA2 + D, W2K, pre + 3 * D, W1N, t->dpre + 3 * D, W1N, M, F);
+        note_launch(3);
+        SHOWO_CUDA_OK(cudaGetLastError());
+        // d W1 = dpre^T * xh, d b1 = column sums of dpre
+        SHOWO_TRY(transpose_to_bf16<bf16>(t->dpre, W1N, M, W1N, t->tA, Mp, nullptr, 0, st));
+        SHOWO_TRY(transpose_to_bf16<bf16>(t->xh + (size_t)l * mD, D, M, D, t->tB, Mp, nullptr, 0, st));
+        SHOWO_TRY(gemm_plain(t->tA, Mp, t->tB, Mp, W1N, D, M, GL + gl.w1, D, true, st));
+        SHOWO_TRY(rowsum_bf16(t->tA, Mp, W1N, M, GL + gl.b1, st));
+        // d xh = dpre * W1, then LayerNorm backward into the residual gradient
+        SHOWO_TRY(gemm_plain(t->dpre, W1N, t->w1t + (size_t)l * D * W1N, W1N, M, D, W1N, t->dxh, D, true, st));
+        SHOWO_TRY(layernorm_backward(t, t->dxh, t->xs + (size_t)l * mD, t->stats + (size_t)l * M, w.ln_g, t->dx, true, GL + gl.ln_g,
+                                     GL + gl.ln_b, M, D, st));
+    }
+    if (t->from_ids) {
+        SHOWO_CUDA_OK(cudaMemsetAsync(G + gl.embed, 0, (size_t)V * D * 4, st));
+        embed_scatter_add_kernel<<<M, 128, 0, st>>>(t->ids, t->dx, G + gl.embed, M, D, V);
+        note_launch();
+        SHOWO_CUDA_OK(cudaGetLastError());
+    } else {
+        SHOWO_CUDA_OK(cudaMemsetAsync(G + gl.embed, 0, (size_t)V * D * 4, st));
+    }
+    if (dembeds_out_dev) SHOWO_CUDA_OK(cudaMemcpyAsync(dembeds_out_dev, t->dx, mD * 4, cudaMemcpyDeviceToDevice, st));
+    e->launches_last = launches_total() - l0;
+    return 0;
+}
+
+int showo_read_grad(showo_engine_t* e, const char* name, float* out_dev, int64_t numel, void* stream) {
+    SHOWO_CHECK(e && name && out_dev, "read_grad: null argument");
+    SHOWO_CHECK(e->train && e->train->grads, "read_grad: no backward has run");
+    SHOWO_CUDA_OK(cudaSetDevice(e->device));
+    float* p = nullptr; int64_t rows = 0, cols = 0, ld = 0;
+    SHOWO_TRY(named_grad(e, name, &p, &rows, &cols, &ld));
+    SHOWO_CHECK(numel == rows * cols, std::string("read_grad: ") + name + " has " + std::to_string(rows * cols) + " elements, got " + std::to_string(numel));
+    return copy_f32_to_f32_rows(p, ld, out_dev, cols, (int)rows, (int)cols, (cudaStream_t)stream);
+}
+
+int showo_attention_bwd_test(const void* q_dev, const void* k_dev, const void* v_dev, const void* o_dev, const void* do_dev,
+                             const float* lse_dev, void* dq_dev, void* dk_dev, void* dv_dev, int n_seq, int L, int H,
+                             const showo_seq_mask_t* masks_host, void* stream) {
+    SHOWO_CHECK(showo_device_count() > 0, "no sm_100 CUDA device visible: libshowo_b200 has no CPU fallback");
+    cudaStream_t st = (cudaStream_t)stream;
+    showo_seq_mask_t* dm = nullptr; float* delta = nullptr;
+    SHOWO_TRY(dev_alloc(&dm, (size_t)n_seq));
+    SHOWO_TRY(dev_alloc(&delta, (size_t)n_seq * L * H));
+    SHOWO_CUDA_OK(cudaMemcpyAsync(dm, masks_host, (size_t)n_seq * sizeof(showo_seq_mask_t), cudaMemcpyHostToDevice, st));
+    const int64_t ld = (int64_t)H * 64;
+    AttnBwdArgs a{};
+    a.q = (const bf16*)q_dev; a.k = (const bf16*)k_dev; a.v = (const bf16*)v_dev; a.o = (const bf16*)o_dev; a.d_o = (const bf16*)do_dev;
+    a.q_ld = a.k_ld = a.v_ld = a.o_ld = a.do_ld = a.dq_ld = a.dk_ld = a.dv_ld = ld;
+    a.lse = lse_dev; a.delta = delta; a.dq = (bf16*)dq_dev; a.dk = (bf16*)dk_dev; a.dv = (bf16*)dv_dev;
+    a.n_seq = n_seq; a.H = H; a.L = L; a.masks = dm; a.scale = 0.125f;
+    const int rc = omni_attention_backward(a, st);
+    cudaStreamSynchronize(st);
+    cudaFree(dm); cudaFree(delta);
+    return rc;
+}
+
+}  // extern "C"

@@ -61,6 +61,33 @@ def descriptors_causal(batch: int) -> List[Desc]:
     return [(0, 0, 0, 0, 0) for _ in range(batch)]
 
 
+def _descriptors_from_dense_cuda(m: torch.Tensor, verify: bool) -> List[Desc]:
+    """CUDA tensors: one kernel (showo_mask_descriptors) derives and verifies the descriptors; 24 bytes per sequence come back."""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.require_gpu()
+    if m.dtype == torch.bool:
+        m = m.view(torch.uint8)
+    elif m.dtype not in (torch.float32, torch.uint8):
+        m = m.float()
+    if m.stride(-1) != 1 or m.stride(-2) != m.shape[-1]:
+        m = m.contiguous()
+    B, L, _ = m.shape
+    descs = (_lib.SeqMask * B)()
+    bad = (C.c_int32 * B)()
+    with torch.cuda.device(m.device):
+        _lib.check(lib.showo_mask_descriptors(_lib.ptr(m), m.element_size(), B, L, m.stride(0), descs, bad, _lib.current_stream_ptr()),
+                   "showo_mask_descriptors")
+    out = [(d.pad_end, d.full_begin, d.full_end, d.win_begin, d.win_end) for d in descs]
+    if verify:
+        for b in range(B):
+            if bad[b]:
+                raise NotImplementedError(
+                    f"attention_mask row {b} is not an omni mask (causal / image-span / window / left-pad): "
+                    f"derived descriptor {out[b]} does not reproduce it")
+    return out
+
+
 def descriptors_from_dense(attention_mask: torch.Tensor, verify: bool = True) -> List[Desc]:
     """attention_mask: additive [B,1,L,L] (0 = attend) or bool (True = attend).  One device->host copy of O(B*L) ints."""
     m = attention_mask
@@ -68,6 +95,8 @@ def descriptors_from_dense(attention_mask: torch.Tensor, verify: bool = True) ->
         m = m[:, 0]
     if m.dim() == 2:
         m = m[None]
+    if m.is_cuda:
+        return _descriptors_from_dense_cuda(m, verify)
     allowed = m if m.dtype == torch.bool else (m == 0)
     B, L, _ = allowed.shape
     dev = allowed.device

@@ -84,6 +84,28 @@ class _PhiForCausalLM(nn.Module):
         return e
 
 
+class _TrainStep(torch.autograd.Function):
+    """autograd bridge of the training step: forward = showo_train_forward, backward = showo_backward + showo_read_grad.
+    (Plumbing only: no arithmetic happens in torch.)"""
+
+    @staticmethod
+    def forward(ctx, model, ids, emb, descs, labels, terms, names, *params):
+        logits, losses = model.train_forward(ids, emb, descs, labels, terms)
+        ctx.model, ctx.names, ctx.params = model, names, params
+        ctx.emb = emb if (emb is not None and emb.requires_grad) else None
+        ctx.mark_non_differentiable(logits)
+        return logits, losses[0, 0], losses[1, 0], losses[2, 0]
+
+    @staticmethod
+    def backward(ctx, _g_logits, g1, g2, g3):
+        m = ctx.model
+        dev = m._engine_device
+        g = torch.stack([x.float().reshape(()) if x is not None else torch.zeros((), device=dev) for x in (g1, g2, g3)])
+        demb = m.backward(g, ctx.emb)
+        grads = [m.read_grad(n, like=p) if p.requires_grad else None for n, p in zip(ctx.names, ctx.params)]
+        return (None, None, demb, None, None, None, None, *grads)
+
+
 class Showo(nn.Module):
     """Reference signature: Showo(w_clip_vit, vocab_size, llm_vocab_size, llm_model_path='', codebook_size=8192,
     num_vq_tokens=256, load_from_showo=True, **kwargs)   (modeling_showo.py:27-37).
@@ -187,8 +209,19 @@ class Showo(nn.Module):
         self._streamed = True
         return self
 
+    def _param_key(self, p):
+        return (p._version, p.data_ptr(), p.device)
+
+    def refresh_engine(self):
+        """Force a full reload of the engine's bf16 weights from the torch parameters.  Needed after writes that autograd's
+        version counter cannot see (`p.data.copy_(...)`, `p.data.add_(...)`, EMA swaps through `.data`); everything that goes
+        through `load_state_dict`, `.to()`, or an in-place op on the parameter itself is picked up automatically."""
+        self._engine_versions = None
+        return self._sync_engine()
+
     def _sync_engine(self):
-        """(Re)load the engine's bf16 copy when the torch parameters changed (load_state_dict, optimizer step)."""
+        """(Re)load the engine's bf16 copy of every parameter whose (version, storage) changed since the last upload
+        (load_state_dict, optimizer step, .to()): only those tensors are re-packed."""
         if self.showo is None:
             if not self._streamed:
                 raise _lib.ShowoError("no weights: call load_weights() or construct with materialize=True")
@@ -196,14 +229,32 @@ class Showo(nn.Module):
         dev = self.showo.lm_head.weight.device
         if dev.type != "cuda":
             raise _lib.ShowoError("Showo must live on a CUDA (B200) device: show-o_b200 has no CPU fallback")
-        versions = tuple(p._version for p in self.showo.parameters())
-        if self._engine is not None and self._engine_versions == versions and self._engine_device == dev:
+        if self._engine is not None and self._engine_device != dev:
+            _lib.load().showo_engine_destroy(self._engine)
+            self._engine, self._engine_versions = None, None
+        keys = {"showo." + k: self._param_key(p) for k, p in self.showo.named_parameters()}
+        prev = self._engine_versions or {}
+        stale = {k: v for k, v in keys.items() if prev.get(k) != v}
+        if self._engine is not None and not stale:
             return self._engine
-        sd = {"showo." + k: v for k, v in self.showo.state_dict().items()}
+        params = dict(self.showo.named_parameters())
         with torch.cuda.device(dev):
-            self.load_weights(sd, device=dev)
-        self._engine_versions = versions
+            # the upload runs on the legacy default stream: fence it against whatever the caller's stream still has in flight
+            torch.cuda.current_stream().synchronize()
+            self.load_weights({k: params[k[len("showo."):]] for k in stale}, device=dev)
+            torch.cuda.synchronize(dev)
+        self._engine_versions = keys
         return self._engine
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self._engine_versions = None          # .to() / .cuda() / .float(): storages moved
+        return out
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        out = super().load_state_dict(state_dict, strict=strict, assign=assign)
+        self._engine_versions = None
+        return out
 
     def __del__(self):
         try:
@@ -223,16 +274,36 @@ class Showo(nn.Module):
         return masks.descriptors_from_dense(attention_mask)
 
     # ------------------------------------------------------------------ forward
+    @staticmethod
+    def _check_ids(ids, what):
+        if ids.dtype != torch.int64 or not ids.is_cuda:
+            raise _lib.ShowoError(f"{what}: token ids must be a CUDA int64 tensor (got {ids.dtype} on {ids.device}); "
+                                  "the kernels read them as const int64_t* (out-of-range ids are clamped to [0, vocab) by the "
+                                  "embedding gather where torch would raise)")
+        return ids.contiguous()
+
+    def _loss_terms(self, B, L, batch_size_t2i, batch_size_lm, batch_size_mmu, max_seq_length):
+        """Row ranges of the three F.cross_entropy terms (modeling_showo.py:81-100), quirks included: logits[-batch_size_mmu:]
+        is the WHOLE batch when batch_size_mmu == 0 (python's -0), while an empty t2i / lm slice gives a NaN mean."""
+        P = max_seq_length + 1
+        bt = min(max(batch_size_t2i, 0), B)
+        lm0 = min(batch_size_t2i, B)
+        lm1 = min(batch_size_t2i + batch_size_lm, B)
+        mmu0 = B - batch_size_mmu if 0 < batch_size_mmu <= B else 0
+        return ((0, bt, P, max(L - P, 0), 0), (lm0, max(lm1 - lm0, 0), 0, L - 1, 1), (mmu0, B - mmu0, 0, L - 1, 1))
+
     def forward(self, input_ids, input_embeddings=None, attention_mask=None, labels=None, label_smoothing=0.0,
                 batch_size_t2i=0, batch_size_lm=0, batch_size_mmu=0, max_seq_length=128, labels_mask_text=None,
                 labels_mask_image=None, **kwargs):
         """modeling_showo.py:59-102.  Returns logits fp32 [B,L,V] (and the three CE losses when labels are given).
-        Inference-only in this round: the logits carry no autograd graph."""
+        With labels and autograd enabled (training/train.py:589-612) the call runs the engine's training forward, which
+        keeps the activations, and `loss.backward()` runs showo_backward: parameters (and `input_embeddings`) receive
+        gradients; the returned logits are a non-differentiable output (the reference only uses them for logging)."""
         lib = _lib.require_gpu()
         eng = self._sync_engine()
         if input_embeddings is None:
             B, L = input_ids.shape
-            ids = input_ids.contiguous()
+            ids = self._check_ids(input_ids, "Showo.forward")
             emb = None
             dev = ids.device
         else:
@@ -241,6 +312,12 @@ class Showo(nn.Module):
             emb = input_embeddings.float().contiguous()
             dev = emb.device
         descs = self._mask_descs(attention_mask, B)
+        if labels is not None and torch.is_grad_enabled():
+            terms = self._loss_terms(B, L, batch_size_t2i, batch_size_lm, batch_size_mmu, max_seq_length)
+            lab = labels.to(dev).long().contiguous()
+            params = list(self.showo.named_parameters()) if self.showo is not None else []
+            names = ["showo." + k for k, _ in params]
+            return _TrainStep.apply(self, ids, emb, descs, lab, terms, names, *[p for _, p in params])
         logits = torch.empty(B, L, self.vocab_size, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             _lib.check(lib.showo_forward(eng, _lib.ptr(ids), _lib.ptr(emb), B, L, _lib.masks_array(descs),
@@ -249,14 +326,7 @@ class Showo(nn.Module):
             V = self.output_size
             lab = labels.to(dev).long().contiguous()
             out = torch.empty(3, 2, dtype=torch.float32, device=dev)
-            P = max_seq_length + 1
-            # the same row ranges as the reference's slices, quirks included: logits[-batch_size_mmu:] is the WHOLE batch when
-            # batch_size_mmu == 0 (python's -0), while an empty t2i / lm slice gives a NaN mean
-            bt = min(max(batch_size_t2i, 0), B)
-            lm0 = min(batch_size_t2i, B)
-            lm1 = min(batch_size_t2i + batch_size_lm, B)
-            mmu0 = B - batch_size_mmu if 0 < batch_size_mmu <= B else 0
-            terms = ((0, bt, P, L - P, 0), (lm0, max(lm1 - lm0, 0), 0, L - 1, 1), (mmu0, B - mmu0, 0, L - 1, 1))
+            terms = self._loss_terms(B, L, batch_size_t2i, batch_size_lm, batch_size_mmu, max_seq_length)
             with torch.cuda.device(dev):
                 for i, (b0, nb, t0, nt, shift) in enumerate(terms):
                     _lib.check(lib.showo_cross_entropy(_lib.ptr(logits), _lib.ptr(lab), L, V, b0, nb, t0, max(nt, 0), shift, -100,
@@ -264,6 +334,47 @@ class Showo(nn.Module):
             loss_t2i, loss_lm, loss_mmu = out[0, 0], out[1, 0], out[2, 0]
             return logits, loss_t2i, loss_lm, loss_mmu
         return logits
+
+    def train_forward(self, input_ids=None, input_embeddings=None, attention_mask=None, labels=None, terms=None,
+                      want_logits=True):
+        """The engine's training forward without autograd plumbing (used by _TrainStep and by the benchmarks): returns
+        (logits or None, losses [3, 2] = {mean, count} per term)."""
+        lib = _lib.require_gpu()
+        eng = self._sync_engine()
+        if input_embeddings is None:
+            B, L = input_ids.shape
+            ids, emb, dev = self._check_ids(input_ids, "Showo.train_forward"), None, input_ids.device
+        else:
+            B, L, _ = input_embeddings.shape
+            ids, emb, dev = None, input_embeddings.detach().float().contiguous(), input_embeddings.device
+        descs = self._mask_descs(attention_mask, B)
+        lab = self._check_ids(labels, "Showo.train_forward(labels)")
+        logits = torch.empty(B, L, self.vocab_size, dtype=torch.float32, device=dev) if want_logits else None
+        losses = torch.empty(3, 2, dtype=torch.float32, device=dev)
+        flat = (C.c_int32 * 15)(*[int(v) for t in terms for v in t])
+        with torch.cuda.device(dev):
+            _lib.check(lib.showo_train_forward(eng, _lib.ptr(ids), _lib.ptr(emb), B, L, _lib.masks_array(descs), _lib.ptr(lab), flat,
+                                               -100, _lib.ptr(logits), _lib.ptr(losses), _lib.current_stream_ptr()), "showo_train_forward")
+        return logits, losses
+
+    def backward(self, loss_grads, want_input_grad_like=None):
+        """showo_backward for loss = sum_i loss_grads[i] * loss_i of the last train_forward; returns d loss / d input_embeddings
+        when `want_input_grad_like` (a [B, L, hidden] tensor) is given."""
+        lib = _lib.require_gpu()
+        g = torch.as_tensor(loss_grads, dtype=torch.float32, device=self._engine_device).contiguous()
+        demb = torch.empty_like(want_input_grad_like, dtype=torch.float32) if want_input_grad_like is not None else None
+        with torch.cuda.device(self._engine_device):
+            _lib.check(lib.showo_backward(self._engine, _lib.ptr(g), _lib.ptr(demb), _lib.current_stream_ptr()), "showo_backward")
+        return demb
+
+    def read_grad(self, name: str, like: Optional[torch.Tensor] = None, shape=None):
+        """Gradient of one parameter (reference state_dict name) as a fresh fp32 tensor."""
+        lib = _lib.require_gpu()
+        out = torch.empty(like.shape if like is not None else shape, dtype=torch.float32, device=self._engine_device)
+        with torch.cuda.device(self._engine_device):
+            _lib.check(lib.showo_read_grad(self._engine, name.encode(), _lib.ptr(out), out.numel(), _lib.current_stream_ptr()),
+                       f"showo_read_grad({name})")
+        return out
 
     # ------------------------------------------------------------------ t2i
     def _t2i_layout(self, input_ids, uncond_input_ids, attention_mask, guidance_scale, config):
@@ -351,7 +462,7 @@ class Showo(nn.Module):
         eng = self._sync_engine()
         if input_embeddings is None:
             B, L0 = idx.shape
-            ids, emb, dev = idx.contiguous(), None, idx.device
+            ids, emb, dev = self._check_ids(idx, "Showo.mmu_generate"), None, idx.device
         else:
             B, L0, _ = input_embeddings.shape
             ids, emb, dev = None, input_embeddings.float().contiguous(), input_embeddings.device

@@ -134,3 +134,38 @@ def train_batch(voc):
 TRAIN_GRAD_PROBES = ["showo.model.layers.0.self_attn.q_proj.weight", "showo.model.layers.0.self_attn.k_layernorm.weight",
                      "showo.model.layers.1.mlp.fc2.bias", "showo.model.layers.1.self_attn.dense.weight",
                      "showo.model.final_layernorm.weight", "showo.lm_head.bias"]
+
+
+# ---------------------------------------------------------------- full-size cases (make_golden_full.py / test_gpu_full_size.py)
+def full_cfg1_inputs(voc):
+    """BASELINE configs[1]: 8 prompts (SURVEY 8d seed 1234), CFG pair rows, all 256 image positions masked."""
+    cond, uncond = O.make_t2i_prompts(8, voc, seed=1234)
+    mask = O.create_attention_mask_predict_next(torch.cat([cond, uncond]))
+    return cond, uncond, mask
+
+
+def full_cfg1_noise(step, B=8, N=256, C=8192):
+    """The noise denoise step `step` consumes, in the reference's order ([B*N, C] exponentials, then [B, N] uniforms)."""
+    r = rng(1000 + step)
+    expo = torch.from_numpy(r.standard_exponential(size=(B * N, C), dtype=np.float32))
+    unif = torch.from_numpy(r.random(size=(B, N), dtype=np.float32))
+    return expo, unif
+
+
+def full_cfg2_inputs(voc):
+    """BASELINE configs[2]: 16 MMU rows [mmu, soi, 256 codes, eoi, bos, 16 question ids], L0 = 276."""
+    r = rng(31)
+    codes = torch.from_numpy(r.integers(0, 8192, size=(16, 256)).astype("int64"))
+    return O.make_mmu_prompts(16, voc, codes, q_len=16, seed=32)
+
+
+def full_cfg3_inputs(voc1024):
+    """BASELINE configs[3] geometry: one CFG pair at N = 1024 (L = 1155), half of the image tokens already decided."""
+    cond, uncond = O.make_t2i_prompts(1, voc1024, seed=77)
+    r = rng(33)
+    fill = torch.from_numpy(r.random(size=(1, 1024), dtype=np.float32) < 0.5)
+    codes = torch.from_numpy(r.integers(0, 8192, size=(1, 1024)).astype("int64")) + voc1024.image_offset
+    cond[:, 130:1154] = torch.where(fill, codes, cond[:, 130:1154])
+    uncond[:, 129:] = cond[:, 129:]
+    mask = O.create_attention_mask_predict_next(torch.cat([cond, uncond]))
+    return cond, uncond, mask

@@ -1,0 +1,225 @@
+"""GPU parity tests of the training step (run with -m gpu): showo_train_forward / showo_backward / showo_read_grad and
+the attention backward kernel, through the C ABI, against (a) the reference's own losses and gradients committed in
+tests/golden/train_step.npz and (b) the oracle's forward differentiated by torch autograd (CPU, fp32) for every parameter.
+
+Tolerances: the engine multiplies in bf16 with fp32 accumulation and keeps bf16 activations; gradients are compared as a
+relative L2 error per tensor (||g - ref|| / ||ref||) and as a norm ratio against the reference's golden norms.  The bound
+is stated next to each assert; the observed values are printed and written to gpurun_out/train_parity.json.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import fixtures as FX
+import showo_b200
+from oracle import showo_oracle as O
+from showo_b200 import _lib, masks as M
+
+pytestmark = pytest.mark.gpu
+VOC = O.ShowoVocab()
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REL_L2_TOL = 0.06            # bf16 operands + bf16 activations, 2 layers + head
+NORM_TOL = 0.03
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda", 0)
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return _lib.require_gpu()
+
+
+def S():
+    return _lib.current_stream_ptr()
+
+
+def _record(key, value):
+    p = os.path.join(ROOT, "gpurun_out", "train_parity.json")
+    os.makedirs(os.path.dirname(p), exist_ok=True)
+    d = json.load(open(p)) if os.path.exists(p) else {}
+    d[key] = value
+    json.dump(d, open(p, "w"), indent=1)
+
+
+def _dense_allowed(desc, L):
+    q = torch.arange(L)[:, None]
+    k = torch.arange(L)[None, :]
+    return O.omni_predicate(q, k, *desc)
+
+
+@pytest.mark.parametrize("n_seq,L,H,descs", [
+    (1, 64, 2, [(0, 0, 0, 0, 0)]),                                        # pure causal, one tile
+    (2, 200, 2, [(17, 130, 200, 0, 0), (0, 0, 0, 0, 0)]),                 # t2i row with left pads + full span, and an lm row
+    (2, 387, 4, [(60, 129, 387, 0, 0), (0, 0, 0, 0, 259)]),               # t2i + mmu window
+    (1, 1155, 2, [(100, 129, 1155, 0, 0)]),                               # 512x512 geometry
+])
+def test_attention_backward_against_autograd(lib, dev, n_seq, L, H, descs):
+    g = torch.Generator().manual_seed(L + H)
+    D = H * 64
+    q, k, v, d_o = (torch.randn(n_seq * L, D, generator=g).bfloat16() for _ in range(4))
+    qf, kf, vf = (t.float().view(n_seq, L, H, 64).transpose(1, 2).clone().requires_grad_(True) for t in (q, k, v))
+    allowed = torch.stack([_dense_allowed(d, L) for d in descs])[:, None]
+    s = (qf @ kf.transpose(-1, -2)) / 8.0
+    s = s.masked_fill(~allowed, float("-inf"))
+    p = s.softmax(-1)
+    o = p @ vf
+    lse2 = torch.logsumexp(s, -1) / np.log(2.0)                                 # exp2 domain
+    dof = d_o.float().view(n_seq, L, H, 64).transpose(1, 2)
+    (o * dof).sum().backward()
+    o_bf = o.detach().transpose(1, 2).reshape(n_seq * L, D).bfloat16()
+    lse_d = lse2.detach().transpose(1, 2).reshape(n_seq * L, H).contiguous().float().to(dev)
+    dq, dk, dv = (torch.full((n_seq * L, D), float("nan"), dtype=torch.bfloat16, device=dev) for _ in range(3))
+    qd, kd, vd, od, dod = (t.contiguous().to(dev) for t in (q, k, v, o_bf, d_o))
+    _lib.check(lib.showo_attention_bwd_test(_lib.ptr(qd), _lib.ptr(kd), _lib.ptr(vd), _lib.ptr(od), _lib.ptr(dod), _lib.ptr(lse_d),
+                                            _lib.ptr(dq), _lib.ptr(dk), _lib.ptr(dv), n_seq, L, H, _lib.masks_array(descs), S()),
+               "attention_bwd_test")
+    torch.cuda.synchronize()
+    errs = {}
+    for name, got, ref in (("dq", dq, qf.grad), ("dk", dk, kf.grad), ("dv", dv, vf.grad)):
+        r = ref.transpose(1, 2).reshape(n_seq * L, D)
+        gt = got.float().cpu()
+        assert torch.isfinite(gt).all(), name
+        errs[name] = float((gt - r).norm() / r.norm())
+    print(f"attention backward L={L}: rel L2 {errs}")
+    _record(f"attention_bwd_L{L}", errs)
+    assert max(errs.values()) < 0.02, errs          # bf16 P / dS operands, bf16 outputs
+
+
+@pytest.fixture(scope="module")
+def tiny_train(dev):
+    dims = O.PhiDims(**FX.TINY)
+    W = O.make_showo_weights(dims, seed=3)
+    m = showo_b200.Showo(False, dims.vocab_size, VOC.llm_vocab_size, phi_dims=FX.TINY, materialize=False)
+    m.load_weights(W, device=dev)
+    return dims, W, m
+
+
+def _oracle_grads(dims, W, ids, mask, labels, sizes, coeff, input_embeddings=None):
+    Wg = {k: v.clone().requires_grad_(True) for k, v in W.items()}
+    if input_embeddings is not None:
+        input_embeddings = input_embeddings.clone().requires_grad_(True)
+        logits = O.showo_logits(Wg, dims, input_embeddings=input_embeddings, add_mask=mask)
+    else:
+        logits = O.showo_logits(Wg, dims, input_ids=ids, add_mask=mask)
+    l = O.showo_losses(logits, labels, *sizes, 128)
+    (coeff[0] * l[0] + coeff[1] * l[1] + coeff[2] * l[2]).backward()
+    return logits.detach(), [float(x) for x in l], {k: v.grad for k, v in Wg.items()}, (input_embeddings.grad if input_embeddings is not None else None)
+
+
+def test_train_step_against_reference_golden_and_oracle_autograd(tiny_train, dev):
+    """losses + gradient norms + gradient probes of the reference (train_step.npz), and every parameter's gradient against the
+    oracle's forward differentiated by autograd."""
+    dims, W, m = tiny_train
+    z = FX.load("train_step.npz")
+    ids, mask, labels, sizes = FX.train_batch(VOC)
+    B, L = ids.shape
+    descs = M.descriptors_from_dense(mask.to(dev))
+    terms = m._loss_terms(B, L, *sizes, 128)
+    logits, losses = m.train_forward(ids.to(dev), None, descs, labels.to(dev), terms)
+    got_l = losses[:, 0].cpu().numpy()
+    print("losses", got_l, "reference", z["losses"], "counts", losses[:, 1].cpu().numpy())
+    assert np.allclose(got_l, z["losses"], rtol=2e-3)
+    dl = np.abs(logits[:, ::32, ::997].cpu().numpy() - z["logits_slice"]).max()
+    assert dl < 0.03, dl
+    # training forward == inference forward of the same engine up to the bf16 rounding of the un-fused q/k/fc1 buffer
+    inf = m(ids.to(dev), attention_mask=descs)
+    assert (inf - logits).abs().max().item() < 0.03
+    m.backward(FX.TRAIN_COEFF)
+    names = [str(n) for n in z["grad_names"]]
+    _, ref_l, ref_g, _ = _oracle_grads(dims, W, ids, mask, labels, sizes, FX.TRAIN_COEFF)
+    table, worst = {}, 0.0
+    for i, k in enumerate(names):
+        g = m.read_grad(k, like=W[k]).cpu()
+        assert torch.isfinite(g).all(), k
+        ref = ref_g[k]
+        rel = float((g - ref).norm() / (ref.norm() + 1e-30))
+        ratio = float(g.double().norm() / z["grad_norms"][i])
+        table[k] = (rel, ratio)
+        worst = max(worst, rel)
+    for k, (rel, ratio) in sorted(table.items(), key=lambda kv: -kv[1][0])[:12]:
+        print(f"  {k:60s} rel L2 {rel:.4f}  norm ratio vs reference {ratio:.4f}")
+    _record("tiny_train_step", {"loss_rel_err": float(np.abs(got_l / z["losses"] - 1).max()), "worst_rel_l2": worst,
+                                "worst_norm_ratio_dev": float(max(abs(r - 1) for _, r in table.values()))})
+    bad = {k: v for k, v in table.items() if v[0] > REL_L2_TOL or abs(v[1] - 1) > NORM_TOL}
+    assert not bad, bad
+    for k in FX.TRAIN_GRAD_PROBES:
+        g = m.read_grad(k, like=W[k]).cpu()
+        got = (g[:8, :8] if g.dim() == 2 else g[:64]).numpy()
+        ref = z["grad:" + k]
+        assert np.abs(got - ref).max() <= 0.08 * np.abs(ref).max() + 1e-9, (k, np.abs(got - ref).max(), np.abs(ref).max())
+    # the backward is deterministic except for the embedding scatter-add (fp32 atomics)
+    m.train_forward(ids.to(dev), None, descs, labels.to(dev), terms, want_logits=False)
+    m.backward(FX.TRAIN_COEFF)
+    k = "showo.model.layers.0.self_attn.q_proj.weight"
+    a = m.read_grad(k, like=W[k])
+    m.train_forward(ids.to(dev), None, descs, labels.to(dev), terms, want_logits=False)
+    m.backward(FX.TRAIN_COEFF)
+    assert torch.equal(a, m.read_grad(k, like=W[k]))
+
+
+def test_train_step_embeddings_input_and_loss_term_quirks(tiny_train, dev):
+    """input_embeddings path (train_w_clip_vit.py): gradient wrt the embeddings; batch_size_mmu = 0 makes the mmu term cover
+    the whole batch (python's -0 slice) and an empty lm slice gives NaN -- both reproduced, and the NaN term does not
+    poison the gradients of the other terms when its coefficient is 0."""
+    dims, W, m = tiny_train
+    ids, mask, labels, _ = FX.train_batch(VOC)
+    ids, mask, labels = ids[:3], mask[:3], labels[:3]
+    B, L = ids.shape
+    emb = W["showo.model.embed_tokens.weight"][ids]
+    sizes, coeff = (2, 0, 0), (1.0, 0.0, 0.5)
+    descs = M.descriptors_from_dense(mask.to(dev))
+    terms = m._loss_terms(B, L, *sizes, 128)
+    _, losses = m.train_forward(None, emb.to(dev), descs, labels.to(dev), terms, want_logits=False)
+    demb = m.backward(coeff, want_input_grad_like=emb.to(dev)).cpu()
+    _, ref_l, ref_g, ref_demb = _oracle_grads(dims, W, ids, mask, labels, sizes, coeff, input_embeddings=emb)
+    got = losses[:, 0].cpu().numpy()
+    assert np.isnan(got[1]) and np.isnan(ref_l[1])
+    assert np.allclose(got[[0, 2]], [ref_l[0], ref_l[2]], rtol=2e-3)
+    rel = float((demb - ref_demb).norm() / ref_demb.norm())
+    print("d input_embeddings rel L2", rel)
+    assert torch.isfinite(demb).all() and rel < REL_L2_TOL
+    k = "showo.lm_head.weight"
+    g = m.read_grad(k, like=W[k]).cpu()
+    assert float((g - ref_g[k]).norm() / ref_g[k].norm()) < REL_L2_TOL
+    assert float(m.read_grad("showo.model.embed_tokens.weight", like=W["showo.model.embed_tokens.weight"]).abs().max()) == 0.0
+
+
+def test_autograd_bridge_matches_engine_gradients(dev):
+    """Showo.forward(labels=...) under autograd + loss.backward() (training/train.py:589-612): parameters of the torch module
+    receive exactly what showo_read_grad returns, an optimizer step re-packs the engine weights, and the loss goes down."""
+    dims = O.PhiDims(**FX.TINY)
+    W = O.make_showo_weights(dims, seed=3)
+    m = showo_b200.Showo(False, dims.vocab_size, VOC.llm_vocab_size, phi_dims=FX.TINY).to(dev)
+    m.load_state_dict({k: v for k, v in W.items()}, strict=True)
+    ids, mask, labels, sizes = FX.train_batch(VOC)
+    kw = dict(attention_mask=mask.to(dev), labels=labels.to(dev), batch_size_t2i=sizes[0], batch_size_lm=sizes[1],
+              batch_size_mmu=sizes[2], max_seq_length=128)
+    opt = torch.optim.SGD(m.parameters(), lr=0.05)
+    logits, l1, l2, l3 = m(ids.to(dev), **kw)
+    assert not logits.requires_grad and l1.requires_grad
+    loss0 = FX.TRAIN_COEFF[0] * l1 + FX.TRAIN_COEFF[1] * l2 + FX.TRAIN_COEFF[2] * l3
+    loss0.backward()
+    p = dict(m.named_parameters())
+    for k in ("showo.model.layers.1.mlp.fc2.weight", "showo.model.layers.0.self_attn.k_layernorm.weight", "showo.lm_head.bias"):
+        assert torch.equal(p[k].grad, m.read_grad(k, like=p[k])), k
+    assert all(q.grad is not None and torch.isfinite(q.grad).all() for q in m.parameters())
+    opt.step()
+    with torch.no_grad():
+        _, a1, a2, a3 = m(ids.to(dev), **kw)
+    loss1 = FX.TRAIN_COEFF[0] * a1 + FX.TRAIN_COEFF[1] * a2 + FX.TRAIN_COEFF[2] * a3
+    print("loss before / after one SGD step", float(loss0), float(loss1))
+    assert float(loss1) < float(loss0)
+    # writes through .data are invisible to autograd's version counter: refresh_engine() is the documented way to pick them up
+    with torch.no_grad():
+        before = m(ids.to(dev), attention_mask=mask.to(dev))
+        p["showo.lm_head.bias"].data.add_(1.0)
+        stale = m(ids.to(dev), attention_mask=mask.to(dev))
+        m.refresh_engine()
+        fresh = m(ids.to(dev), attention_mask=mask.to(dev))
+    assert torch.equal(before, stale) and (fresh - before - 1.0).abs().max().item() < 1e-4
