@@ -197,6 +197,12 @@ SHOWO_API int showo_attention_test(void* qkv_dev, int64_t ld, int n_seq, int row
 SHOWO_API int showo_attention_bwd_test(const void* q_dev, const void* k_dev, const void* v_dev, const void* o_dev, const void* do_dev,
                              const float* lse_dev, void* dq_dev, void* dk_dev, void* dv_dev, int n_seq, int L, int H,
                              const showo_seq_mask_t* masks_host, void* stream);
+/* the prefill / denoise-step attention kernels alone on prepared operands (benchmarks, profiling): q bf16 [n_seq*rows, ld]
+ * (head h at columns 64h..64h+63, already normalised + rotated), K cache [n_seq][H][Lmax][64], V^T cache [n_seq][H][64][Lmax],
+ * descriptors ON THE DEVICE; output to out_dev (row stride out_ld) or, when NULL, in place over q. */
+SHOWO_API int showo_attention_run(void* q_dev, int64_t ld, int n_seq, int rows_per_seq, int pos0, int H, const void* kcache_dev,
+                        const void* vtcache_dev, int Lmax, int n_keys, const showo_seq_mask_t* masks_dev, void* out_dev,
+                        int64_t out_ld, void* stream);
 SHOWO_API int showo_layernorm_test(const float* x_dev, const float* gamma_dev, const float* beta_dev, float eps, void* out_bf16_dev,
                          int rows, int D, void* stream);
 /* NHWC bf16 3x3 (taps=9) or 1x1 (taps=1) convolution, stride 1, same padding; w [cout_pad, taps*cin] bf16 */

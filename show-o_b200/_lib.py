@@ -68,6 +68,7 @@ _PROTOS = {
     "showo_gemm_bf16": (_I, [_P, _I64, _P, _I64, _I, _I, _I, _P, _I64, _P, _P, _I64, _I, _I, _I, _P]),
     "showo_attention_test": (_I, [_P, _I64, _I, _I, _I, _I, _P, _P, _P, _P, _F, _F, _I, _P, _P, _I, _I,
                                   C.POINTER(SeqMask), _P]),
+    "showo_attention_run": (_I, [_P, _I64, _I, _I, _I, _I, _P, _P, _I, _I, _P, _P, _I64, _P]),
     "showo_layernorm_test": (_I, [_P, _P, _P, _F, _P, _I, _I, _P]),
     "showo_conv_test": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
 }

@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(128) omni_attention_kernel(AttnArgs a) {
     pdl_wait();
 
     const int seq = blockIdx.z, h = blockIdx.y;
-    const int q0 = blockIdx.x * 64;
+    const int q0 = a.row_begin + blockIdx.x * 64;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t4 = lane & 3;
     const showo_seq_mask_t msk = a.masks[seq];
@@ -188,9 +188,13 @@ int omni_attention(const AttnArgs& a, cudaStream_t st) {
     if (a.n_seq == 0 || a.rows_per_seq == 0) return 0;
     SHOWO_CHECK(a.Lmax % 64 == 0, "attention: Lmax must be a multiple of 64");
     SHOWO_CHECK(a.n_keys <= a.Lmax, "attention: n_keys exceeds the cache length");
-    if (a.out == nullptr && attention_tc_supported(a)) return omni_attention_tc(a, st);      // whole score row fits in TMEM: tcgen05 path
-    dim3 grid(cdiv(a.rows_per_seq, 64), a.H, a.n_seq);
-    SHOWO_CUDA_OK(launch_kernel(omni_attention_kernel, grid, dim3(128), 0, st, 1, a));
+    // full 128-row tiles of every sequence on tcgen05 / TMEM; the ragged tail (and everything when the switch is off) on mma.sync
+    AttnArgs b = a;
+    b.row_begin = attention_tc_rows(a);
+    if (b.row_begin > 0) SHOWO_TRY(omni_attention_tc(a, st));
+    if (b.row_begin >= a.rows_per_seq) return 0;
+    dim3 grid(cdiv(a.rows_per_seq - b.row_begin, 64), a.H, a.n_seq);
+    SHOWO_CUDA_OK(launch_kernel(omni_attention_kernel, grid, dim3(128), 0, st, 1, b));
     note_launch();
     SHOWO_CUDA_OK(cudaGetLastError());
     return 0;
@@ -396,11 +400,8 @@ int omni_attention_decode(const AttnArgs& a, cudaStream_t st) {
     const size_t smem = (size_t)n_pad * 128 + (size_t)64 * vstride + (size_t)n_pad * 4;
     if (variant == 2 && a.Lmax % 8 == 0 && n_pad <= a.Lmax && smem <= 200 * 1024 && a.ld % 8 == 0 && a.pos0 == a.n_keys - 1 &&
         a.rows_per_seq == 1) {
-        static bool attr = false;
-        if (!attr) {
-            SHOWO_CUDA_OK(cudaFuncSetAttribute(omni_attention_decode_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr = true;
-        }
+        static PerDeviceOnce once;
+        if (once.need()) SHOWO_CUDA_OK(cudaFuncSetAttribute(omni_attention_decode_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         SHOWO_CUDA_OK(launch_kernel(omni_attention_decode_bulk_kernel, grid, dim3(128), smem, st, 1, a, n_pad, vstride));
         note_launch();
         return 0;

@@ -38,6 +38,19 @@ void note_launch(int n = 1);   // counts kernel launches (bench.py's gpu_launche
     } while (0)
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+// "do this once per device" guard for per-context state such as cudaFuncSetAttribute (an engine may live on any device of the
+// process: Showo on cuda:0 and MAGVIT-v2 on cuda:1 share this library)
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool need() {
+        int d = 0;
+        cudaGetDevice(&d);
+        d &= 63;
+        if (done[d]) return false;
+        done[d] = true;
+        return true;
+    }
+};
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 #ifdef __CUDACC__

@@ -492,13 +492,12 @@ int decode_mega_step(const DecodeMegaDesc& d, cudaStream_t st) {
     const int stages = std::min(std::max(stages_env, 2), kSk2MaxStages);
     a.stages = stages;
     const size_t smem = mega_smem_bytes(stages);
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce once;
+    if (once.need()) {
         SHOWO_CUDA_OK(cudaFuncSetAttribute(decode_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         int per_sm = 0;
         SHOWO_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_mega_kernel, kSk2Threads, smem));
         SHOWO_CHECK(per_sm >= 1, "decode_mega_step: kernel does not fit on an SM");
-        attr = true;
     }
     static int prof_mode = -1, prof_calls = 0;
     static unsigned long long* d_prof = nullptr;

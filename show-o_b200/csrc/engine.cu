@@ -718,6 +718,18 @@ int showo_attention_test(void* qkv_dev, int64_t ld, int n_seq, int rows_per_seq,
     return rc;
 }
 
+int showo_attention_run(void* q_dev, int64_t ld, int n_seq, int rows_per_seq, int pos0, int H, const void* kcache_dev,
+                        const void* vtcache_dev, int Lmax, int n_keys, const showo_seq_mask_t* masks_dev, void* out_dev,
+                        int64_t out_ld, void* stream) {
+    SHOWO_CHECK(showo_device_count() > 0, "no sm_100 CUDA device visible: libshowo_b200 has no CPU fallback");
+    SHOWO_CHECK(q_dev && kcache_dev && vtcache_dev && masks_dev, "attention_run: null argument");
+    AttnArgs a{};
+    a.q = (bf16*)q_dev; a.ld = ld; a.n_seq = n_seq; a.H = H; a.rows_per_seq = rows_per_seq; a.pos0 = pos0;
+    a.kcache = (const bf16*)kcache_dev; a.vtcache = (const bf16*)vtcache_dev; a.Lmax = Lmax; a.n_keys = n_keys;
+    a.masks = masks_dev; a.scale = 0.125f; a.out = (bf16*)out_dev; a.out_ld = out_ld;
+    return omni_attention(a, (cudaStream_t)stream);
+}
+
 int showo_conv_test(const void* x_dev, const void* w_dev, const float* bias_dev, const void* resid_dev, void* out_dev,
                     int NB, int H, int W, int cin, int cout, int taps, void* stream) {
     SHOWO_CHECK(showo_device_count() > 0, "no sm_100 CUDA device visible: libshowo_b200 has no CPU fallback");

@@ -115,24 +115,19 @@ int make_tmap_2d(void* out_cutensormap, const void* ptr, uint64_t inner, uint64_
 }
 
 int gemm_num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    }
-    return n;
+    static int n[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (n[dev & 63] == 0) cudaDeviceGetAttribute(&n[dev & 63], cudaDevAttrMultiProcessorCount, dev);
+    return n[dev & 63];
 }
 
 template <int BN, int EPI, int AMODE, int BK = 64, int CL = 1, int CG = 1>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int num_tiles, cudaStream_t st) {
     using Cfg = GemmCfg<BN, BK, CG>;
-    static bool attr_set = false;
+    static PerDeviceOnce once;
     auto kern = gemm_tcgen05_kernel<BN, EPI, AMODE, BK, CL, CG>;
-    if (!attr_set) {
-        SHOWO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-        attr_set = true;
-    }
+    if (once.need()) SHOWO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     int grid = num_tiles < gemm_num_sms() ? num_tiles : gemm_num_sms();
     if constexpr (CL > 1) {
         // num_tiles counts work units (CL m-tiles each); one cluster per unit, as many clusters as fit the SMs
@@ -141,11 +136,12 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams
         SHOWO_CUDA_OK(launch_kernel(kern, dim3(clusters * CL), dim3(Cfg::kThreads), Cfg::kSmemBytes, st, CL, ma, mb, p));
         note_launch();
         return 0;
+    } else {
+        SHOWO_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, st, 1, ma, mb, p));
+        note_launch();
+        SHOWO_CUDA_OK(cudaGetLastError());
+        return 0;
     }
-    SHOWO_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, st, 1, ma, mb, p));
-    note_launch();
-    SHOWO_CUDA_OK(cudaGetLastError());
-    return 0;
 }
 
 template <int BN, int BK = 64, int CL = 1, int CG = 1>

@@ -290,11 +290,9 @@ static int gemm_skinny2(const GemmArgs& a, int epi, const QkvFuse* qf, int tiles
     SHOWO_TRY(make_tmap_2d(&mx, a.A, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda * 2, 64, 16));
 #define SK2_LAUNCH(E)                                                                                             \
     do {                                                                                                          \
-        static bool attr = false;                                                                                 \
-        if (!attr) {                                                                                              \
+        static PerDeviceOnce once;                                                                                \
+        if (once.need())                                                                                          \
             SHOWO_CUDA_OK(cudaFuncSetAttribute(skinny2_gemm_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sk2_smem_bytes(kSk2MaxStages))); \
-            attr = true;                                                                                          \
-        }                                                                                                         \
         SHOWO_CUDA_OK(launch_kernel(skinny2_gemm_kernel<E>, dim3(sc.grid), dim3(kSk2Threads), kSk2Smem, st, 1, mw, mx, p, sc)); \
     } while (0)
     switch (epi) {
@@ -351,11 +349,9 @@ int gemm_skinny(const GemmArgs& a, int epi, const QkvFuse* qf, cudaStream_t st) 
     dim3 grid(tiles, splits);
 #define SK_LAUNCH(E)                                                                                              \
     do {                                                                                                          \
-        static bool attr = false;                                                                                 \
-        if (!attr) {                                                                                              \
+        static PerDeviceOnce once;                                                                                \
+        if (once.need())                                                                                          \
             SHOWO_CUDA_OK(cudaFuncSetAttribute(skinny_gemm_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024)); \
-            attr = true;                                                                                          \
-        }                                                                                                         \
         skinny_gemm_kernel<E><<<grid, kSkThreads, smem, st>>>(p);                                                 \
     } while (0)
     switch (epi) {

@@ -121,10 +121,12 @@ struct AttnArgs {
     // log-sum-exp in the exp2 domain (max * scale * log2e + log2(sum)) is saved at lse[row * H + head]
     bf16* out = nullptr; int64_t out_ld = 0;
     float* lse = nullptr;
+    int row_begin = 0;                   // mma.sync kernel: first query row (of every sequence) it processes
 };
 int omni_attention(const AttnArgs& a, cudaStream_t st);
-// tcgen05/TMEM/TMA variant for n_keys <= 448 (attention_tc.cu); omni_attention() dispatches to it when supported
-bool attention_tc_supported(const AttnArgs& a);
+// tcgen05/TMEM/TMA kernel (attention_tc.cu) for the leading full 128-row tiles of every sequence: attention_tc_rows() says how
+// many rows it takes; omni_attention() sends the remaining rows (row_begin ..) to the mma.sync kernel
+int attention_tc_rows(const AttnArgs& a);
 int omni_attention_tc(const AttnArgs& a, cudaStream_t st);
 // single-query (decode) variant: one query row per sequence at position n_keys-1
 int omni_attention_decode(const AttnArgs& a, cudaStream_t st);

@@ -658,7 +658,9 @@ def test_magvit_get_code_against_golden(vq, dev):
                                 "max_abs_z_at_differing_bit": float(zabs[mism].max()) if mism.any() else 0.0,
                                 "codes_differing": int((codes != codes_ref).sum()), "codes": int(codes.numel()),
                                 "bits_with_abs_z_below_0p03": int((zabs < 0.03).sum())})
-    assert (zabs[mism] < 0.03).all() and mism.float().mean().item() < 0.02     # only bits whose pre-sign value is ~0
+    # observed on B200 (profiles/r2_parity_observed.json): 19 of 3328 bits (0.57 %), largest |z| at a differing bit 0.0122 -- the
+    # bounds are 2x that; 360 bits of the fixture have |z| < 0.03, so 'below the margin' does not mean 'free to differ'
+    assert (zabs[mism] < 0.025).all() and mism.float().mean().item() < 0.012     # only bits whose pre-sign value is ~0
     # encode -> decode -> encode is stable for codes away from the sign boundary (round trip through the engine)
     rec = vq.decode_code(codes.to(dev))
     assert rec.shape == (1, 3, 256, 256) and torch.isfinite(rec).all()

@@ -21,8 +21,8 @@ from showo_b200 import _lib, masks as M
 pytestmark = pytest.mark.gpu
 VOC = O.ShowoVocab()
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-REL_L2_TOL = 0.06            # bf16 operands + bf16 activations, 2 layers + head
-NORM_TOL = 0.03
+REL_L2_TOL = 0.06            # bf16 operands + bf16 activations, 2 layers + head; observed worst 0.030 (profiles/r2_train_parity_observed.json)
+NORM_TOL = 0.01              # observed worst 0.0049
 
 
 @pytest.fixture(scope="module")
@@ -88,7 +88,7 @@ def test_attention_backward_against_autograd(lib, dev, n_seq, L, H, descs):
         errs[name] = float((gt - r).norm() / r.norm())
     print(f"attention backward L={L}: rel L2 {errs}")
     _record(f"attention_bwd_L{L}", errs)
-    assert max(errs.values()) < 0.02, errs          # bf16 P / dS operands, bf16 outputs
+    assert max(errs.values()) < 0.006, errs          # bf16 P / dS operands, bf16 outputs; observed 0.0027
 
 
 @pytest.fixture(scope="module")
