@@ -160,6 +160,31 @@ SHOWO_API int showo_backward(showo_engine_t* e, const float* loss_grads_dev, flo
 /* gradient of one parameter of the reference state_dict (same names as showo_load_weight) -> out_dev (fp32, contiguous) */
 SHOWO_API int showo_read_grad(showo_engine_t* e, const char* name, float* out_dev, int64_t numel, void* stream);
 
+/* The producer of the training step's t2i rows, on the device (training/train.py:468-488): training/utils.py:77-154
+ * mask_or_random_replace_tokens (noise_type "mask", no contiguous-region masking, predict_all_tokens off -- every shipped yaml)
+ * and training/prompting_utils.py:39-90 UniversalPrompting.t2i_prompt.  mode bit 1 = mask step, bit 2 = prompt step; 3 = both in
+ * one launch.
+ *   image_tokens_dev [B, N] int64: codes + text-vocabulary offset (train.py:476-477).  text_ids_dev [B, text_stride] int64 /
+ *   text_len_dev [B] int32: the tokenised captions without specials (tokenisation is host work).  special_ids_host: int64[8] =
+ *   {pad, bos, eos, task (<|t2i|>), soi, eoi, mask_id, ignore_id}.  schedule: 0 cosine, 1 linear, 2 pow (schedule_param), 3 =
+ *   timesteps_dev already holds mask_prob (any Python schedule evaluated by the caller).
+ *   Noise, in the order the reference draws it: timesteps_dev [B] = torch.rand(batch_size), rand_dev [B, N] =
+ *   torch.rand(batch_size, seq_len) (position j is masked iff argsort(rand)[j] < round(N * mask_prob), stable ties),
+ *   drop_probs_dev [B] = torch.rand(len(text_ids)) of t2i_prompt; any of them NULL -> the library's Philox stream keyed by seed.
+ *   Outputs: mode 3 / 2: input_ids_out_dev, labels_out_dev [B, L] int64 with L = max_text_len + 1 + N + 2; attn_ones_out_dev
+ *   optional [B, L + 1] int64 (t2i_prompt's attention_masks: the reference computes the pad count after padding, so the row is
+ *   all ones and one element longer than the sequence); descs_out_dev optional DEVICE array of B mask descriptors (what
+ *   create_attention_mask_predict_next gives for these rows); mask_prob_out_dev optional [B].  mode 1: input_ids_out_dev /
+ *   labels_out_dev are the [B, N] masked ids / labels of mask_or_random_replace_tokens; mode 2 reads them back through
+ *   masked_in_dev / labels_in_dev. */
+SHOWO_API int showo_t2i_train_prep(const int64_t* image_tokens_dev, int B, int N, const int64_t* text_ids_dev,
+                         const int32_t* text_len_dev, int64_t text_stride, int max_text_len, const int64_t* special_ids_host,
+                         float min_masking_rate, float cond_dropout_prob, int schedule, float schedule_param,
+                         const float* timesteps_dev, const float* rand_dev, const float* drop_probs_dev, uint64_t seed,
+                         int mode, const int64_t* masked_in_dev, const int64_t* labels_in_dev, int64_t* input_ids_out_dev,
+                         int64_t* labels_out_dev, int64_t* attn_ones_out_dev, showo_seq_mask_t* descs_out_dev,
+                         float* mask_prob_out_dev, void* stream);
+
 /* seconds spent / kernels launched by the last generate call (for bench.py's gpu_launches) */
 SHOWO_API int64_t showo_kernel_launches(showo_engine_t* e);
 

@@ -199,3 +199,24 @@ def test_train_step_losses_and_gradients_match_reference_golden():
         got = (g[:8, :8] if g.dim() == 2 else g[:64]).numpy()
         ref = z["grad:" + k]
         assert np.abs(got - ref).max() <= 1e-4 * np.abs(ref).max() + 1e-9, k
+
+
+def test_train_input_oracle_against_reference_golden():
+    """oracle/train_inputs_oracle.py (mask_or_random_replace_tokens + t2i_prompt restated on numpy) == the unmodified reference's
+    outputs on the same draws (tests/golden/make_golden_prep.py), bit for bit."""
+    import importlib.util
+    from oracle import train_inputs_oracle as TO
+    spec = importlib.util.spec_from_file_location("make_golden_prep", os.path.join(os.path.dirname(__file__), "golden", "make_golden_prep.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "train_prep.npz"))
+    for name in ("a256", "b1024", "c_trunc"):
+        N, T, rate, drop, texts, codes, _ = mg.case_inputs(name)
+        mp = TO.cosine_mask_prob(z[f"{name}_timesteps"])
+        ids_img, lab_img, mpc = TO.mask_image_tokens(codes.numpy(), 58497, mp, z[f"{name}_rand"], rate)
+        assert np.array_equal(ids_img, z[f"{name}_ids_img"]) and np.array_equal(lab_img, z[f"{name}_lab_img"])
+        assert np.allclose(mpc, z[f"{name}_mask_prob"], rtol=0, atol=1e-6)
+        ids, masks, labels = TO.t2i_prompt_rows(texts, ids_img, lab_img, z[f"{name}_probs"], max_text_len=T, pad=50295, bos=50256, eos=50256,
+                                               task=50300, soi=50296, eoi=50297, cond_dropout_prob=drop)
+        assert np.array_equal(ids, z[f"{name}_ids"]) and np.array_equal(labels, z[f"{name}_labels"]) and np.array_equal(masks, z[f"{name}_masks"])
+        assert np.array_equal(TO.t2i_descriptors(ids, 50295, 50296, 50297), z[f"{name}_descs"])
