@@ -212,7 +212,11 @@ def run_ours(args):
     ids_d = torch.empty_like(cond_h, device=dev)
     cond_d0 = cond_h.to(dev)
 
+    phase_s = {"mask": 0.0, "generate_call": 0.0, "decode_call": 0.0, "tail_sync": 0.0}
+    e2e_step_ms = []
+
     def one_step(e2e: bool):
+        t0 = time.perf_counter()
         if e2e:
             ids_d.copy_(cond_pin, non_blocking=True)           # H2D of this step's prompts (pinned)
             unc_d.copy_(unc_pin, non_blocking=True)
@@ -223,13 +227,19 @@ def run_ours(args):
         else:
             ids_d.copy_(cond_d0)                               # device-resident inputs
             mask = descs
+        t1 = time.perf_counter()
         codes = model.t2i_generate(ids_d, unc_d, mask, guidance_scale=CFG_W, timesteps=T_STEPS, config=cfg)
+        t2 = time.perf_counter()
         imgs = vq.decode_code_uint8(torch.clamp(codes, 0, CODEBOOK - 1))
         if world > 1:
             dist.all_gather_into_tensor(gather_buf, imgs)
+        t3 = time.perf_counter()
         if e2e:
             imgs_pin.copy_(imgs, non_blocking=True)            # D2H of the step's result
             torch.cuda.current_stream().synchronize()
+            t4 = time.perf_counter()                           # host-side split of the e2e step (reported under e2e.host_phases_ms)
+            phase_s["mask"] += t1 - t0; phase_s["generate_call"] += t2 - t1; phase_s["decode_call"] += t3 - t2; phase_s["tail_sync"] += t4 - t3
+            e2e_step_ms.append(round(1e3 * (t4 - t0), 1))
         return imgs
 
     def timed(e2e: bool, steps: int):
@@ -255,14 +265,27 @@ def run_ours(args):
     sampler.start()
     ms_dev = timed(False, args.steps)
     launches = model.kernel_launches() + vq.kernel_launches()
+    for k in phase_s:
+        phase_s[k] = 0.0
     ms_e2e = timed(True, args.steps)
+    host_phases = {k: round(1e3 * v / args.steps, 2) for k, v in phase_s.items()}
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
     # ---- secondaries run on EVERY rank (weak scaling like the headline) and are aggregated below
+    if os.environ.get("SHOWO_BENCH_HEADLINE_ONLY"):           # A/B runs while tuning: the headline line only
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": round(world * B_PER_GPU * args.steps / (ms_dev / 1e3), 3), "ms_per_step": round(ms_dev / args.steps, 3),
+                              "e2e_ms_per_step": round(ms_e2e / args.steps, 3), "e2e_host_phases_ms": host_phases, "e2e_step_ms_all": e2e_step_ms, "clocks": sampler.summary(),
+                              "env": {k: v for k, v in os.environ.items() if k.startswith("SHOWO_")}}), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return None
     mmu_local = mmu_decode_bench(torch, model, vq, dev, measured_peaks(), seed=5 + rank)
     mmu_agg = torch.tensor([mmu_local["ms_per_decode_step"], mmu_local["value"]], device=dev, dtype=torch.float64)
     t512 = t2i512_bench(torch, dist, model, vq, dev, world, rank)
+    train = None if os.environ.get("SHOWO_BENCH_SKIP_TRAIN") else train_step_bench(torch, dist, model, dev, world, rank)
     if world > 1:
         mx = mmu_agg.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
@@ -323,7 +346,7 @@ def run_ours(args):
                        "global_batch": world * B_PER_GPU, "seq_len": L_SEQ, "timesteps": T_STEPS, "guidance": CFG_W,
                        "parallelism": f"dp{world}", "l2": "weights 2.9 GB bf16 streamed every step >> 126 MB L2 (no flush needed)"},
             "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": int(2 * cond_h.numel() * 8),
-                    "d2h_bytes_per_step": int(imgs_pin.numel()), "ms_per_step": round(ms_e2e / args.steps, 3)},
+                    "d2h_bytes_per_step": int(imgs_pin.numel()), "ms_per_step": round(ms_e2e / args.steps, 3), "host_phases_ms": host_phases},
             "gpu_launches": int(launches * args.steps),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": round(kern_tflops, 1), "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
@@ -339,6 +362,7 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "secondary": mmu,
             "secondary_t2i512": t512,
+            "secondary_train": train,
         }
         print(json.dumps(out), flush=True)
     if world > 1:
@@ -408,6 +432,99 @@ def t2i512_bench(torch, dist, model, vq, dev, world, rank, warm=1, steps=2):
                          "unit": "TFLOP/s per GPU", "frac": round(f_img * value / world / 1e12 / peaks["bf16_sustained"], 4),
                          "algorithmic_tflop_per_image": round(f_img / 1e12, 2), "kernel": "whole job (SURVEY 8d F_img at N=1024 + decode)"}}
 
+
+
+class _BenchTokenizer:
+    """id layout of the Show-o tokenizer (phi-1.5 vocabulary + [PAD] + the nine task / span tokens); tokenisation itself is host work
+    outside the hot path, the bench feeds synthetic caption ids"""
+    bos_token_id = eos_token_id = 50256
+    pad_token_id = 50295
+    _ids = {"[PAD]": 50295, "<|soi|>": 50296, "<|eoi|>": 50297, "<|sov|>": 50298, "<|eov|>": 50299, "<|t2i|>": 50300,
+            "<|mmu|>": 50301, "<|t2v|>": 50302, "<|v2v|>": 50303, "<|lvg|>": 50304}
+
+    def add_special_tokens(self, d):
+        return 0
+
+    def add_tokens(self, t):
+        return 0
+
+    def convert_tokens_to_ids(self, t):
+        return [self._ids[x] for x in t] if isinstance(t, (list, tuple)) else self._ids[t]
+
+    def __len__(self):
+        return 50305
+
+
+def train_step_bench(torch, dist, model, dev, world, rank, warm=1, steps=2):
+    """BASELINE.json configs[4]: showo_demo_w_clip_vit_512x512.yaml mixed t2i + lm + mmu training step, forward / backward in bf16
+    (fp32 master gradients), per-GPU micro-batch 8 rows of L = 1155 (3 t2i + 1 lm + 4 mmu-vit), data parallel:
+    the t2i rows come from the device-side producer (showo_t2i_train_prep), the fp32 gradients (5.8 GB) are all-reduced per layer
+    on a side stream while the earlier layers' backward runs.  No optimizer step (the reference's AdamW is torch's)."""
+    from showo_b200 import train_inputs as TI
+    L5, N5, B_T2I, B_LM, B_MMU = 1155, 1024, 3, 1, 4
+    g = torch.Generator().manual_seed(777 + rank)
+    up = TI.UniversalPrompting(_BenchTokenizer(), max_text_len=P_TXT - 1, ignore_id=-100, cond_dropout_prob=0.1)
+
+    class _Cfg(dict):
+        __getattr__ = dict.get
+    cfg = _Cfg(training=_Cfg(min_masking_rate=0.0, noise_type="mask"))
+    codes = (torch.randint(0, CODEBOOK, (B_T2I, N5), generator=g) + 50305).to(dev)
+    texts = [torch.randint(0, 50256, (int(torch.randint(8, 65, (1,), generator=g)),), generator=g).tolist() for _ in range(B_T2I)]
+    lm_ids = torch.randint(0, 50257, (B_LM, L5), generator=g).to(dev)
+    mmu_ids = torch.randint(0, 50257, (B_MMU, L5), generator=g).to(dev)
+    mmu_lab = torch.full((B_MMU, L5), -100, dtype=torch.int64)
+    mmu_lab[:, L5 - 548:] = mmu_ids[:, L5 - 548:].cpu()
+    mmu_lab = mmu_lab.to(dev)
+    loss_w = torch.tensor([1.0, 0.1, 1.0], device=dev)          # training.t2i_coeff / lm_coeff / mmu_coeff of the yaml
+    comm = torch.cuda.Stream(dev) if world > 1 else None
+
+    def step():
+        torch.manual_seed(1000 + rank)
+        ids_t2i, lab_t2i, _, descs_t2i = up.t2i_train_rows(texts, codes, V - 1, cfg, showo_b200_cosine())
+        ids = torch.cat([ids_t2i, lm_ids, mmu_ids])
+        labels = torch.cat([lab_t2i, lm_ids, mmu_lab])
+        descs = [tuple(r) for r in descs_t2i.tolist()] + [(0, 0, 0, 0, 0)] * B_LM + [(0, 0, 0, 30, 606)] * B_MMU
+        terms = model._loss_terms(ids.shape[0], L5, B_T2I, B_LM, B_MMU, P_TXT - 1)
+        _, losses = model.train_forward(ids, None, descs, labels, terms, want_logits=False)
+        if world > 1:
+            done = model.backward_overlapped(loss_w, comm_stream=comm)
+            torch.cuda.current_stream().wait_event(done)
+        else:
+            model.backward(loss_w)
+        return losses
+    for _ in range(warm):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        losses = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item()) / steps
+    B = B_T2I + B_LM + B_MMU
+    f_step = 3 * B * L5 * (G_TOK + A_PAIR * L5 + 2 * D * V)
+    peaks = measured_peaks()
+    return {"metric": "train_step_tokens_per_sec_mixed_t2i_lm_mmu_L1155", "value": round(world * B * L5 / ms * 1e3, 1), "unit": "tokens/s",
+            "n_gpus": world, "ms_per_step": round(ms, 2), "steps": steps, "warmup": warm,
+            "config": {"workload": "showo_demo_w_clip_vit_512x512.yaml geometry: forward + backward of 8 rows x L=1155 per GPU (3 t2i from the "
+                                   "device-side producer + 1 lm + 4 mmu-vit), bf16 operands / fp32 gradients, per-layer gradient all-reduce "
+                                   "(fp32, 5.8 GB) overlapped with backward for N > 1; no optimizer step",
+                       "global_batch": world * B, "seq_len": L5},
+            "losses": [round(float(x), 4) for x in losses[:, 0].tolist()],
+            "roofline": {"bound": "tensor", "achieved": round(f_step / ms / 1e9, 1), "peak": peaks["bf16_sustained"], "unit": "TFLOP/s per GPU",
+                         "frac": round(f_step / ms / 1e9 / peaks["bf16_sustained"], 4), "algorithmic_tflop_per_step": round(f_step / 1e12, 2),
+                         "kernel": "whole step (3 x forward FLOPs, SURVEY 8d config 5)"}}
+
+
+def showo_b200_cosine():
+    from showo_b200 import cosine_schedule
+    return cosine_schedule
 
 def cpu_mmu_sample(n_tokens=2):
     """The reference's MMU path on the host cores (modeling_showo.py:183-240: B = 1, NO KV cache, the whole sequence is

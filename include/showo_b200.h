@@ -157,6 +157,15 @@ SHOWO_API int showo_train_forward(showo_engine_t* e, const int64_t* ids_dev, con
  * [B, L, hidden] fp32, receives the gradient wrt the input embeddings (the mm_projector / embed_tokens side of
  * train_w_clip_vit.py).  loss_grads_dev: float[3] on the device. */
 SHOWO_API int showo_backward(showo_engine_t* e, const float* loss_grads_dev, float* dembeds_out_dev, void* stream);
+/* The same backward in phases, so that the caller can overlap the gradient all-reduce of finished parameters with the backward of
+ * the earlier layers (what DDP's buckets do under accelerate, training/train.py:612): phase -1 = loss, head and final LayerNorm,
+ * then phase l = decoder layer l for l = n_layers-1 .. 0, then phase -2 = embedding (+ dembeds_out_dev).  showo_backward runs all
+ * of them in this order. */
+SHOWO_API int showo_backward_phase(showo_engine_t* e, int phase, const float* loss_grads_dev, float* dembeds_out_dev, void* stream);
+/* The engine's gradient buffer (fp32, one allocation, the packed layout of the weights) and the [begin, end) element range a phase
+ * of showo_backward_phase writes: the buckets of the data-parallel gradient all-reduce. */
+SHOWO_API int showo_grad_buffer(showo_engine_t* e, float** base_dev, int64_t* numel);
+SHOWO_API int showo_grad_range(showo_engine_t* e, int phase, int64_t* begin, int64_t* end);
 /* gradient of one parameter of the reference state_dict (same names as showo_load_weight) -> out_dev (fp32, contiguous) */
 SHOWO_API int showo_read_grad(showo_engine_t* e, const char* name, float* out_dev, int64_t numel, void* stream);
 

@@ -46,5 +46,48 @@ def full(path):
         print()
 
 
+def sass_summary(lib_path):
+    """per-kernel counts of the Blackwell-native SASS mnemonics (tcgen05 MMA = UTCHMMA / UTCQMMA..., TMEM ld/st = LDTM / STTM,
+    TMA = UTMALDG / UTMASTG / UBLKCP, mbarrier = SYNCS) next to the legacy tensor-core HMMA, from `cuobjdump -sass`."""
+    import collections
+    import re
+    import subprocess
+    txt = subprocess.run(["cuobjdump", "-sass", lib_path], capture_output=True, text=True).stdout
+    pats = {"UTCHMMA": r"\bUTC[A-Z]*MMA\b", "LDTM": r"\bLDTM\b", "STTM": r"\bSTTM\b", "UTMALDG": r"\bUTMALDG\b", "UTMASTG": r"\bUTMASTG\b",
+            "UBLKCP": r"\bUBLKCP\b", "SYNCS": r"\bSYNCS\b", "HMMA": r"\bHMMA\b", "MUFU.EX2": r"\bMUFU\.EX2\b", "LDGSTS": r"\bLDGSTS\b"}
+    counts = collections.OrderedDict()
+    cur = None
+    for line in txt.splitlines():
+        m = re.match(r"\s*Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            counts[cur] = collections.Counter()
+            continue
+        if cur is None:
+            continue
+        for k, p in pats.items():
+            if re.search(p, line):
+                counts[cur][k] += 1
+    dem = subprocess.run(["cu++filt"] + list(counts), capture_output=True, text=True).stdout.splitlines()
+    names = dict(zip(counts, dem)) if len(dem) == len(counts) else {k: k for k in counts}
+    cols = list(pats)
+    print("# cuobjdump -sass %s : instruction counts per kernel" % lib_path)
+    print("%-110s " % "kernel" + " ".join("%8s" % c for c in cols))
+    tot = collections.Counter()
+    for k, c in counts.items():
+        full = names[k].replace("void ", "").replace("showo::", "")
+        depth, cut = 0, len(full)
+        for i, ch in enumerate(full):          # cut at the parameter list: the first "(" outside the template brackets
+            depth += ch == "<"
+            depth -= ch == ">"
+            if ch == "(" and depth == 0:
+                cut = i
+                break
+        label = full[:cut][:110]
+        print("%-110s " % label + " ".join("%8d" % c[x] for x in cols))
+        tot.update(c)
+    print("%-110s " % "TOTAL" + " ".join("%8d" % tot[x] for x in cols))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "sass": sass_summary}[sys.argv[1]](sys.argv[2])

@@ -184,6 +184,7 @@ __global__ void __launch_bounds__(128) omni_attention_kernel(AttnArgs a) {
     }
 }
 
+
 int omni_attention(const AttnArgs& a, cudaStream_t st) {
     if (a.n_seq == 0 || a.rows_per_seq == 0) return 0;
     SHOWO_CHECK(a.Lmax % 64 == 0, "attention: Lmax must be a multiple of 64");
@@ -191,6 +192,8 @@ int omni_attention(const AttnArgs& a, cudaStream_t st) {
     // full 128-row tiles of every sequence on tcgen05 / TMEM; the ragged tail (and everything when the switch is off) on mma.sync
     AttnArgs b = a;
     b.row_begin = attention_tc_rows(a);
+    const int n_tail = a.rows_per_seq - b.row_begin;
+    if (b.row_begin > 0 && attention_tc_tail_rows(a) == n_tail) return omni_attention_tc(a, st);     // the kernel's tail phase takes them
     if (b.row_begin > 0) SHOWO_TRY(omni_attention_tc(a, st));
     if (b.row_begin >= a.rows_per_seq) return 0;
     dim3 grid(cdiv(a.rows_per_seq - b.row_begin, 64), a.H, a.n_seq);
@@ -283,11 +286,6 @@ __global__ void __launch_bounds__(128) omni_attention_decode_kernel(AttnArgs a) 
 // each V^T row is a contiguous run, so ONE cp.async.bulk brings K and 64 row copies bring V^T -- all bytes of the CTA are
 // in flight at once (70 KB at 276 keys, 2-3 CTAs per SM) instead of a few 16 B loads per thread, and the math then
 // runs out of shared memory: 8 lanes per key (one 128 B row per quarter-warp, conflict-free), two threads per output dim.
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
 
 __global__ void __launch_bounds__(128) omni_attention_decode_bulk_kernel(AttnArgs a, int n_pad, int vstride) {
     extern __shared__ __align__(128) uint8_t dec_smem[];
@@ -301,6 +299,8 @@ __global__ void __launch_bounds__(128) omni_attention_decode_bulk_kernel(AttnArg
     if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
     __syncthreads();
     pdl_trigger();
+    if (a.l2_prefetch_bytes)         // the successor GEMM's weights -> L2 while this kernel streams the cache
+        l2_prefetch_slice(a.l2_prefetch, a.l2_prefetch_bytes, (int)(blockIdx.y * gridDim.x + blockIdx.x) * 128 + tid, (int)(gridDim.x * gridDim.y) * 128);
     // Only the row / column of the current token (position n_keys - 1) comes from the predecessor GEMM; everything older was
     // written by earlier decode steps, so those bytes are requested BEFORE griddepcontrol.wait and stream in while the
     // predecessor drains.

@@ -29,6 +29,32 @@ __device__ __forceinline__ bool omni_tile_all_allowed(const showo_seq_mask_t& m,
     const bool win = (k_lo >= m.win_begin) && (k_hi <= m.win_end);
     return causal || full || win;
 }
+
+// The keys one query row may attend to, as (at most) two half-open intervals [a0,a1) U [b0,b1) of [0, n_keys):
+//   row past the left pads : [pad_end, ...) only;  bidirectional row : everything up to n_keys;
+//   otherwise              : the causal prefix [.., q] plus the always-visible window.
+struct RowKeys { int a0, a1, b0, b1; };
+__device__ __forceinline__ RowKeys omni_row_keys(const showo_seq_mask_t& m, int q, int n_keys) {
+    const int lo = q >= m.pad_end ? m.pad_end : 0;
+    RowKeys r;
+    r.a0 = lo;
+    if (q >= m.full_begin && q < m.full_end) { r.a1 = n_keys; r.b0 = 0; r.b1 = 0; return r; }
+    r.a1 = min(q + 1, n_keys);
+    r.b0 = max(m.win_begin, lo);
+    r.b1 = max(min(m.win_end, n_keys), r.b0);
+    return r;
+}
+// bit c of the result: is key k0 + c inside [lo, hi) ?   (64 keys per block)
+__device__ __forceinline__ uint64_t omni_range_bits(int lo, int hi, int k0) {
+    lo = max(lo - k0, 0); hi = min(hi - k0, 64);
+    return hi > lo ? ((~0ull >> (64 - (hi - lo))) << lo) : 0ull;
+}
+// 1-D bulk copy global -> shared, completing on an mbarrier (size and both addresses multiples of 16 bytes)
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_row) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])

@@ -126,6 +126,33 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
+// Pull this thread's slice of a contiguous global range into L2 (cp.async.bulk.prefetch.L2, 4 KB pieces): participant
+// `who` of `n_who` takes the pieces who, who + n_who, ...  Used by the decode kernels to fetch the NEXT kernel's weights while the
+// current one still streams its own: the chain's kernels cannot share an SM (their smem rings are too large), so without this
+// HBM idles during every kernel's tail / the successor's gated start.
+__device__ __forceinline__ void l2_prefetch_slice(const void* base, size_t bytes, int who, int n_who) {
+    const char* p = reinterpret_cast<const char*>(base);
+    for (size_t off = (size_t)who * 4096; off < bytes; off += (size_t)n_who * 4096) {
+        const uint32_t n = (uint32_t)((bytes - off < 4096 ? bytes - off : 4096) & ~(size_t)15);
+        if (n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(p + off)), "r"(n) : "memory");
+    }
+}
+
+// Same wait for the single-lane helper roles (TMA producer, MMA issuer) that share a scheduler with busy compute warps: a failed
+// poll backs off with nanosleep instead of re-issuing at once, so the spin does not take issue slots from the warps it waits for.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns = 32) {
+    uint32_t done;
+    for (;;) {
+        asm volatile(
+            "{\n\t.reg .pred P1;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, P1;\n\t}\n"
+            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done) return;
+        if (ns) __nanosleep(ns);
+    }
+}
+
 // ---- TMA (cp.async.bulk.tensor), tile mode, completes on an mbarrier
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

@@ -62,6 +62,8 @@ struct showo_engine {
     float* logits_ws = nullptr; float* conf_ws = nullptr; int* sampled_ws = nullptr;
     int64_t* tok_ws = nullptr; int64_t tok_ws_cap = 0;
     unsigned long long* argmax_keys = nullptr;            // [16] packed (logit, ~index) maxima of the fused greedy head
+    int* attn_ctr = nullptr;                              // work counter of the attention kernel's tail phase (self-resetting, zero between launches)
+    int* finished_ws = nullptr;                           // [64] rows of the running mmu_generate that have produced eot_token
     int64_t launches_last = 0;
     showo::TrainState* train = nullptr;                  // training-step buffers (train.cu), allocated on first use
 };

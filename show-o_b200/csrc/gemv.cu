@@ -176,6 +176,8 @@ __global__ void __launch_bounds__(kSk2Threads, 1) skinny2_gemm_kernel(const __gr
                 else if (lane == 10) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.qf.sin_tab + (int64_t)p.qf.pos0 * 32));
             }
         }
+        if (lane > 0 && p.l2_prefetch_bytes)      // idle lanes: the successor kernel's weights -> L2, this CTA's 1/grid share
+            l2_prefetch_slice(p.l2_prefetch, p.l2_prefetch_bytes, (int)blockIdx.x * 31 + (lane - 1), (int)gridDim.x * 31);
         if (lane == 0) {
             const int n = c_end - c_begin;
             const int pre = n < kSk2Stages ? n : kSk2Stages;
@@ -219,6 +221,8 @@ __global__ void __launch_bounds__(kSk2Threads, 1) skinny2_gemm_kernel(const __gr
     RingPos rp{0, 0u};
     sk2_consume<EPI>(p, sc, sm, blockIdx.x, c_begin, c_end, rp);
 }
+
+
 
 static int skinny_stages() {
     static int v = -1;
@@ -282,6 +286,7 @@ static int gemm_skinny2(const GemmArgs& a, int epi, const QkvFuse* qf, int tiles
     p.out = a.out; p.ldc = a.ldc; p.bias = a.bias; p.resid = a.resid; p.ldr = a.ldr; p.gelu_from = a.gelu_from;
     if (qf) p.qf = *qf;
     p.argmax_keys = a.argmax_keys;
+    p.l2_prefetch = a.l2_prefetch; p.l2_prefetch_bytes = a.l2_prefetch_bytes;
     if (epi == SK_ARGMAX) SHOWO_CHECK(a.argmax_keys != nullptr, "gemm_skinny: argmax epilogue needs a key buffer");
     SHOWO_TRY(ensure_skinny_ws((size_t)sc.grid * 2 * 1024, (size_t)tiles, st));
     p.partials = g_partials; p.tickets = g_tickets;

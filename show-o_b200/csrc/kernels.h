@@ -23,6 +23,8 @@ struct GemmArgs {
     int block_n;                      // 0 = auto, else 64 / 128 / 256
     // decode-path extras (gemm_skinny only): fused input LayerNorm of fp32 rows, greedy argmax epilogue
     unsigned long long* argmax_keys = nullptr;
+    // decode path: bytes the NEXT kernel of the chain will stream (its weights), pulled into L2 while this kernel runs
+    const void* l2_prefetch = nullptr; size_t l2_prefetch_bytes = 0;
 };
 int gemm_bf16(const GemmArgs& a, GemmEpi epi, cudaStream_t st);
 
@@ -122,12 +124,17 @@ struct AttnArgs {
     bf16* out = nullptr; int64_t out_ld = 0;
     float* lse = nullptr;
     int row_begin = 0;                   // mma.sync kernel: first query row (of every sequence) it processes
+    int* work_ctr = nullptr;             // tcgen05 kernel: self-resetting work counter of its tail phase (engine-owned; NULL: per-device default)
+    // decode kernel: bytes the next kernel of the chain will stream (its weights), pulled into L2 while this kernel runs
+    const void* l2_prefetch = nullptr; size_t l2_prefetch_bytes = 0;
 };
 int omni_attention(const AttnArgs& a, cudaStream_t st);
 // tcgen05/TMEM/TMA kernel (attention_tc.cu) for the leading full 128-row tiles of every sequence: attention_tc_rows() says how
 // many rows it takes; omni_attention() sends the remaining rows (row_begin ..) to the mma.sync kernel
 int attention_tc_rows(const AttnArgs& a);
 int omni_attention_tc(const AttnArgs& a, cudaStream_t st);
+int attention_tc_tail_rows(const AttnArgs& a);   // trailing rows the tcgen05 kernel takes itself (its tail phase), else 0
+int attention_tc_tail_rows(const AttnArgs& a);   // trailing rows the tcgen05 kernel handles itself (its tail phase), else 0
 // single-query (decode) variant: one query row per sequence at position n_keys-1
 int omni_attention_decode(const AttnArgs& a, cudaStream_t st);
 

@@ -184,15 +184,26 @@ extern "C" int showo_mask_descriptors(const void* mask_dev, int elem_bytes, int 
     SHOWO_CHECK(elem_bytes == 4 || elem_bytes == 1, "mask_descriptors: fp32 (additive) or 1-byte (bool) masks only");
     SHOWO_CHECK(showo_device_count() > 0, "no sm_100 CUDA device visible: libshowo_b200 has no CPU fallback");
     cudaStream_t st = (cudaStream_t)stream;
-    int* d = nullptr;
-    SHOWO_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&d), (size_t)B * 6 * 4, st));
+    // result buffer: one per device, grown on demand (a cudaMallocAsync per call made the first calls after every sync slow:
+    // the pool hands its memory back at each synchronisation)
+    static int* bufs[64] = {};
+    static int caps[64] = {};
+    int dev = 0;
+    SHOWO_CUDA_OK(cudaGetDevice(&dev));
+    int*& d = bufs[dev & 63];
+    if (caps[dev & 63] < B) {
+        SHOWO_CUDA_OK(cudaStreamSynchronize(st));
+        if (d) cudaFree(d);
+        d = nullptr;
+        SHOWO_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&d), (size_t)B * 6 * 4));
+        caps[dev & 63] = B;
+    }
     if (elem_bytes == 4) mask_descriptor_kernel<float><<<B, 256, 0, st>>>((const float*)mask_dev, batch_stride_elems, L, d);
     else mask_descriptor_kernel<uint8_t><<<B, 256, 0, st>>>((const uint8_t*)mask_dev, batch_stride_elems, L, d);
     note_launch();
     std::vector<int> h((size_t)B * 6);
     SHOWO_CUDA_OK(cudaMemcpyAsync(h.data(), d, h.size() * 4, cudaMemcpyDeviceToHost, st));
     SHOWO_CUDA_OK(cudaStreamSynchronize(st));
-    cudaFreeAsync(d, st);
     for (int b = 0; b < B; ++b) {
         out_host[b] = showo_seq_mask_t{h[b * 6], h[b * 6 + 1], h[b * 6 + 2], h[b * 6 + 3], h[b * 6 + 4]};
         mismatches_host[b] = h[b * 6 + 5];

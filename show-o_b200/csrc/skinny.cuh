@@ -14,6 +14,7 @@ struct SkinnyParams {
     float* partials; int* tickets;
     QkvFuse qf;
     unsigned long long* argmax_keys;     // SK_ARGMAX: per-row packed (orderable logit, ~index) maxima, atomicMax'ed
+    const void* l2_prefetch; size_t l2_prefetch_bytes;      // the next kernel's weights -> L2 (idle producer lanes)
 };
 
 __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {

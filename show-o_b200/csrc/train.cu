@@ -688,7 +688,7 @@ int showo_train_forward(showo_engine_t* e, const int64_t* ids_dev, const float* 
         SHOWO_CUDA_OK(cudaGetLastError());
         AttnArgs a{};
         a.q = t->qrot + (size_t)l * mD; a.ld = D; a.n_seq = B; a.H = H; a.rows_per_seq = L; a.pos0 = 0;
-        a.kcache = e->kcache; a.vtcache = e->vtcache; a.Lmax = e->cap_L; a.n_keys = L; a.masks = e->d_masks; a.scale = 0.125f;
+        a.kcache = e->kcache; a.vtcache = e->vtcache; a.Lmax = e->cap_L; a.n_keys = L; a.masks = e->d_masks; a.scale = 0.125f; a.work_ctr = e->attn_ctr;
         a.out = a2; a.out_ld = W2K; a.lse = t->lse + (size_t)l * M * H;
         SHOWO_TRY(omni_attention(a, st));
         GemmArgs g2{};
@@ -724,18 +724,15 @@ int showo_train_forward(showo_engine_t* e, const int64_t* ids_dev, const float* 
     return 0;
 }
 
-int showo_backward(showo_engine_t* e, const float* loss_grads_dev, float* dembeds_out_dev, void* stream) {
-    SHOWO_TRY(engine_check_ready(e));
-    SHOWO_CHECK(e->train && e->train->have_forward, "backward: call showo_train_forward first");
-    SHOWO_CHECK(loss_grads_dev != nullptr, "backward: null loss gradients");
-    cudaStream_t st = (cudaStream_t)stream;
-    const int64_t l0 = launches_total();
+// phase -1: loss -> dlogits -> head + final LayerNorm;  phase l in [0, NL): decoder layer l (in DEcreasing order);  phase -2: embedding
+static int backward_phase(showo_engine_t* e, int phase, const float* loss_grads_dev, float* dembeds_out_dev, cudaStream_t st) {
     TrainState* t = e->train;
     const int M = t->M, B = t->B, L = t->L, D = e->D, H = e->H, W1N = e->W1N, W2K = e->W2K, V = e->V, NL = e->NL, F = e->F;
     const int64_t Mp = (int64_t)(M + 7) / 8 * 8, Vp = t->Vp;
     const size_t mD = (size_t)M * D;
     const GradLayout gl = grad_layout(e);
     float* G = t->grads;
+    if (phase == -1) {
     // ---- loss -> dlogits (bf16) -> head
     CeBwdArgs c{};
     c.logits = t->logits_used; c.labels = t->labels; c.L = L; c.V = V; c.Vp = Vp; c.ignore_index = t->ignore_index;
@@ -754,7 +751,10 @@ int showo_backward(showo_engine_t* e, const float* loss_grads_dev, float* dembed
     // final LayerNorm
     SHOWO_TRY(layernorm_backward(t, t->dxh, t->xs + (size_t)NL * mD, t->stats + (size_t)NL * M, e->fln_g, t->dx, false, G + gl.fln_g,
                                  G + gl.fln_b, M, D, st));
-    for (int l = NL - 1; l >= 0; --l) {
+        return 0;
+    }
+    if (phase >= 0) {
+        const int l = phase;
         const LayerW& w = e->layers[l];
         float* GL = G + gl.per_layer * l;
         const bf16* pre = t->pre + (size_t)l * M * W1N;
@@ -795,6 +795,7 @@ int showo_backward(showo_engine_t* e, const float* loss_grads_dev, float* dembed
         SHOWO_TRY(gemm_plain(t->dpre, W1N, t->w1t + (size_t)l * D * W1N, W1N, M, D, W1N, t->dxh, D, true, st));
         SHOWO_TRY(layernorm_backward(t, t->dxh, t->xs + (size_t)l * mD, t->stats + (size_t)l * M, w.ln_g, t->dx, true, GL + gl.ln_g,
                                      GL + gl.ln_b, M, D, st));
+        return 0;
     }
     if (t->from_ids) {
         SHOWO_CUDA_OK(cudaMemsetAsync(G + gl.embed, 0, (size_t)V * D * 4, st));
@@ -805,7 +806,45 @@ int showo_backward(showo_engine_t* e, const float* loss_grads_dev, float* dembed
         SHOWO_CUDA_OK(cudaMemsetAsync(G + gl.embed, 0, (size_t)V * D * 4, st));
     }
     if (dembeds_out_dev) SHOWO_CUDA_OK(cudaMemcpyAsync(dembeds_out_dev, t->dx, mD * 4, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+static int backward_check(showo_engine_t* e, const float* loss_grads_dev) {
+    SHOWO_TRY(engine_check_ready(e));
+    SHOWO_CHECK(e->train && e->train->have_forward, "backward: call showo_train_forward first");
+    SHOWO_CHECK(loss_grads_dev != nullptr, "backward: null loss gradients");
+    return 0;
+}
+
+int showo_backward(showo_engine_t* e, const float* loss_grads_dev, float* dembeds_out_dev, void* stream) {
+    SHOWO_TRY(backward_check(e, loss_grads_dev));
+    const int64_t l0 = launches_total();
+    SHOWO_TRY(backward_phase(e, -1, loss_grads_dev, nullptr, (cudaStream_t)stream));
+    for (int l = e->NL - 1; l >= 0; --l) SHOWO_TRY(backward_phase(e, l, loss_grads_dev, nullptr, (cudaStream_t)stream));
+    SHOWO_TRY(backward_phase(e, -2, loss_grads_dev, dembeds_out_dev, (cudaStream_t)stream));
     e->launches_last = launches_total() - l0;
+    return 0;
+}
+
+int showo_backward_phase(showo_engine_t* e, int phase, const float* loss_grads_dev, float* dembeds_out_dev, void* stream) {
+    SHOWO_TRY(backward_check(e, loss_grads_dev));
+    SHOWO_CHECK(phase >= -2 && phase < e->NL, "backward_phase: phase must be -1 (head), a layer index, or -2 (embedding)");
+    return backward_phase(e, phase, loss_grads_dev, dembeds_out_dev, (cudaStream_t)stream);
+}
+
+int showo_grad_buffer(showo_engine_t* e, float** base_dev, int64_t* numel) {
+    SHOWO_CHECK(e && e->train && e->train->grads && base_dev && numel, "grad_buffer: no training state (call showo_train_forward first)");
+    *base_dev = e->train->grads;
+    *numel = grad_layout(e).total;
+    return 0;
+}
+
+int showo_grad_range(showo_engine_t* e, int phase, int64_t* begin, int64_t* end) {
+    SHOWO_CHECK(e && begin && end && phase >= -2 && phase < e->NL, "grad_range: bad arguments");
+    const GradLayout gl = grad_layout(e);
+    if (phase >= 0) { *begin = gl.per_layer * phase; *end = gl.per_layer * (phase + 1); }
+    else if (phase == -1) { *begin = gl.head_w; *end = gl.embed; }
+    else { *begin = gl.embed; *end = gl.total; }
     return 0;
 }
 

@@ -90,21 +90,40 @@ class MAGVITv2(nn.Module):
         self._versions = None
         self._streamed = False
 
-    # state_dict under the reference's dotted names
-    def state_dict(self, *args, **kwargs):
-        return {self._names[k]: v for k, v in self._parameters.items()}
+    # state_dict under the reference's dotted names (nn.Module forbids dots in parameter names: they are registered with "__")
+    def state_dict(self, *args, destination=None, prefix="", keep_vars=False, **kwargs):
+        if args:                         # legacy positional form (destination, prefix, keep_vars)
+            destination = args[0]
+            prefix = args[1] if len(args) > 1 else prefix
+            keep_vars = args[2] if len(args) > 2 else keep_vars
+        out = destination if destination is not None else {}
+        for k, v in self._parameters.items():
+            out[prefix + self._names[k]] = v if keep_vars else v.detach()
+        return out
 
-    def load_state_dict(self, sd, strict=True, **kw):
+    def _save_to_state_dict(self, destination, prefix, keep_vars):      # nested in a parent module: parent.state_dict() works
+        self.state_dict(destination=destination, prefix=prefix, keep_vars=keep_vars)
+
+    def load_state_dict(self, sd, strict=True, assign=False, prefix=""):
         missing = []
+        known = set(self._names.values())
+        unexpected = [k for k in sd if k.startswith(prefix) and k[len(prefix):] not in known and not k[len(prefix):].startswith("quantize.")]
         with torch.no_grad():
             for key, name in self._names.items():
-                if name in sd:
-                    self._parameters[key].copy_(sd[name])
+                if prefix + name in sd:
+                    self._parameters[key].copy_(sd[prefix + name])
                 else:
                     missing.append(name)
-        if strict and missing:
-            raise KeyError(f"missing keys: {missing[:5]}...")
-        return missing, []
+        if strict and (missing or unexpected):
+            raise KeyError(f"MAGVITv2.load_state_dict: missing keys {missing[:5]}{'...' if len(missing) > 5 else ''}, "
+                           f"unexpected keys {unexpected[:5]}{'...' if len(unexpected) > 5 else ''}")
+        self._versions = None            # in-place copies bump _version, but be explicit: the engine reloads on next use
+        return missing, unexpected
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        m, u = self.load_state_dict(state_dict, strict=False, prefix=prefix)
+        missing_keys.extend(prefix + k for k in m)
+        unexpected_keys.extend(u)
 
     @classmethod
     def from_pretrained(cls, path, **kw):
@@ -119,6 +138,9 @@ class MAGVITv2(nn.Module):
 
     def save_pretrained(self, path, max_shard_bytes: int = 5 << 30):
         from . import checkpoint
+        if not self._parameters:
+            raise _lib.ShowoError("MAGVITv2.save_pretrained: the weights were streamed into the engine (materialize=False); "
+                                  "there are no torch parameters to write")
         checkpoint.write_checkpoint(path, self.state_dict(), {"_class_name": "MAGVITv2"}, max_shard_bytes)
 
     @property
@@ -152,7 +174,7 @@ class MAGVITv2(nn.Module):
         dev = self.device
         if dev.type != "cuda":
             raise _lib.ShowoError("MAGVITv2 must live on a CUDA (B200) device: show-o_b200 has no CPU fallback")
-        versions = tuple(p._version for p in self._parameters.values())
+        versions = (str(dev),) + tuple((p._version, p.data_ptr()) for p in self._parameters.values())   # device moves re-upload too
         if self._engine is None or versions != self._versions:
             with torch.cuda.device(dev):
                 self.load_weights(self.state_dict(), device=dev)

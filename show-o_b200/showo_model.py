@@ -165,6 +165,9 @@ class Showo(nn.Module):
     def save_pretrained(self, path, max_shard_bytes: int = 5 << 30):
         """config.json + safetensors in the layout `from_pretrained` (and the reference's ModelMixin) reads back."""
         from . import checkpoint
+        if self.showo is None:
+            raise _lib.ShowoError("Showo.save_pretrained: the weights were streamed into the engine (materialize=False); "
+                                  "there are no torch parameters to write")
         cfg = {"_class_name": "Showo", "w_clip_vit": bool(self.config.w_clip_vit), "vocab_size": int(self.vocab_size),
                "llm_vocab_size": int(self.config.llm_vocab_size), "llm_model_path": "", "codebook_size": int(self.config.codebook_size),
                "num_vq_tokens": int(self.config.num_vq_tokens), "load_from_showo": False}
@@ -366,6 +369,54 @@ class Showo(nn.Module):
         with torch.cuda.device(self._engine_device):
             _lib.check(lib.showo_backward(self._engine, _lib.ptr(g), _lib.ptr(demb), _lib.current_stream_ptr()), "showo_backward")
         return demb
+
+    def backward_phase(self, phase: int, loss_grads, want_input_grad_like=None):
+        """One phase of showo_backward (-1: loss / head / final LN, then layers n_layers-1 .. 0, then -2: embedding)."""
+        lib = _lib.require_gpu()
+        g = torch.as_tensor(loss_grads, dtype=torch.float32, device=self._engine_device).contiguous()
+        demb = torch.empty_like(want_input_grad_like, dtype=torch.float32) if (want_input_grad_like is not None and phase == -2) else None
+        with torch.cuda.device(self._engine_device):
+            _lib.check(lib.showo_backward_phase(self._engine, int(phase), _lib.ptr(g), _lib.ptr(demb), _lib.current_stream_ptr()),
+                       "showo_backward_phase")
+        return demb
+
+    def grad_buffer(self) -> torch.Tensor:
+        """Zero-copy fp32 view of the engine's gradient buffer (packed weight layout) -- what a data-parallel all-reduce runs on."""
+        lib = _lib.require_gpu()
+        base, n = C.c_void_p(), C.c_int64()
+        _lib.check(lib.showo_grad_buffer(self._engine, C.byref(base), C.byref(n)), "showo_grad_buffer")
+
+        class _View:
+            __cuda_array_interface__ = {"shape": (int(n.value),), "typestr": "<f4", "data": (int(base.value), False), "version": 2}
+        return torch.as_tensor(_View(), device=self._engine_device)
+
+    def grad_range(self, phase: int):
+        lib = _lib.require_gpu()
+        b, e_ = C.c_int64(), C.c_int64()
+        _lib.check(lib.showo_grad_range(self._engine, int(phase), C.byref(b), C.byref(e_)), "showo_grad_range")
+        return int(b.value), int(e_.value)
+
+    def backward_overlapped(self, loss_grads, group=None, comm_stream=None, average: bool = True):
+        """Data-parallel backward: runs the phases in order and all-reduces each phase's gradient range on `comm_stream` as soon
+        as the phase has been enqueued (per-layer buckets; the layer's bytes move over NCCL while the next layer's backward runs).
+        Returns the CUDA event after which every gradient is reduced."""
+        import torch.distributed as dist
+        dev = self._engine_device
+        cur = torch.cuda.current_stream(dev)
+        comm = comm_stream or torch.cuda.Stream(dev)
+        G = self.grad_buffer()
+        phases = [-1] + list(range(self._dims.n_layers - 1, -1, -1)) + [-2]
+        for ph in phases:
+            self.backward_phase(ph, loss_grads)
+            ready = torch.cuda.Event()
+            ready.record(cur)
+            b, e_ = self.grad_range(ph)
+            with torch.cuda.stream(comm):
+                comm.wait_event(ready)
+                dist.all_reduce(G[b:e_], op=dist.ReduceOp.AVG if average else dist.ReduceOp.SUM, group=group)
+        done = torch.cuda.Event()
+        done.record(comm)
+        return done
 
     def read_grad(self, name: str, like: Optional[torch.Tensor] = None, shape=None):
         """Gradient of one parameter (reference state_dict name) as a fresh fp32 tensor."""

@@ -68,7 +68,11 @@ def test_single_row_logits_slice(full, dev):
     flips = sl.argmax(-1).numpy() != z["argmax"]
     assert (z["margin"][flips] <= 2 * TOL_FULL).all() and flips.mean() < 0.1
     full_logits = m(ids.to(dev), attention_mask=mask.to(dev))
-    assert torch.equal(full_logits[:, 130:386, VOC.image_offset:-1].cpu(), sl)
+    # (bitwise with the mma.sync attention; the tcgen05 kernel's key blocks depend on the pass's tile split, so the two passes
+    #  differ by bf16 rounding noise through 24 layers: observed 0.022, bound = half the logit tolerance)
+    d = (full_logits[:, 130:386, VOC.image_offset:-1].cpu() - sl).abs().max().item()
+    _record("single_row_step_vs_forward", {"max_abs_dlogit": d})
+    assert d < TOL_FULL / 2
 
 
 def test_config1_t2i_b8_cfg5_three_denoise_steps(full, dev):

@@ -10,6 +10,7 @@ Tolerances (stated once): the engine computes in bf16 with fp32 accumulation, th
 """
 import ctypes as C
 import math
+import os
 
 import numpy as np
 import pytest
@@ -326,9 +327,18 @@ def test_prefix_reuse_equals_full_recompute(tiny, dev):
     ids = torch.cat([cond, uncond]).to(dev)
     full = m(ids, attention_mask=mask.to(dev))[:, 130:386, VOC.image_offset:-1]
     step = m.t2i_step_logits(cond.to(dev), uncond.to(dev), mask.to(dev), guidance_scale=5.0, config=cfg_ns())
-    assert torch.equal(step, full)              # same kernels, same per-row reduction order: bitwise identical
     one = m.t2i_step_logits(cond[:1].to(dev), None, mask[:1].to(dev), guidance_scale=0.0, config=cfg_ns())
-    assert torch.equal(one[0], full[0])         # batch-size independence (B=1, no CFG branch)
+    if os.environ.get("SHOWO_ATTN_TC") == "0":
+        # mma.sync attention: every row is reduced in the same order whatever tile it lands in -> bitwise identical
+        assert torch.equal(step, full)
+        assert torch.equal(one[0], full[0])     # batch-size independence (B=1, no CFG branch)
+    else:
+        # tcgen05 attention (default): a row's 64-key blocks start at its tile's first visible key and the tile / tail split
+        # depends on the row offset of the pass, so the two passes sum in different orders: equal to fp32-reordering accuracy
+        d1, d2 = (step - full).abs().max().item(), (one[0] - full[0]).abs().max().item()
+        print(f"prefix reuse vs full recompute: max|dlogit| {d1:.2e} (B=1: {d2:.2e})")
+        _record("prefix_reuse_vs_full", {"max_abs_dlogit": d1, "max_abs_dlogit_b1": d2})
+        assert d1 < 5e-3 and d2 < 5e-3
 
 
 def test_forward_masks_lm_mmu_and_embeddings_input(tiny, dev):

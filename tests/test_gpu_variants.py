@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 GEMM_K = "gemm_tcgen05 or gemm_linearity or forward_tiny or prefix_reuse"
-ATTN_K = "omni_attention or forward_tiny or forward_masks or t2i_512"
+ATTN_K = "omni_attention or forward_tiny or forward_masks or t2i_512 or prefix_reuse"
 DECODE_K = "skinny or mmu_generate_batched or step_and_decode or megakernel"
 VARIANTS = {
     "attention_tcgen05": ({"SHOWO_ATTN_TC": "1"}, ATTN_K),
