@@ -30,6 +30,11 @@ bool pdl_enabled() {
     return v == 1;
 }
 int64_t launches_total() { return g_launches.load(); }
+bool fused_decode_ln() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SHOWO_DECODE_LN_FUSED"); v = (e && atoi(e) == 0) ? 0 : 1; }
+    return v == 1;
+}
 bool l2_prefetch_enabled() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("SHOWO_L2_PREFETCH"); v = (e && atoi(e) == 1) ? 1 : 0; }    // opt-in: measured 1.61 vs 1.45 ms per decode step
@@ -121,9 +126,10 @@ static int run_layers(showo_engine* e, int n_seq, int rows_per_seq, int pos0, in
     const int D = e->D, F = e->F;
     for (int l = 0; l < e->NL; ++l) {
         const LayerW& w = e->layers[l];
-        // (normalising the 16-row slab inside the decode GEMM was measured slower than this stand-alone launch: every CTA
-        // re-reads 16 x 8 KB three times -- 2.81 vs 2.14 ms per decode step)
-        SHOWO_TRY(layernorm_bf16(e->x, w.ln_g, w.ln_b, e->cfg.ln_eps, e->xh, M, D, M, M, 0, st));
+        // decode: only the first layer's LayerNorm is a launch of its own -- every later one (and the final LayerNorm) is done by the
+        // CTA that finishes the last tile of the previous layer's second GEMM (skinny.cuh: sk2_tile_done)
+        const bool ln_fused = decode && fused_decode_ln() && M <= 16 && D % 128 == 0 && D <= 2048;
+        if (!(ln_fused && l > 0)) SHOWO_TRY(layernorm_bf16(e->x, w.ln_g, w.ln_b, e->cfg.ln_eps, e->xh, M, D, M, M, 0, st));
         bf16* kc = e->kcache + (size_t)l * layer_cache_stride(e);
         bf16* vc = e->vtcache + (size_t)l * layer_cache_stride(e);
         // GEMM1 + (q/k LayerNorm, partial rotary, K / V^T cache scatter, gelu_new) in one kernel
@@ -145,6 +151,11 @@ static int run_layers(showo_engine* e, int n_seq, int rows_per_seq, int pos0, in
         GemmArgs g2{};
         g2.A = e->buf + 2 * D; g2.lda = e->W1N; g2.B = w.w2; g2.ldb = e->W2K; g2.M = M; g2.N = D; g2.K = D + F;
         g2.out = e->x; g2.ldc = D; g2.bias = w.b2; g2.resid = e->x; g2.ldr = D;
+        if (ln_fused) {
+            g2.ln_out = e->xh; g2.ln_eps = e->cfg.ln_eps;
+            g2.ln_gamma = l + 1 < e->NL ? e->layers[l + 1].ln_g : e->fln_g;
+            g2.ln_beta = l + 1 < e->NL ? e->layers[l + 1].ln_b : e->fln_b;
+        }
         if (decode && l2_prefetch_enabled()) {      // the next layer's fused projection (or the start of the head) streams next
             if (l + 1 < e->NL) { g2.l2_prefetch = e->layers[l + 1].w1; g2.l2_prefetch_bytes = (size_t)e->W1N * D * sizeof(bf16); }
             else { g2.l2_prefetch = e->head_w; g2.l2_prefetch_bytes = std::min((size_t)e->V * D * sizeof(bf16), (size_t)64 << 20); }
@@ -214,6 +225,7 @@ static int decode_step_layers(showo_engine* e, int B, int pos0, int max_keys, cu
     }
     if (decode_mega_supported(d)) return decode_mega_step(d, st);
     SHOWO_TRY(run_layers(e, B, 1, pos0, pos0 + 1, true, st));
+    if (fused_decode_ln() && B <= 16 && e->D % 128 == 0 && e->D <= 2048) return 0;      // the last layer's GEMM wrote LN_f(x) to xh
     return layernorm_bf16(e->x, e->fln_g, e->fln_b, e->cfg.ln_eps, e->xh, B, e->D, B, B, 0, st);
 }
 

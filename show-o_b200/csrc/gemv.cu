@@ -287,9 +287,15 @@ static int gemm_skinny2(const GemmArgs& a, int epi, const QkvFuse* qf, int tiles
     if (qf) p.qf = *qf;
     p.argmax_keys = a.argmax_keys;
     p.l2_prefetch = a.l2_prefetch; p.l2_prefetch_bytes = a.l2_prefetch_bytes;
+    p.ln_out = nullptr;
+    if (epi == SK_RESID_F32 && a.ln_out != nullptr) {
+        SHOWO_CHECK(a.N % 128 == 0 && a.N <= 2048 && a.ldc == a.N, "gemm_skinny: fused LayerNorm needs a contiguous hidden size <= 2048");
+        p.ln_out = a.ln_out; p.ln_gamma = a.ln_gamma; p.ln_beta = a.ln_beta; p.ln_eps = a.ln_eps;
+    }
     if (epi == SK_ARGMAX) SHOWO_CHECK(a.argmax_keys != nullptr, "gemm_skinny: argmax epilogue needs a key buffer");
-    SHOWO_TRY(ensure_skinny_ws((size_t)sc.grid * 2 * 1024, (size_t)tiles, st));
+    SHOWO_TRY(ensure_skinny_ws((size_t)sc.grid * 2 * 1024, (size_t)tiles + 1, st));
     p.partials = g_partials; p.tickets = g_tickets;
+    p.ln_ctr = g_tickets + tiles;                 // one more self-resetting counter behind the tile tickets
     CUtensorMap mw, mx;
     SHOWO_TRY(make_tmap_2d(&mw, a.B, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldb * 2, 64, 64));
     SHOWO_TRY(make_tmap_2d(&mx, a.A, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda * 2, 64, 16));
@@ -320,6 +326,7 @@ int gemm_skinny(const GemmArgs& a, int epi, const QkvFuse* qf, cudaStream_t st) 
     const int tiles = cdiv(a.N, kSkTileN);
     if (skinny_variant() == 2 && a.K % kSk2ChunkK == 0)
         return gemm_skinny2(a, epi, qf, tiles, st);
+    SHOWO_CHECK(a.ln_out == nullptr, "gemm_skinny: the fused LayerNorm needs the TMA-streamed kernel (K % 128 == 0)");
     // enough CTAs to cover the SMs a few times over, K per split a multiple of 64 and <= 2048 (X slab <= 64 KB of smem)
     int splits = 1;
     // at least one full wave of CTAs, X slab <= 64 KB of smem; fewer, longer-streaming CTAs beat many short ones

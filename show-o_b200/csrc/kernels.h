@@ -25,6 +25,8 @@ struct GemmArgs {
     unsigned long long* argmax_keys = nullptr;
     // decode path: bytes the NEXT kernel of the chain will stream (its weights), pulled into L2 while this kernel runs
     const void* l2_prefetch = nullptr; size_t l2_prefetch_bytes = 0;
+    // decode path, GEMM_RESID_F32 with M <= 16: the CTA finishing the last tile also writes LayerNorm(out rows) as bf16 to ln_out
+    bf16* ln_out = nullptr; const float* ln_gamma = nullptr; const float* ln_beta = nullptr; float ln_eps = 0.f;
 };
 int gemm_bf16(const GemmArgs& a, GemmEpi epi, cudaStream_t st);
 

@@ -15,6 +15,9 @@ struct SkinnyParams {
     QkvFuse qf;
     unsigned long long* argmax_keys;     // SK_ARGMAX: per-row packed (orderable logit, ~index) maxima, atomicMax'ed
     const void* l2_prefetch; size_t l2_prefetch_bytes;      // the next kernel's weights -> L2 (idle producer lanes)
+    // SK_RESID_F32 (the layer's second GEMM, x += ...): the CTA that finishes the LAST feature tile also runs the next LayerNorm over
+    // the M rows (phi.py:776 / :1065) and writes its bf16 output -- the stand-alone 16-row LayerNorm launch cost 6 us per layer
+    bf16* ln_out; const float* ln_gamma; const float* ln_beta; float ln_eps; int* ln_ctr;
 };
 
 __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -192,6 +195,60 @@ __device__ __forceinline__ void sk2_sum_partials(const SkinnyParams& p, const Sk
 // ring position, in step with the producer's issue order (it carries over between phases in the decode megakernel).
 struct Sk2Smem { uint8_t* ring; float* part; uint64_t* full; uint64_t* empty; int* s_flag; int* s_defer; int stages; };
 
+
+// After a finished tile of the residual GEMM: count it; the CTA that completes the last tile normalises the M rows of the residual
+// stream (every tile's stores are ordered before its count by the fence; the reads below bypass L1).  128 consumer threads.
+template <int EPI>
+__device__ __forceinline__ void sk2_tile_done(const SkinnyParams& p, const Skinny2Sched& sc, int* s_flag, int tid) {
+    if constexpr (EPI == SK_RESID_F32) {
+        if (p.ln_out == nullptr) return;
+        consumer_bar();                           // the tile's stores of all 128 threads precede thread 0's fence
+        if (tid == 0) {
+            __threadfence();
+            const int t = atomicAdd(p.ln_ctr, 1);
+            const int last = (t == sc.tiles - 1);
+            if (last) *p.ln_ctr = 0;              // self-resetting for the next launch
+            *s_flag = last;
+        }
+        consumer_bar();
+        const bool last = *s_flag != 0;
+        consumer_bar();                           // s_flag may be rewritten
+        if (!last) return;
+        __threadfence();
+        const int warp = tid >> 5, lane = tid & 31;
+        const int D = p.N;                        // the GEMM's N is the hidden size
+        for (int r = warp; r < p.M; r += 4) {
+            const float4* xr = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.out) + (int64_t)r * p.ldc);
+            float4 v[16];
+            float s = 0.f;
+            const int nvec = D >> 7;              // float4 per lane (D <= 2048)
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (i < nvec) { v[i] = __ldcg(xr + i * 32 + lane); s += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
+            const float mean = warp_sum(s) / (float)D;
+            float q = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (i < nvec) {
+                    const float a0 = v[i].x - mean, a1 = v[i].y - mean, a2 = v[i].z - mean, a3 = v[i].w - mean;
+                    q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+                }
+            const float rstd = rsqrtf(warp_sum(q) / (float)D + p.ln_eps);
+            uint2* orow = reinterpret_cast<uint2*>(p.ln_out + (int64_t)r * D);
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (i < nvec) {
+                    const float4 g = __ldg(reinterpret_cast<const float4*>(p.ln_gamma) + i * 32 + lane);
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.ln_beta) + i * 32 + lane);
+                    uint2 pk;
+                    pk.x = pack_bf16((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
+                    pk.y = pack_bf16((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+                    orow[i * 32 + lane] = pk;
+                }
+        }
+    }
+}
+
 template <int EPI>
 __device__ __forceinline__ void sk2_consume(const SkinnyParams& p, const Skinny2Sched& sc, const Sk2Smem& sm, int cta,
                                             int c_begin, int c_end, RingPos& rp) {
@@ -294,7 +351,7 @@ __device__ __forceinline__ void sk2_consume(const SkinnyParams& p, const Skinny2
                 if (finish) sk2_sum_partials(p, sc, tile_c0, first, last, r, cq, f);
             }
         }
-        if (finish) skinny_epilogue<EPI>(p, f, tile * 64, tid);
+        if (finish) { skinny_epilogue<EPI>(p, f, tile * 64, tid); sk2_tile_done<EPI>(p, sc, s_flag, tid); }
     }
     if (deferred_tile >= 0) {
         consumer_bar();                           // thread 0's ticket result is in smem
@@ -303,6 +360,7 @@ __device__ __forceinline__ void sk2_consume(const SkinnyParams& p, const Skinny2
             float f[8];
             sk2_sum_partials(p, sc, tile_c0, sk2_cta_of(sc, tile_c0), sk2_cta_of(sc, tile_c0 + sc.cpt - 1), tid >> 3, (tid & 7) * 8, f);
             skinny_epilogue<EPI>(p, f, deferred_tile * 64, tid);
+            sk2_tile_done<EPI>(p, sc, s_flag, tid);
         }
         consumer_bar();                           // s_defer may be rewritten by the next phase
     }
