@@ -122,6 +122,40 @@ int gemm_num_sms() {
     return n[dev & 63];
 }
 
+// SHOWO_GEMM_STREAMK=1 selects stream-K for the residual GEMM.  Off by default: with every cluster at a different k offset the
+// operand blocks are no longer shared in L2 while they are hot (A + B of dense|fc2 = 127 MB, the size of the L2): measured
+// 170 vs 137 us for 4128 x 2048 x 10240 although 147 instead of 160 k blocks are on the critical path.
+static int gemm_streamk() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SHOWO_GEMM_STREAMK"); v = (e && atoi(e) == 1) ? 1 : 0; }
+    return v;
+}
+// parked partial tiles + their flags, one set per device (the library runs one stream of GEMMs per device; flags reset themselves)
+struct StreamKWs { float* ws = nullptr; size_t ws_cap = 0; int* flags = nullptr; size_t flags_cap = 0; };
+static int streamk_workspace(size_t ws_floats, size_t n_flags, float** ws, int** flags, cudaStream_t st) {
+    static StreamKWs g[64];
+    int dev = 0;
+    SHOWO_CUDA_OK(cudaGetDevice(&dev));
+    StreamKWs& w = g[dev & 63];
+    if (ws_floats > w.ws_cap) {
+        SHOWO_CUDA_OK(cudaStreamSynchronize(st));
+        if (w.ws) cudaFree(w.ws);
+        w.ws = nullptr;
+        SHOWO_CUDA_OK(cudaMalloc(&w.ws, ws_floats * sizeof(float)));
+        w.ws_cap = ws_floats;
+    }
+    if (n_flags > w.flags_cap) {
+        SHOWO_CUDA_OK(cudaStreamSynchronize(st));
+        if (w.flags) cudaFree(w.flags);
+        w.flags = nullptr;
+        SHOWO_CUDA_OK(cudaMalloc(&w.flags, n_flags * sizeof(int)));
+        SHOWO_CUDA_OK(cudaMemset(w.flags, 0, n_flags * sizeof(int)));
+        w.flags_cap = n_flags;
+    }
+    *ws = w.ws; *flags = w.flags;
+    return 0;
+}
+
 template <int BN, int EPI, int AMODE, int BK = 64, int CL = 1, int CG = 1>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int num_tiles, cudaStream_t st) {
     using Cfg = GemmCfg<BN, BK, CG>;
@@ -158,6 +192,14 @@ static int gemm_bn(const GemmArgs& a, GemmEpi epi, cudaStream_t st) {
     p.M = a.M; p.N = a.N; p.K = a.K;
     p.out = a.out; p.ldc = a.ldc; p.bias = a.bias; p.resid = a.resid; p.ldr = a.ldr; p.gelu_from = a.gelu_from;
     const int tiles = cdiv(cdiv(a.M, 128), CL) * cdiv(a.N, BN);
+    if constexpr (CG == 2) {
+        // stream-K for the residual GEMM when the tiles do not fill whole waves of clusters (dense|fc2: 136 tiles on 74 clusters)
+        const int clusters = std::min(tiles, gemm_num_sms() / CL), num_kb = cdiv(a.K, BK);
+        if (epi == GEMM_RESID_F32 && gemm_streamk() && tiles > clusters && tiles % clusters != 0 &&
+            (long long)tiles * num_kb / clusters >= num_kb) {
+            SHOWO_TRY(streamk_workspace((size_t)tiles * 2 * BN * 128, (size_t)tiles * 2, &p.sk_ws, &p.sk_flags, st));
+        }
+    }
     switch (epi) {
         case GEMM_BIAS_BF16: return launch<BN, EPI_BIAS_BF16, A_PLAIN, BK, CL, CG>(ma, mb, p, tiles, st);
         case GEMM_RESID_F32: return launch<BN, EPI_RESID_F32, A_PLAIN, BK, CL, CG>(ma, mb, p, tiles, st);

@@ -51,6 +51,12 @@ struct GemmParams {
     const float* q_gamma; const float* q_beta; const float* k_gamma; const float* k_beta; float qk_eps;
     const float* cos_tab; const float* sin_tab;     // [max_pos][32]
     __nv_bfloat16* kcache; __nv_bfloat16* vtcache;  // [seq][H][Lmax][64], [seq][H][64][Lmax]
+    // stream-K (CTA-pair path, EPI_RESID_F32): the (tile, k block) pairs are linearised and every cluster takes an equal contiguous
+    // range, so that 136 tiles on 74 clusters cost 1.84 tile times instead of 2.  A tile cut between two clusters: the cluster holding
+    // its TAIL k blocks meets it FIRST in its range and parks the raw fp32 accumulators in sk_ws[unit][cta rank][col][row]; the
+    // cluster holding its HEAD k blocks meets it LAST, adds the parked partial (fixed order: deterministic) and runs the epilogue.
+    float* sk_ws;           // nullptr: classic tile loop
+    int* sk_flags;          // [units][2] one flag per (tile, CTA rank), zero between launches
 };
 
 template <int BN, int BK_ = 64, int CG = 1>
@@ -64,6 +70,31 @@ struct GemmCfg {
     static constexpr int kTmemCols = 2 * BN;                // 2 accumulator stages (power of two for BN in {64,128,256})
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 512 /*barriers*/;
     static constexpr int kThreads = 192;
+};
+
+// The work of one CTA (cluster) as a list of segments = (tile, k block range): classic = whole tiles unit0, unit0 + stride, ...;
+// stream-K = the cluster's contiguous share of the linearised (tile, k block) space, cut at tile boundaries.
+struct GemmSegCursor {
+    bool sk; int num_kb, num_units, stride, unit; long long c, c_end;
+    __device__ __forceinline__ GemmSegCursor(bool sk_, int unit0, int stride_, int num_units_, int num_kb_)
+        : sk(sk_), num_kb(num_kb_), num_units(num_units_), stride(stride_), unit(unit0) {
+        const long long total = (long long)num_units_ * num_kb_;
+        c = sk_ ? (long long)unit0 * total / stride_ : 0;
+        c_end = sk_ ? (long long)(unit0 + 1) * total / stride_ : 0;
+    }
+    __device__ __forceinline__ bool next(int& u, int& kb0, int& kb1) {
+        if (sk) {
+            if (c >= c_end) return false;
+            u = (int)(c / num_kb); kb0 = (int)(c % num_kb);
+            const long long left = c_end - c;
+            kb1 = (long long)(num_kb - kb0) <= left ? num_kb : kb0 + (int)left;
+            c += kb1 - kb0;
+            return true;
+        }
+        if (unit >= num_units) return false;
+        u = unit; kb0 = 0; kb1 = num_kb; unit += stride;
+        return true;
+    }
 };
 
 template <int BN, int EPI, int AMODE, int BK_ = 64, int CL = 1, int CG = 1>
@@ -104,6 +135,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int num_units = tiles_mc * tiles_n;
     const int unit0 = blockIdx.x / CL, unit_stride = gridDim.x / CL;
     const int num_kb = (AMODE == A_CONV3) ? p.conv_taps * ((p.conv_cin + BK - 1) / BK) : (p.K + BK - 1) / BK;
+    const bool sk = (CG == 2 && EPI == EPI_RESID_F32 && AMODE == A_PLAIN) && p.sk_ws != nullptr;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
@@ -138,7 +170,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int unit = unit0; unit < num_units; unit += unit_stride) {
+            GemmSegCursor cur(sk, unit0, unit_stride, num_units, num_kb);
+            int unit, kb_begin, kb_end;
+            while (cur.next(unit, kb_begin, kb_end)) {
                 const int tm = (unit % tiles_mc) * CL + crank, tn = unit / tiles_mc;
                 int img = 0, y0 = 0, x0 = 0;
                 if constexpr (AMODE == A_CONV3) {
@@ -148,7 +182,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     y0 = (r / tw) * p.conv_TH;
                     x0 = (r % tw) * p.conv_TW;
                 }
-                for (int kb = 0; kb < num_kb; ++kb) {
+                for (int kb = kb_begin; kb < kb_end; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     if constexpr (CG == 2) {
                         // both CTAs load their A tile and their half of B; all bytes are credited to the LEADER barrier
@@ -193,13 +227,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         uint32_t phase = 0;
         int it = 0;
         const bool issuer = (CG == 1) || (crank == 0);               // only the pair leader issues 2-SM MMAs
-        for (int unit = unit0; issuer && unit < num_units; unit += unit_stride, ++it) {
+        GemmSegCursor cur(sk, unit0, unit_stride, num_units, num_kb);
+        int unit, kb_begin, kb_end;
+        for (; issuer && cur.next(unit, kb_begin, kb_end); ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * BN;
-            for (int kb = 0; kb < num_kb; ++kb) {
+            for (int kb = kb_begin; kb < kb_end; ++kb) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
                 if (lane == 0) {
@@ -210,16 +246,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         constexpr int kRowB = (BK >= 64) ? 128 : BK * 2;            // bytes per smem row (swizzle width)
                         const uint64_t da = umma_desc_kmajor<kRowB>(a_addr + (k >> 2) * (BM * 128) + (k & 3) * 32);
                         const uint64_t db = umma_desc_kmajor<kRowB>(b_addr + (k >> 2) * ((BN / CG) * 128) + (k & 3) * 32);
-                        if constexpr (CG == 2) umma_bf16_cg2(d_tmem, da, db, idesc, (kb | k) != 0);
-                        else umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
+                        if constexpr (CG == 2) umma_bf16_cg2(d_tmem, da, db, idesc, ((kb - kb_begin) | k) != 0);
+                        else umma_bf16(d_tmem, da, db, idesc, ((kb - kb_begin) | k) != 0);
                     }
                     if constexpr (CG == 2) {                          // frees the slot / publishes the accumulator in BOTH CTAs
                         umma_commit_cg2(&empty_bar[stage], 3);
-                        if (kb == num_kb - 1) umma_commit_cg2(&tmem_full[acc], 3);
+                        if (kb == kb_end - 1) umma_commit_cg2(&tmem_full[acc], 3);
                     } else {
                         if constexpr (CL == 1) umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
                         else umma_commit_multicast(&empty_bar[stage], (uint16_t)((1u << CL) - 1));   // ... in every CTA of the cluster
-                        if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
+                        if (kb == kb_end - 1) umma_commit(&tmem_full[acc]);
                     }
                 }
                 __syncwarp();
@@ -236,10 +272,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (EPI == EPI_RESID_F32 || (EPI == EPI_CONV_BF16 && p.resid != nullptr))
             out_vec_ok = out_vec_ok && ((p.ldr * kOutElem) % 16 == 0) && ((reinterpret_cast<uintptr_t>(p.resid) & 15) == 0);
         int it = 0;
-        for (int unit = unit0; unit < num_units; unit += unit_stride, ++it) {
+        GemmSegCursor cur(sk, unit0, unit_stride, num_units, num_kb);
+        int unit, kb_begin, kb_end;
+        for (; cur.next(unit, kb_begin, kb_end); ++it) {
             const int tm = (unit % tiles_mc) * CL + crank, tn = unit / tiles_mc;
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
+            // stream-K: a segment without the tile's first k block parks its accumulators; one with the first but not the last
+            // block finishes the tile with the parked partial of the cluster that met it first
+            const bool sk_park = kb_begin > 0;
+            const bool sk_join = kb_begin == 0 && kb_end < num_kb;
             // output row of this thread
             int64_t m;
             bool row_ok;
@@ -258,6 +300,36 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr0 = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16);
+            float* sk_part = nullptr;                 // this thread's row of the parked partial: [col][128 rows] (lanes contiguous)
+            if constexpr (CG == 2 && EPI == EPI_RESID_F32 && AMODE == A_PLAIN) {
+                if (sk_park || sk_join) sk_part = p.sk_ws + ((size_t)unit * 2 + crank) * (size_t)(BN * 128) + row_in_tile;
+                if (sk_park) {
+#pragma unroll 1
+                    for (int c = 0; c < BN; c += 32) {
+                        uint32_t v[32];
+                        __syncwarp();
+                        tmem_ld32(taddr0 + c, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) sk_part[(size_t)(c + j) * 128] = __uint_as_float(v[j]);
+                    }
+                    __threadfence();
+                    asm volatile("bar.sync 2, 128;" ::: "memory");          // the four epilogue warps: all rows of this CTA are stored
+                    if (warp == 2 && lane == 0) atomicExch(p.sk_flags + unit * 2 + crank, 1);
+                    __syncwarp();
+                    tc_fence_before();
+                    if (crank != 0) mbar_arrive_remote(&tmem_empty[acc], 0);
+                    else mbar_arrive(&tmem_empty[acc]);
+                    continue;
+                }
+                if (sk_join) {
+                    volatile int* fl = p.sk_flags + unit * 2 + crank;
+                    while (*fl == 0) { }
+                    __threadfence();
+                    asm volatile("bar.sync 2, 128;" ::: "memory");          // everyone has seen the flag before it is cleared
+                    if (warp == 2 && lane == 0) *fl = 0;                     // self-resetting for the next launch
+                }
+            }
             if constexpr (EPI == EPI_QKV_BF16) {
                 const int D = p.qkv_D;
                 const int seq = row_ok ? (int)(m / p.qkv_rows_per_seq) : 0;
@@ -354,6 +426,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 float f[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                if constexpr (CG == 2 && EPI == EPI_RESID_F32 && AMODE == A_PLAIN) {
+                    if (sk_join) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] += __ldcg(sk_part + (size_t)(c + j) * 128);
+                    }
+                }
                 if (p.bias != nullptr) {
                     if (full && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)) {
 #pragma unroll

@@ -571,7 +571,7 @@ static int ensure_train(showo_engine* e, int M, cudaStream_t st) {
         dev_free(t->xs); dev_free(t->stats); dev_free(t->xh); dev_free(t->pre); dev_free(t->a2); dev_free(t->qrot); dev_free(t->krot);
         dev_free(t->lse); dev_free(t->dx); dev_free(t->dxh); dev_free(t->dxb); dev_free(t->dA2); dev_free(t->dpre); dev_free(t->dqk);
         dev_free(t->delta); dev_free(t->tA); dev_free(t->tB); dev_free(t->dlogits); dev_free(t->ids); dev_free(t->labels);
-        const size_t m = (size_t)M, Mp = (size_t)(M + 7) / 8 * 8;
+        const size_t m = (size_t)M, Mp = (size_t)(M + 127) / 128 * 128;    // wgrad contracts over the tokens: K padded to the GEMM's 128-wide k block, pad columns zero
         SHOWO_TRY(dev_alloc(&t->xs, (size_t)(NL + 1) * m * D));
         SHOWO_TRY(dev_alloc(&t->stats, (size_t)(NL + 1) * m));
         SHOWO_TRY(dev_alloc(&t->xh, (size_t)(NL + 1) * m * D));
@@ -590,6 +590,8 @@ static int ensure_train(showo_engine* e, int M, cudaStream_t st) {
         const size_t ra = (size_t)(t->Vp > W1N ? t->Vp : W1N), rbm = (size_t)(W2K > D ? W2K : D);
         SHOWO_TRY(dev_alloc(&t->tA, ra * Mp));
         SHOWO_TRY(dev_alloc(&t->tB, rbm * Mp));
+        SHOWO_CUDA_OK(cudaMemsetAsync(t->tA, 0, ra * Mp * sizeof(bf16), st));      // the transposes only ever write columns [0, M)
+        SHOWO_CUDA_OK(cudaMemsetAsync(t->tB, 0, rbm * Mp * sizeof(bf16), st));
         SHOWO_TRY(dev_alloc(&t->dlogits, m * (size_t)t->Vp));
         SHOWO_TRY(dev_alloc(&t->ids, m));
         SHOWO_TRY(dev_alloc(&t->labels, m));
@@ -728,7 +730,7 @@ int showo_train_forward(showo_engine_t* e, const int64_t* ids_dev, const float* 
 static int backward_phase(showo_engine_t* e, int phase, const float* loss_grads_dev, float* dembeds_out_dev, cudaStream_t st) {
     TrainState* t = e->train;
     const int M = t->M, B = t->B, L = t->L, D = e->D, H = e->H, W1N = e->W1N, W2K = e->W2K, V = e->V, NL = e->NL, F = e->F;
-    const int64_t Mp = (int64_t)(M + 7) / 8 * 8, Vp = t->Vp;
+    const int64_t Mp = (int64_t)(M + 127) / 128 * 128, Vp = t->Vp;
     const size_t mD = (size_t)M * D;
     const GradLayout gl = grad_layout(e);
     float* G = t->grads;
@@ -746,7 +748,7 @@ static int backward_phase(showo_engine_t* e, int phase, const float* loss_grads_
     // d Wh = dlogits^T * xh_f, d bh = column sums of dlogits
     SHOWO_TRY(transpose_to_bf16<bf16>(t->dlogits, Vp, M, (int)Vp, t->tA, Mp, nullptr, 0, st));
     SHOWO_TRY(transpose_to_bf16<bf16>(t->xh + (size_t)NL * mD, D, M, D, t->tB, Mp, nullptr, 0, st));
-    SHOWO_TRY(gemm_plain(t->tA, Mp, t->tB, Mp, V, D, M, G + gl.head_w, D, true, st));
+    SHOWO_TRY(gemm_plain(t->tA, Mp, t->tB, Mp, V, D, (int)Mp, G + gl.head_w, D, true, st));
     SHOWO_TRY(rowsum_bf16(t->tA, Mp, V, M, G + gl.head_b, st));
     // final LayerNorm
     SHOWO_TRY(layernorm_backward(t, t->dxh, t->xs + (size_t)NL * mD, t->stats + (size_t)NL * M, e->fln_g, t->dx, false, G + gl.fln_g,
@@ -764,7 +766,7 @@ static int backward_phase(showo_engine_t* e, int phase, const float* loss_grads_
         SHOWO_TRY(rowsum_bf16(t->tA, Mp, D, M, GL + gl.b2, st));
         // d W2 = dx^T * [attn | act]
         SHOWO_TRY(transpose_to_bf16<bf16>(a2, W2K, M, W2K, t->tB, Mp, nullptr, 0, st));
-        SHOWO_TRY(gemm_plain(t->tA, Mp, t->tB, Mp, D, W2K, M, GL + gl.w2, W2K, true, st));
+        SHOWO_TRY(gemm_plain(t->tA, Mp, t->tB, Mp, D, W2K, (int)Mp, GL + gl.w2, W2K, true, st));
         // d [attn | act] = dx * W2
         SHOWO_TRY(gemm_plain(t->dxb, D, t->w2t + (size_t)l * W2K * D, D, M, W2K, D, t->dA2, W2K, false, st));
         // attention backward: d q_rot, d k_rot -> dqk, d v -> dpre[:, D:2D]
@@ -789,7 +791,7 @@ static int backward_phase(showo_engine_t* e, int phase, const float* loss_grads_
         // d W1 = dpre^T * xh, d b1 = column sums of dpre
         SHOWO_TRY(transpose_to_bf16<bf16>(t->dpre, W1N, M, W1N, t->tA, Mp, nullptr, 0, st));
         SHOWO_TRY(transpose_to_bf16<bf16>(t->xh + (size_t)l * mD, D, M, D, t->tB, Mp, nullptr, 0, st));
-        SHOWO_TRY(gemm_plain(t->tA, Mp, t->tB, Mp, W1N, D, M, GL + gl.w1, D, true, st));
+        SHOWO_TRY(gemm_plain(t->tA, Mp, t->tB, Mp, W1N, D, (int)Mp, GL + gl.w1, D, true, st));
         SHOWO_TRY(rowsum_bf16(t->tA, Mp, W1N, M, GL + gl.b1, st));
         // d xh = dpre * W1, then LayerNorm backward into the residual gradient
         SHOWO_TRY(gemm_plain(t->dpre, W1N, t->w1t + (size_t)l * D * W1N, W1N, M, D, W1N, t->dxh, D, true, st));

@@ -120,6 +120,34 @@ def test_skinny_weight_streaming_gemm(lib, dev, Mm, N, K):
     assert (outr - (ref + res)).abs().max().item() < 2e-3
 
 
+def test_gemm_streamk_residual_epilogue_exact_and_deterministic(lib, dev):
+    """the layer's second GEMM at full size (4128 x 2048 x 10240, x += A W^T + b: 136 pair tiles on 74 clusters -> stream-K with parked
+    partial tiles): exact on small-integer operands whatever the split, identical from run to run, strided A like the engine's."""
+    Mm, N, K, ld = 4128, 2048, 10240, 14336
+    g = torch.Generator(device=dev).manual_seed(11)
+    buf = torch.randint(-4, 5, (Mm, ld), device=dev, generator=g).to(torch.bfloat16)
+    Bw = torch.randint(-2, 3, (N, K), device=dev, generator=g).to(torch.bfloat16)
+    bias = torch.randint(-8, 9, (N,), device=dev, generator=g).float()
+    res = torch.randint(-64, 65, (Mm, N), device=dev, generator=g).float()
+    A = buf[:, ld - K:]
+    ref = A.float() @ Bw.float().t() + bias + res
+    outs = []
+    for _ in range(3):
+        x = res.clone()
+        _lib.check(lib.showo_gemm_bf16(_lib.ptr(A), ld, _lib.ptr(Bw), K, Mm, N, K, _lib.ptr(x), N, _lib.ptr(bias), _lib.ptr(x), N, N, 1, 0, S()))
+        outs.append(x)
+    assert torch.equal(outs[0], ref)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
+    # random bf16 operands: fp32 accuracy with the partial sums added in a fixed order
+    A2 = (torch.randn(Mm, K, device=dev, generator=g) * 0.5).bfloat16()
+    B2 = (torch.randn(N, K, device=dev, generator=g) * 0.02).bfloat16()
+    ref2 = A2.float() @ B2.float().t() + bias + res
+    x1, x2 = res.clone(), res.clone()
+    for x in (x1, x2):
+        _lib.check(lib.showo_gemm_bf16(_lib.ptr(A2), K, _lib.ptr(B2), K, Mm, N, K, _lib.ptr(x), N, _lib.ptr(bias), _lib.ptr(x), N, N, 1, 0, S()))
+    assert (x1 - ref2).abs().max().item() < 2e-3 and torch.equal(x1, x2)
+
+
 def test_gemm_linearity_and_strided_operands(lib, dev):
     """size-independent properties at full size: C(A1 + A2) = C(A1) + C(A2) for exactly representable sums; A may be
     a strided column block of a wider buffer (the engine reads attn|act out of the k|v|q|act buffer)."""

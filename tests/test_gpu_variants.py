@@ -18,12 +18,15 @@ DECODE_K = "skinny or mmu_generate_batched or step_and_decode or megakernel"
 VARIANTS = {
     "attention_tcgen05": ({"SHOWO_ATTN_TC": "1"}, ATTN_K),
     "attention_mma_sync": ({"SHOWO_ATTN_TC": "0"}, ATTN_K),
+    "gemm_streamk": ({"SHOWO_GEMM_STREAMK": "1"}, GEMM_K + " or streamk"),
     "gemm_one_cta": ({"SHOWO_GEMM_CG": "1"}, GEMM_K),
     "gemm_cluster_multicast": ({"SHOWO_GEMM_CG": "1", "SHOWO_GEMM_CL": "2"}, GEMM_K),
     "gemm_bk32": ({"SHOWO_GEMM_CG": "1", "SHOWO_GEMM_BK": "32"}, GEMM_K),
     "gemm_pair_bk64": ({"SHOWO_GEMM_BK": "64"}, GEMM_K),
     "skinny_register_prefetch": ({"SHOWO_SKINNY": "1"}, DECODE_K),
     "decode_attention_per_thread": ({"SHOWO_DECODE_ATTN": "1"}, DECODE_K),
+    "decode_ln_fused": ({"SHOWO_DECODE_LN_FUSED": "1"}, DECODE_K),
+    "decode_l2_prefetch": ({"SHOWO_L2_PREFETCH": "1"}, DECODE_K),
     "no_pdl": ({"SHOWO_PDL": "0"}, "forward_tiny or mmu_generate_batched or teacher_forced"),
 }
 
