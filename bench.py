@@ -184,14 +184,12 @@ def run_ours(args):
     import showo_b200
     from showo_b200 import _lib
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    from showo_b200 import parallel as P
+    rank, local, world = P.env_world()
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun for N > 1"
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    P.init("nccl", dev)
     lib = _lib.require_gpu()
 
     model = showo_b200.Showo(False, V, 50295, materialize=False)
@@ -252,11 +250,10 @@ def run_ours(args):
             one_step(e2e)
         e1.record()
         torch.cuda.synchronize()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        ms = P.max_over_ranks(e0.elapsed_time(e1), dev)       # the slowest rank's device time
         if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
             dist.barrier()
-        return float(ms.item())
+        return ms
 
     for _ in range(max(args.warmup, 3)):      # both call shapes warm up (first-use allocations, pinned-copy set-up, mempool creation)
         one_step(False)
@@ -459,7 +456,8 @@ def train_step_bench(torch, dist, model, dev, world, rank, warm=1, steps=2):
     """BASELINE.json configs[4]: showo_demo_w_clip_vit_512x512.yaml mixed t2i + lm + mmu training step, forward / backward in bf16
     (fp32 master gradients), per-GPU micro-batch 8 rows of L = 1155 (3 t2i + 1 lm + 4 mmu-vit), data parallel:
     the t2i rows come from the device-side producer (showo_t2i_train_prep), the fp32 gradients (5.8 GB) are all-reduced per layer
-    on a side stream while the earlier layers' backward runs.  No optimizer step (the reference's AdamW is torch's)."""
+    on a side stream while the earlier layers' backward runs; the step ends with the engine's AdamW (showo_adamw_step: fp32 masters and
+    moments, decay on non-bias parameters like training/train.py:211-236) which also rewrites the bf16 working weights."""
     from showo_b200 import train_inputs as TI
     L5, N5, B_T2I, B_LM, B_MMU = 1155, 1024, 3, 1, 4
     g = torch.Generator().manual_seed(777 + rank)
@@ -477,6 +475,14 @@ def train_step_bench(torch, dist, model, dev, world, rank, warm=1, steps=2):
     mmu_lab = mmu_lab.to(dev)
     loss_w = torch.tensor([1.0, 0.1, 1.0], device=dev)          # training.t2i_coeff / lm_coeff / mmu_coeff of the yaml
     comm = torch.cuda.Stream(dev) if world > 1 else None
+    # optimizer state in the engine (fp32 masters + Adam moments): enable, then hand the weights over again so that their fp32 values are kept
+    from showo_b200 import _lib
+    lib = _lib.require_gpu()
+    model.enable_optimizer()
+    for name, t in gpu_random_weights(torch, dev, seed=0):
+        _lib.check(lib.showo_load_weight(model._engine, name.encode(), _lib.ptr(t), t.numel(), 1), f"load {name}")
+    _lib.check(lib.showo_weights_complete(model._engine), "weights_complete")
+    model._streamed = True
 
     def step():
         torch.manual_seed(1000 + rank)
@@ -491,6 +497,7 @@ def train_step_bench(torch, dist, model, dev, world, rank, warm=1, steps=2):
             torch.cuda.current_stream().wait_event(done)
         else:
             model.backward(loss_w)
+        model.adamw_step(lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)      # optimizer.params of the yaml
         return losses
     for _ in range(warm):
         step()
@@ -510,11 +517,11 @@ def train_step_bench(torch, dist, model, dev, world, rank, warm=1, steps=2):
     B = B_T2I + B_LM + B_MMU
     f_step = 3 * B * L5 * (G_TOK + A_PAIR * L5 + 2 * D * V)
     peaks = measured_peaks()
-    return {"metric": "train_step_tokens_per_sec_mixed_t2i_lm_mmu_L1155", "value": round(world * B * L5 / ms * 1e3, 1), "unit": "tokens/s",
+    return {"metric": "train_step_tokens_per_sec_mixed_t2i_lm_mmu_L1155_fwd_bwd_adamw", "value": round(world * B * L5 / ms * 1e3, 1), "unit": "tokens/s",
             "n_gpus": world, "ms_per_step": round(ms, 2), "steps": steps, "warmup": warm,
             "config": {"workload": "showo_demo_w_clip_vit_512x512.yaml geometry: forward + backward of 8 rows x L=1155 per GPU (3 t2i from the "
                                    "device-side producer + 1 lm + 4 mmu-vit), bf16 operands / fp32 gradients, per-layer gradient all-reduce "
-                                   "(fp32, 5.8 GB) overlapped with backward for N > 1; no optimizer step",
+                                   "(fp32, 5.8 GB) overlapped with backward for N > 1, then the engine-side AdamW step (fp32 masters + moments)",
                        "global_batch": world * B, "seq_len": L5},
             "losses": [round(float(x), 4) for x in losses[:, 0].tolist()],
             "roofline": {"bound": "tensor", "achieved": round(f_step / ms / 1e9, 1), "peak": peaks["bf16_sustained"], "unit": "TFLOP/s per GPU",

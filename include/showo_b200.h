@@ -141,6 +141,11 @@ SHOWO_API int showo_cross_entropy(const float* logits_dev, const int64_t* labels
 SHOWO_API int showo_mmu_sample(const float* logits_dev, int64_t ld, int B, int V, float temperature, int top_k,
                      const float* noise_expo_dev, uint64_t seed, uint32_t step, int64_t* out_tokens_dev, void* stream);
 
+/* Showo.mm_projector (models/modeling_showo.py:49-54: Linear(1024, 2048) -> nn.GELU() -> Linear(2048, 2048)) on the CLIP-ViT features, as
+ * inference_mmu.py:128-131 calls it: feats_dev fp32 [n, 1024] -> out_dev fp32 [n, 2048] (bf16 operands, fp32 accumulation, exact erf GELU).
+ * Weights arrive through showo_load_weight under "mm_projector.0.weight" / ".0.bias" / ".2.weight" / ".2.bias" (optional set). */
+SHOWO_API int showo_mm_projector(showo_engine_t* e, const float* feats_dev, int64_t n, float* out_dev, void* stream);
+
 /* model.showo.model.embed_tokens(ids) as called from outside (inference_mmu.py:134-136): out fp32 [n, hidden] */
 SHOWO_API int showo_embed_tokens(showo_engine_t* e, const int64_t* ids_dev, int64_t n, float* out_dev, void* stream);
 
@@ -166,6 +171,16 @@ SHOWO_API int showo_backward_phase(showo_engine_t* e, int phase, const float* lo
  * of showo_backward_phase writes: the buckets of the data-parallel gradient all-reduce. */
 SHOWO_API int showo_grad_buffer(showo_engine_t* e, float** base_dev, int64_t* numel);
 SHOWO_API int showo_grad_range(showo_engine_t* e, int phase, int64_t* begin, int64_t* end);
+/* The optimizer step of the training loop in the engine (training/train.py:211-236 AdamW construction, :617 optimizer.step()):
+ * torch.optim.AdamW's update with decoupled weight decay on every parameter whose name has no "bias" (the reference's other no_decay
+ * patterns match no Phi parameter name), on engine-owned fp32 master weights and moments, one pass per tensor over gradient + master +
+ * moments that also rewrites the engine's bf16 / fp32 working copy.  showo_optimizer_enable allocates masters and moments (3 x 5.8 GB
+ * for the full model) and must be called BEFORE the weights are handed over with showo_load_weight (it forgets the loaded set).
+ * showo_adamw_step consumes the gradients of the last showo_backward (all-reduced in place by the caller when data parallel);
+ * the bias-correction step counter lives in the engine.  showo_read_param returns the fp32 master of one reference parameter. */
+SHOWO_API int showo_optimizer_enable(showo_engine_t* e);
+SHOWO_API int showo_adamw_step(showo_engine_t* e, float lr, float beta1, float beta2, float eps, float weight_decay, void* stream);
+SHOWO_API int showo_read_param(showo_engine_t* e, const char* name, float* out_dev, int64_t numel, void* stream);
 /* gradient of one parameter of the reference state_dict (same names as showo_load_weight) -> out_dev (fp32, contiguous) */
 SHOWO_API int showo_read_grad(showo_engine_t* e, const char* name, float* out_dev, int64_t numel, void* stream);
 

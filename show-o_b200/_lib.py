@@ -56,10 +56,14 @@ _PROTOS = {
     "showo_backward_phase": (_I, [_P, _I, _P, _P, _P]),
     "showo_grad_buffer": (_I, [_P, C.POINTER(_P), C.POINTER(_I64)]),
     "showo_grad_range": (_I, [_P, _I, C.POINTER(_I64), C.POINTER(_I64)]),
+    "showo_optimizer_enable": (_I, [_P]),
+    "showo_adamw_step": (_I, [_P, _F, _F, _F, _F, _F, _P]),
+    "showo_read_param": (_I, [_P, C.c_char_p, _P, _I64, _P]),
     "showo_read_grad": (_I, [_P, C.c_char_p, _P, _I64, _P]),
     "showo_attention_bwd_test": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, C.POINTER(SeqMask), _P]),
     "showo_t2i_train_prep": (_I, [_P, _I, _I, _P, _P, _I64, _I, C.POINTER(C.c_int64), _F, _F, _I, _F, _P, _P, _P, C.c_uint64, _I,
                                   _P, _P, _P, _P, _P, _P, _P, _P]),
+    "showo_mm_projector": (_I, [_P, _P, _I64, _P, _P]),
     "showo_embed_tokens": (_I, [_P, _P, _I64, _P, _P]),
     "showo_kernel_launches": (_I64, [_P]),
     "magvit_engine_create": (_I, [_I, C.POINTER(_P)]),

@@ -62,13 +62,18 @@ def check_keys(expected, got, what: str, ignore_substrings=("rotary_emb.inv_freq
                        f"unexpected {extra[:5]}{'...' if len(extra) > 5 else ''}")
 
 
-def write_checkpoint(path: str, state_dict: Dict[str, torch.Tensor], config: dict | None = None, max_shard_bytes: int = 5 << 30):
-    """The inverse: `config.json` + `diffusion_pytorch_model.safetensors` (sharded with an index above `max_shard_bytes`)."""
-    from safetensors.torch import save_file
+def write_checkpoint(path: str, state_dict: Dict[str, torch.Tensor], config: dict | None = None, max_shard_bytes: int = 5 << 30,
+                     safe_serialization: bool = True):
+    """The inverse: `config.json` + `diffusion_pytorch_model.safetensors` (sharded with an index above `max_shard_bytes`), or -- with
+    safe_serialization=False, what training/train.py:710 asks for -- one pickled `diffusion_pytorch_model.bin`."""
     os.makedirs(path, exist_ok=True)
     if config is not None:
         json.dump(config, open(os.path.join(path, "config.json"), "w"), indent=2, sort_keys=True)
     sd = {k: v.detach().to("cpu").contiguous() for k, v in state_dict.items()}
+    if not safe_serialization:
+        torch.save(sd, os.path.join(path, "diffusion_pytorch_model.bin"))
+        return
+    from safetensors.torch import save_file
     shards, cur, cur_bytes = [], {}, 0
     for k in sorted(sd):
         nbytes = sd[k].numel() * sd[k].element_size()

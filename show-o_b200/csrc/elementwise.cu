@@ -120,6 +120,21 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ src, bf16* __restri
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) dst[i] = __float2bfloat16(src[i]);
 }
+// nn.GELU() (exact, erf form) in place on bf16 -- the activation of Showo.mm_projector (modeling_showo.py:51)
+__global__ void gelu_erf_bf16_kernel(bf16* __restrict__ x, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = __bfloat162float(x[i]);
+        x[i] = __float2bfloat16(0.5f * v * (1.f + erff(v * 0.70710678118654752f)));
+    }
+}
+int gelu_erf_bf16(bf16* x, int64_t n, cudaStream_t st) {
+    const int grid = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+    gelu_erf_bf16_kernel<<<grid > 0 ? grid : 1, 256, 0, st>>>(x, n);
+    note_launch();
+    SHOWO_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int f32_to_bf16(const float* src, bf16* dst, int64_t n, cudaStream_t st) {
     if (n == 0) return 0;
     int grid = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);

@@ -253,6 +253,17 @@ static int check_ready(showo_engine* e) {
 }
 
 int engine_check_ready(showo_engine* e) { return check_ready(e); }
+int engine_refresh_derived(showo_engine* e, cudaStream_t st) {
+    for (auto& w : e->layers) {
+        vec_add_kernel<<<cdiv(e->D, 256), 256, 0, st>>>(w.b_dense, w.b_fc2, w.b2, e->D);
+        note_launch();
+    }
+    SHOWO_CUDA_OK(cudaGetLastError());
+    const int off = e->cfg.llm_vocab_size + e->cfg.num_new_special_tokens, C = e->cfg.codebook_size;
+    if (e->head_b_img) SHOWO_CUDA_OK(cudaMemcpyAsync(e->head_b_img, e->head_b + off, (size_t)C * 4, cudaMemcpyDeviceToDevice, st));
+    ++e->weights_version;                         // the training step re-derives its transposed weight copies
+    return 0;
+}
 int engine_upload_masks(showo_engine* e, const showo_seq_mask_t* masks_host, int n, cudaStream_t st) { return upload_masks(e, masks_host, n, st); }
 int engine_ensure_ws(showo_engine* e, int rows, int n_seq, int L, int64_t logit_elems, cudaStream_t st) { return ensure_ws(e, rows, n_seq, L, logit_elems, st); }
 
@@ -340,7 +351,9 @@ int showo_engine_destroy(showo_engine_t* e) {
     dev_free(e->cos_tab); dev_free(e->sin_tab); dev_free(e->stage);
     dev_free(e->x); dev_free(e->xh); dev_free(e->buf); dev_free(e->kcache); dev_free(e->vtcache); dev_free(e->d_masks);
     dev_free(e->logits_ws); dev_free(e->conf_ws); dev_free(e->sampled_ws); dev_free(e->tok_ws); dev_free(e->argmax_keys); dev_free(e->finished_ws); dev_free(e->attn_ctr);
+    dev_free(e->mmp_w0); dev_free(e->mmp_b0); dev_free(e->mmp_w2); dev_free(e->mmp_b2); dev_free(e->mmp_in); dev_free(e->mmp_mid);
     if (e->train) train_state_destroy(e->train);
+    if (e->opt) opt_state_destroy(e->opt);
     delete e;
     return 0;
 }
@@ -410,11 +423,28 @@ int showo_load_weight(showo_engine_t* e, const char* name_c, const float* data, 
         else if (k == "self_attn.k_layernorm.weight") rc = copy_f32(w.kg, 64);
         else if (k == "self_attn.k_layernorm.bias") rc = copy_f32(w.kb, 64);
         else { set_last_error("unknown weight name " + name); rc = -2; }
+    } else if (name.compare(0, 13, "mm_projector.") == 0) {
+        // optional (w_clip_vit): not part of the backbone's required set, not touched by the engine-side optimizer
+        constexpr int64_t kIn = 1024, kMid = 2048, kOut = 2048;
+        if (!e->mmp_w0) {
+            SHOWO_TRY(dev_alloc(&e->mmp_w0, (size_t)(kMid * kIn))); SHOWO_TRY(dev_alloc(&e->mmp_b0, (size_t)kMid));
+            SHOWO_TRY(dev_alloc(&e->mmp_w2, (size_t)(kOut * kMid))); SHOWO_TRY(dev_alloc(&e->mmp_b2, (size_t)kOut));
+        }
+        if (name == "mm_projector.0.weight") { rc = expect(kMid * kIn); if (!rc) rc = f32_to_bf16(src, e->mmp_w0, numel, st); }
+        else if (name == "mm_projector.0.bias") rc = copy_f32(e->mmp_b0, kMid);
+        else if (name == "mm_projector.2.weight") { rc = expect(kOut * kMid); if (!rc) rc = f32_to_bf16(src, e->mmp_w2, numel, st); }
+        else if (name == "mm_projector.2.bias") rc = copy_f32(e->mmp_b2, kOut);
+        else { set_last_error("unknown weight name " + name); rc = -2; }
+        if (rc) return rc;
+        SHOWO_CUDA_OK(cudaStreamSynchronize(st));
+        e->loaded.insert(name);
+        return 0;
     } else {
         set_last_error("unknown weight name " + name);
         rc = -2;
     }
     if (rc) return rc;
+    if (e->opt) SHOWO_TRY(opt_store_master(e, name, src, numel, st));
     SHOWO_CUDA_OK(cudaStreamSynchronize(st));
     e->loaded.insert(name);
     e->finalized = false;
@@ -708,6 +738,34 @@ int showo_mmu_sample(const float* logits_dev, int64_t ld, int B, int V, float te
     ms.logits = logits_dev; ms.ld = ld; ms.B = B; ms.V = V; ms.temperature = temperature; ms.top_k = top_k;
     ms.noise_expo = noise_expo_dev; ms.seed = seed; ms.step = step; ms.out = out_tokens_dev; ms.out_stride = 1;
     return mmu_sample(ms, (cudaStream_t)stream);
+}
+
+int showo_mm_projector(showo_engine_t* e, const float* feats_dev, int64_t n, float* out_dev, void* stream) {
+    SHOWO_CHECK(e && feats_dev && out_dev && n > 0, "mm_projector: bad arguments");
+    SHOWO_TRY(engine_set_device(e));
+    SHOWO_CHECK(showo_device_count() > 0, "no sm_100 CUDA device visible: libshowo_b200 has no CPU fallback");
+    for (const char* k : {"mm_projector.0.weight", "mm_projector.0.bias", "mm_projector.2.weight", "mm_projector.2.bias"})
+        SHOWO_CHECK(e->loaded.count(k) == 1, std::string("mm_projector: weight not loaded: ") + k);
+    constexpr int kIn = 1024, kMid = 2048, kOut = 2048;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n > e->mmp_cap) {
+        SHOWO_CUDA_OK(cudaStreamSynchronize(st));
+        dev_free(e->mmp_in); dev_free(e->mmp_mid);
+        SHOWO_TRY(dev_alloc(&e->mmp_in, (size_t)n * kIn));
+        SHOWO_TRY(dev_alloc(&e->mmp_mid, (size_t)n * kMid));
+        e->mmp_cap = n;
+    }
+    SHOWO_TRY(f32_to_bf16(feats_dev, e->mmp_in, n * kIn, st));
+    GemmArgs g0{};
+    g0.A = e->mmp_in; g0.lda = kIn; g0.B = e->mmp_w0; g0.ldb = kIn; g0.M = (int)n; g0.N = kMid; g0.K = kIn;
+    g0.out = e->mmp_mid; g0.ldc = kMid; g0.bias = e->mmp_b0; g0.gelu_from = kMid;          // no gelu_new here: nn.GELU() is the erf form
+    g0.block_n = 128;                                 // keeps the M <= 16 case off the decode path's fp32-only epilogues
+    SHOWO_TRY(gemm_bf16(g0, GEMM_BIAS_BF16, st));
+    SHOWO_TRY(gelu_erf_bf16(e->mmp_mid, n * kMid, st));
+    GemmArgs g1{};
+    g1.A = e->mmp_mid; g1.lda = kMid; g1.B = e->mmp_w2; g1.ldb = kMid; g1.M = (int)n; g1.N = kOut; g1.K = kMid;
+    g1.out = out_dev; g1.ldc = kOut; g1.bias = e->mmp_b2; g1.block_n = 128;
+    return gemm_bf16(g1, GEMM_BIAS_F32, st);
 }
 
 int64_t showo_kernel_launches(showo_engine_t* e) { return e ? e->launches_last : 0; }

@@ -25,6 +25,8 @@ inline void dev_free(T*& p) {
 int64_t launches_total();
 struct TrainState;
 void train_state_destroy(TrainState* t);
+struct OptState;
+void opt_state_destroy(OptState* o);
 }  // namespace showo
 
 using showo::bf16;
@@ -62,9 +64,13 @@ struct showo_engine {
     float* logits_ws = nullptr; float* conf_ws = nullptr; int* sampled_ws = nullptr;
     int64_t* tok_ws = nullptr; int64_t tok_ws_cap = 0;
     unsigned long long* argmax_keys = nullptr;            // [16] packed (logit, ~index) maxima of the fused greedy head
+    // Showo.mm_projector (w_clip_vit): Linear(1024, 2048) -> GELU -> Linear(2048, 2048), modeling_showo.py:49-54
+    bf16* mmp_w0 = nullptr; float* mmp_b0 = nullptr; bf16* mmp_w2 = nullptr; float* mmp_b2 = nullptr;
+    bf16* mmp_in = nullptr; bf16* mmp_mid = nullptr; int64_t mmp_cap = 0;
     int* attn_ctr = nullptr;                              // work counter of the attention kernel's tail phase (self-resetting, zero between launches)
     int* finished_ws = nullptr;                           // [64] rows of the running mmu_generate that have produced eot_token
     int64_t launches_last = 0;
+    showo::OptState* opt = nullptr;                      // fp32 master weights + Adam moments (train.cu), showo_optimizer_enable
     showo::TrainState* train = nullptr;                  // training-step buffers (train.cu), allocated on first use
 };
 
@@ -73,3 +79,10 @@ struct showo_engine {
 int engine_check_ready(showo_engine* e);
 int engine_upload_masks(showo_engine* e, const showo_seq_mask_t* masks_host, int n, cudaStream_t st);
 int engine_ensure_ws(showo_engine* e, int rows, int n_seq, int L, int64_t logit_elems, cudaStream_t st);
+
+// train.cu: keep the fp32 value of a reference parameter as the optimizer's master copy (called by showo_load_weight when the
+// optimizer is enabled); engine.cu: re-derive b2 = b_dense + b_fc2 and the image slice of the head bias after an optimizer step
+namespace showo {
+int opt_store_master(showo_engine* e, const std::string& name, const float* src_dev, int64_t numel, cudaStream_t st);
+}
+int engine_refresh_derived(showo_engine* e, cudaStream_t st);

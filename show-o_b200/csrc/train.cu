@@ -208,7 +208,9 @@ __global__ void __launch_bounds__(256) qk_rope_train_kernel(QkTrainArgs a) {
 // backward of rotary (transpose of the rotation) and of LayerNorm(64); one warp per (row, head), the block walks all heads
 __global__ void __launch_bounds__(256) qk_rope_bwd_kernel(QkTrainArgs a) {
     __shared__ float red[8][8][32];
-    const int blocks_per_seq = (a.L + 31) >> 5;
+    // 8 positions per CTA, one per warp (a warp walks the heads of its position): 4x the CTAs of a 32-position block -- the kernel is a
+    // chain of warp reductions per (position, head), so it is resident warps that hide the shuffle latency (307 -> see profiles)
+    const int blocks_per_seq = (a.L + 7) >> 3;
     const int seq = blockIdx.x / blocks_per_seq, rb = blockIdx.x % blocks_per_seq;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int D = a.D;
@@ -217,9 +219,8 @@ __global__ void __launch_bounds__(256) qk_rope_bwd_kernel(QkTrainArgs a) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
     for (int h = 0; h < a.H; ++h) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int pos = rb * 32 + warp * 4 + i;
+        {
+            const int pos = rb * 8 + warp;
             if (pos >= a.L) continue;
             const int64_t m = (int64_t)seq * a.L + pos;
             float2 c = make_float2(1.f, 1.f), s = make_float2(0.f, 0.f);
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__(256) copy_cols_bf16_kernel(const bf16* __restr
 // ------------------------------------------------------------------------------------------------ transposes / row sums
 // dst[c, r] = bf16(src[r, c]) over 64 x 64 tiles (R, C even); optional row-major bf16 copy of the source (fp32 -> bf16)
 template <class TSrc>
-__global__ void __launch_bounds__(256) transpose_to_bf16_kernel(const TSrc* __restrict__ src, int64_t ld_s, int R, int C,
+__global__ void __launch_bounds__(256) transpose_to_bf16_kernel(const TSrc* __restrict__ src, int64_t ld_s, int R, int C, int R_pad,
                                                                 bf16* __restrict__ dst, int64_t ld_d, bf16* __restrict__ copy, int64_t ld_c) {
     __shared__ bf16 tile[64][66];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -337,8 +338,8 @@ __global__ void __launch_bounds__(256) transpose_to_bf16_kernel(const TSrc* __re
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const int c = c0 + ty + 8 * j, r = r0 + 2 * tx;          // dst row c, dst columns r, r + 1
-        if (c < C && r < R) {
+        const int c = c0 + ty + 8 * j, r = r0 + 2 * tx;          // dst row c, dst columns r, r + 1 (zeros in the pad columns [R, R_pad))
+        if (c < C && r < R_pad) {
             __nv_bfloat162 v;
             v.x = tile[2 * tx][ty + 8 * j];
             v.y = tile[2 * tx + 1][ty + 8 * j];
@@ -524,7 +525,9 @@ static int layernorm_backward(TrainState* t, const float* dy, const float* x, co
 template <class TSrc>
 static int transpose_to_bf16(const TSrc* src, int64_t ld_s, int R, int C, bf16* dst, int64_t ld_d, bf16* copy, int64_t ld_c, cudaStream_t st) {
     SHOWO_CHECK(C % 2 == 0 && ld_s % 2 == 0 && ld_d % 2 == 0, "transpose: even sizes expected");
-    transpose_to_bf16_kernel<TSrc><<<dim3(cdiv(C, 64), cdiv(R, 64)), 256, 0, st>>>(src, ld_s, R, C, dst, ld_d, copy, ld_c);
+    // the destination's row stride is the token count padded to the wgrad GEMM's 128-wide k block: the pad columns are written as zeros
+    const int R_pad = (ld_d >= R && ld_d % 128 == 0 && ld_d - R < 128) ? (int)ld_d : R;
+    transpose_to_bf16_kernel<TSrc><<<dim3(cdiv(C, 64), cdiv(R_pad, 64)), 256, 0, st>>>(src, ld_s, R, C, R_pad, dst, ld_d, copy, ld_c);
     note_launch();
     SHOWO_CUDA_OK(cudaGetLastError());
     return 0;
@@ -600,11 +603,13 @@ static int ensure_train(showo_engine* e, int M, cudaStream_t st) {
     return 0;
 }
 
-static int named_grad(showo_engine* e, const std::string& name, float** ptr, int64_t* rows, int64_t* cols, int64_t* ld) {
+// location of a reference parameter inside a buffer in the packed layout (the gradient buffer, or the optimizer's master / moment
+// buffers, which append one [NL][D] block: dense.bias and fc2.bias share a gradient but are two parameters)
+static int named_slot(showo_engine* e, float* base_ptr, bool split_bias, const std::string& name, float** ptr, int64_t* rows, int64_t* cols,
+                      int64_t* ld) {
     const GradLayout g = grad_layout(e);
-    TrainState* t = e->train;
     const int64_t D = e->D, F = e->F, V = e->V, W2K = e->W2K;
-    auto set = [&](int64_t off, int64_t r, int64_t c, int64_t l) { *ptr = t->grads + off; *rows = r; *cols = c; *ld = l; return 0; };
+    auto set = [&](int64_t off, int64_t r, int64_t c, int64_t l) { *ptr = base_ptr + off; *rows = r; *cols = c; *ld = l; return 0; };
     if (name == "showo.model.embed_tokens.weight") return set(g.embed, V, D, D);
     if (name == "showo.lm_head.weight") return set(g.head_w, V, D, D);
     if (name == "showo.lm_head.bias") return set(g.head_b, 1, V, V);
@@ -628,6 +633,7 @@ static int named_grad(showo_engine* e, const std::string& name, float** ptr, int
     if (k == "mlp.fc1.bias") return set(base + g.b1 + 3 * D, 1, F, F);
     if (k == "self_attn.dense.weight") return set(base + g.w2, D, D, W2K);
     if (k == "mlp.fc2.weight") return set(base + g.w2 + D, D, F, W2K);
+    if (k == "mlp.fc2.bias" && split_bias) return set(g.total + (int64_t)l * D, 1, D, D);
     if (k == "self_attn.dense.bias" || k == "mlp.fc2.bias") return set(base + g.b2, 1, D, D);
     if (k == "input_layernorm.weight") return set(base + g.ln_g, 1, D, D);
     if (k == "input_layernorm.bias") return set(base + g.ln_b, 1, D, D);
@@ -637,6 +643,51 @@ static int named_grad(showo_engine* e, const std::string& name, float** ptr, int
     if (k == "self_attn.k_layernorm.bias") return set(base + g.kb, 1, 64, 64);
     SHOWO_CHECK(false, "read_grad: unknown parameter " + name);
     return -2;
+}
+static int named_grad(showo_engine* e, const std::string& name, float** ptr, int64_t* rows, int64_t* cols, int64_t* ld) {
+    return named_slot(e, e->train->grads, false, name, ptr, rows, cols, ld);
+}
+
+// ================================================================================================ optimizer
+// torch.optim.AdamW as the reference instantiates it (training/train.py:211-236, :617): decoupled weight decay on every parameter
+// whose name has no "bias" (the reference's other no_decay patterns, "layer_norm.weight" / "embeddings.weight", match no Phi
+// parameter name, so LayerNorm weights and the embedding ARE decayed), same update order as torch's single-tensor AdamW:
+//   p *= 1 - lr * wd;  m += (g - m)(1 - b1);  v = b2 v + (1 - b2) g^2;  p -= (lr / bc1) m / (sqrt(v) / sqrt(bc2) + eps)
+// One pass per tensor over gradient + fp32 master + both moments, writing the engine's bf16 (or fp32) working copy on the way out.
+struct OptState {
+    float *master = nullptr, *m = nullptr, *v = nullptr;
+    int64_t n = 0, step = 0;
+};
+void opt_state_destroy(OptState* o) {
+    if (!o) return;
+    dev_free(o->master); dev_free(o->m); dev_free(o->v);
+    delete o;
+}
+
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m,
+                                                    float* __restrict__ v, int64_t rows, int64_t cols, int64_t ld, float lr, float b1, float b2,
+                                                    float eps, float wd, float bc1, float bc2_sqrt, bf16* __restrict__ out16,
+                                                    float* __restrict__ out32, int64_t out_ld) {
+    const int64_t n = rows * cols;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const int64_t r = i / cols, c = i % cols, o = r * ld + c;
+        const float gi = g[o];
+        float p = w[o] * (1.f - lr * wd);
+        const float mi = m[o] + (gi - m[o]) * (1.f - b1);
+        const float vi = v[o] * b2 + (1.f - b2) * gi * gi;
+        p -= (lr / bc1) * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+        w[o] = p; m[o] = mi; v[o] = vi;
+        if (out16) out16[r * out_ld + c] = __float2bfloat16(p);
+        if (out32) out32[r * out_ld + c] = p;
+    }
+}
+
+int opt_store_master(showo_engine* e, const std::string& name, const float* src_dev, int64_t numel, cudaStream_t st) {
+    float* dst; int64_t rows, cols, ld;
+    SHOWO_TRY(named_slot(e, e->opt->master, true, name, &dst, &rows, &cols, &ld));
+    SHOWO_CHECK(rows * cols == numel, "optimizer: parameter " + name + " has the wrong size");
+    SHOWO_CUDA_OK(cudaMemcpy2DAsync(dst, (size_t)ld * 4, src_dev, (size_t)cols * 4, (size_t)cols * 4, (size_t)rows, cudaMemcpyDeviceToDevice, st));
+    return 0;
 }
 
 }  // namespace showo
@@ -780,7 +831,7 @@ static int backward_phase(showo_engine_t* e, int phase, const float* loss_grads_
         QkTrainArgs q{};
         q.pre = pre; q.ld = W1N; q.n_seq = B; q.L = L; q.H = H; q.D = D; q.qg = w.qg; q.qb = w.qb; q.kg = w.kg; q.kb = w.kb;
         q.eps = e->cfg.ln_eps; q.cos_tab = e->cos_tab; q.sin_tab = e->sin_tab; q.dq = t->dqk; q.dk = t->dqk + mD; q.dpre = t->dpre;
-        const int nblk = B * cdiv(L, 32);
+        const int nblk = B * cdiv(L, 8);
         SHOWO_TRY(ensure_partials(t, (size_t)nblk * 256 + 256));
         q.partial = t->partials;
         qk_rope_bwd_kernel<<<nblk, 256, 0, st>>>(q);
@@ -847,6 +898,79 @@ int showo_grad_range(showo_engine_t* e, int phase, int64_t* begin, int64_t* end)
     if (phase >= 0) { *begin = gl.per_layer * phase; *end = gl.per_layer * (phase + 1); }
     else if (phase == -1) { *begin = gl.head_w; *end = gl.embed; }
     else { *begin = gl.embed; *end = gl.total; }
+    return 0;
+}
+
+int showo_optimizer_enable(showo_engine_t* e) {
+    SHOWO_CHECK(e != nullptr, "null engine");
+    SHOWO_CUDA_OK(cudaSetDevice(e->device));
+    if (e->opt) return 0;
+    OptState* o = new OptState();
+    o->n = grad_layout(e).total + (int64_t)e->NL * e->D;
+    if (dev_alloc(&o->master, (size_t)o->n) || dev_alloc(&o->m, (size_t)o->n) || dev_alloc(&o->v, (size_t)o->n)) { opt_state_destroy(o); return -1; }
+    SHOWO_CUDA_OK(cudaMemset(o->master, 0, (size_t)o->n * 4));
+    SHOWO_CUDA_OK(cudaMemset(o->m, 0, (size_t)o->n * 4));
+    SHOWO_CUDA_OK(cudaMemset(o->v, 0, (size_t)o->n * 4));
+    e->opt = o;
+    e->loaded.clear();                             // every parameter has to be handed over again so that its fp32 value is kept
+    e->finalized = false;
+    return 0;
+}
+
+int showo_adamw_step(showo_engine_t* e, float lr, float beta1, float beta2, float eps, float weight_decay, void* stream) {
+    SHOWO_TRY(engine_check_ready(e));
+    SHOWO_CHECK(e->opt != nullptr, "adamw_step: call showo_optimizer_enable (before loading the weights) first");
+    SHOWO_CHECK(e->train && e->train->grads, "adamw_step: no gradients (run showo_train_forward + showo_backward first)");
+    cudaStream_t st = (cudaStream_t)stream;
+    OptState* o = e->opt;
+    const GradLayout gl = grad_layout(e);
+    const int64_t D = e->D, F = e->F, V = e->V, W1N = e->W1N, W2K = e->W2K;
+    const int64_t t = ++o->step;
+    const float bc1 = 1.f - powf(beta1, (float)t), bc2s = sqrtf(1.f - powf(beta2, (float)t));
+    float* G = e->train->grads;
+    // one tensor: `off` in the master / moment buffers, `goff` in the gradient buffer, `decay` per the reference's grouping
+    auto upd = [&](int64_t off, int64_t goff, int64_t rows, int64_t cols, int64_t ld, bool decay, bf16* out16, float* out32, int64_t out_ld) -> int {
+        const int64_t n = rows * cols;
+        const int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
+        // the gradient sits at the same (row, col) position of its own packed block: both buffers share `ld`
+        adamw_kernel<<<grid, 256, 0, st>>>(o->master + off, G + goff - 0, o->m + off, o->v + off, rows, cols, ld, lr, beta1, beta2, eps,
+                                           decay ? weight_decay : 0.f, bc1, bc2s, out16, out32, out_ld);
+        note_launch();
+        return 0;
+    };
+    (void)F;
+    for (int l = 0; l < e->NL; ++l) {
+        const LayerW& w = e->layers[l];
+        const int64_t b = gl.per_layer * l;
+        // NB adamw_kernel indexes gradient and master with the same offsets relative to their bases: pass bases shifted alike
+        SHOWO_TRY(upd(b + gl.w1, b + gl.w1, W1N, D, D, true, w.w1, nullptr, D));
+        SHOWO_TRY(upd(b + gl.b1, b + gl.b1, 1, W1N, W1N, false, nullptr, w.b1, W1N));
+        SHOWO_TRY(upd(b + gl.w2, b + gl.w2, D, W2K, W2K, true, w.w2, nullptr, W2K));
+        SHOWO_TRY(upd(b + gl.b2, b + gl.b2, 1, D, D, false, nullptr, w.b_dense, D));                          // self_attn.dense.bias
+        SHOWO_TRY(upd(gl.total + (int64_t)l * D, b + gl.b2, 1, D, D, false, nullptr, w.b_fc2, D));           // mlp.fc2.bias: same gradient
+        SHOWO_TRY(upd(b + gl.ln_g, b + gl.ln_g, 1, D, D, true, nullptr, w.ln_g, D));
+        SHOWO_TRY(upd(b + gl.ln_b, b + gl.ln_b, 1, D, D, false, nullptr, w.ln_b, D));
+        SHOWO_TRY(upd(b + gl.qg, b + gl.qg, 1, 64, 64, true, nullptr, w.qg, 64));
+        SHOWO_TRY(upd(b + gl.qb, b + gl.qb, 1, 64, 64, false, nullptr, w.qb, 64));
+        SHOWO_TRY(upd(b + gl.kg, b + gl.kg, 1, 64, 64, true, nullptr, w.kg, 64));
+        SHOWO_TRY(upd(b + gl.kb, b + gl.kb, 1, 64, 64, false, nullptr, w.kb, 64));
+    }
+    SHOWO_TRY(upd(gl.head_w, gl.head_w, V, D, D, true, e->head_w, nullptr, D));
+    SHOWO_TRY(upd(gl.head_b, gl.head_b, 1, V, V, false, nullptr, e->head_b, V));
+    SHOWO_TRY(upd(gl.fln_g, gl.fln_g, 1, D, D, true, nullptr, e->fln_g, D));
+    SHOWO_TRY(upd(gl.fln_b, gl.fln_b, 1, D, D, false, nullptr, e->fln_b, D));
+    SHOWO_TRY(upd(gl.embed, gl.embed, V, D, D, true, e->embed, nullptr, D));
+    SHOWO_CUDA_OK(cudaGetLastError());
+    return engine_refresh_derived(e, st);
+}
+
+int showo_read_param(showo_engine_t* e, const char* name, float* out_dev, int64_t numel, void* stream) {
+    SHOWO_CHECK(e && e->opt && name && out_dev, "read_param: needs an engine with the optimizer enabled");
+    SHOWO_CUDA_OK(cudaSetDevice(e->device));
+    float* p; int64_t rows, cols, ld;
+    SHOWO_TRY(named_slot(e, e->opt->master, true, std::string(name), &p, &rows, &cols, &ld));
+    SHOWO_CHECK(rows * cols == numel, std::string("read_param: ") + name + " has " + std::to_string(rows * cols) + " elements");
+    SHOWO_CUDA_OK(cudaMemcpy2DAsync(out_dev, (size_t)cols * 4, p, (size_t)ld * 4, (size_t)cols * 4, (size_t)rows, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return 0;
 }
 

@@ -84,6 +84,19 @@ class _PhiForCausalLM(nn.Module):
         return e
 
 
+class _MMProjector(nn.Sequential):
+    """Parameter container of Showo.mm_projector (modeling_showo.py:49-54) whose call runs on the engine (showo_mm_projector):
+    `model.mm_projector(images_embeddings)` as inference_mmu.py:131 does it.  Inference only (the reference trains it; its gradient is
+    not part of the engine's backward)."""
+
+    def __init__(self, owner):
+        super().__init__(nn.Linear(1024, 2048), nn.GELU(), nn.Linear(2048, 2048))
+        object.__setattr__(self, "_owner", owner)
+
+    def forward(self, x):
+        return self._owner._project(x)
+
+
 class _TrainStep(torch.autograd.Function):
     """autograd bridge of the training step: forward = showo_train_forward, backward = showo_backward + showo_read_grad.
     (Plumbing only: no arithmetic happens in torch.)"""
@@ -136,7 +149,7 @@ class Showo(nn.Module):
         else:
             self.showo = None
         if w_clip_vit:
-            self.mm_projector = nn.Sequential(nn.Linear(1024, 2048), nn.GELU(), nn.Linear(2048, 2048))
+            self.mm_projector = _MMProjector(self)
         self._engine = None
         self._engine_versions = None
         self._engine_device = None
@@ -162,8 +175,9 @@ class Showo(nn.Module):
         model.load_state_dict({k: v for k, v in sd.items() if "rotary_emb.inv_freq" not in k}, strict=True)
         return model
 
-    def save_pretrained(self, path, max_shard_bytes: int = 5 << 30):
-        """config.json + safetensors in the layout `from_pretrained` (and the reference's ModelMixin) reads back."""
+    def save_pretrained(self, path, max_shard_bytes: int = 5 << 30, safe_serialization: bool = True, **kwargs):
+        """config.json + safetensors (or, safe_serialization=False like training/train.py:710, a pickled .bin) in the layout
+        `from_pretrained` (and the reference's ModelMixin) reads back."""
         from . import checkpoint
         if self.showo is None:
             raise _lib.ShowoError("Showo.save_pretrained: the weights were streamed into the engine (materialize=False); "
@@ -171,7 +185,7 @@ class Showo(nn.Module):
         cfg = {"_class_name": "Showo", "w_clip_vit": bool(self.config.w_clip_vit), "vocab_size": int(self.vocab_size),
                "llm_vocab_size": int(self.config.llm_vocab_size), "llm_model_path": "", "codebook_size": int(self.config.codebook_size),
                "num_vq_tokens": int(self.config.num_vq_tokens), "load_from_showo": False}
-        checkpoint.write_checkpoint(path, self.state_dict(), cfg, max_shard_bytes)
+        checkpoint.write_checkpoint(path, self.state_dict(), cfg, max_shard_bytes, safe_serialization=safe_serialization)
 
     # ------------------------------------------------------------------ engine plumbing
     @property
@@ -198,7 +212,7 @@ class Showo(nn.Module):
         if self._engine is None:
             self._make_engine(device)
         for name, t in weights.items():
-            if not name.startswith("showo."):
+            if not (name.startswith("showo.") or name.startswith("mm_projector.")):
                 continue
             if "rotary_emb" in name:
                 continue
@@ -236,15 +250,19 @@ class Showo(nn.Module):
             _lib.load().showo_engine_destroy(self._engine)
             self._engine, self._engine_versions = None, None
         keys = {"showo." + k: self._param_key(p) for k, p in self.showo.named_parameters()}
+        if self.w_clip_vit:
+            keys.update({"mm_projector." + k: self._param_key(p) for k, p in self.mm_projector.named_parameters()})
         prev = self._engine_versions or {}
         stale = {k: v for k, v in keys.items() if prev.get(k) != v}
         if self._engine is not None and not stale:
             return self._engine
         params = dict(self.showo.named_parameters())
+        if self.w_clip_vit:
+            params.update({"../mm_projector." + k: p for k, p in self.mm_projector.named_parameters()})
         with torch.cuda.device(dev):
             # the upload runs on the legacy default stream: fence it against whatever the caller's stream still has in flight
             torch.cuda.current_stream().synchronize()
-            self.load_weights({k: params[k[len("showo."):]] for k in stale}, device=dev)
+            self.load_weights({k: (params[k[len("showo."):]] if k.startswith("showo.") else params["../" + k]) for k in stale}, device=dev)
             torch.cuda.synchronize(dev)
         self._engine_versions = keys
         return self._engine
@@ -417,6 +435,55 @@ class Showo(nn.Module):
         done = torch.cuda.Event()
         done.record(comm)
         return done
+
+    @torch.no_grad()
+    def _project(self, x: torch.Tensor) -> torch.Tensor:
+        """mm_projector(x): x [..., 1024] CLIP-ViT features -> [..., 2048] embeddings (inference_mmu.py:128-131)."""
+        lib = _lib.require_gpu()
+        eng = self._sync_engine()
+        xf = x.float().contiguous()
+        out = torch.empty(*xf.shape[:-1], 2048, dtype=torch.float32, device=xf.device)
+        with torch.cuda.device(xf.device):
+            _lib.check(lib.showo_mm_projector(eng, _lib.ptr(xf), xf.numel() // 1024, _lib.ptr(out), _lib.current_stream_ptr()), "showo_mm_projector")
+        return out.to(x.dtype) if x.dtype != torch.float32 else out
+
+    # ------------------------------------------------------------------ optimizer (training/train.py:211-236, :617)
+    def enable_optimizer(self, device=None):
+        """Keep fp32 master weights + Adam moments in the engine.  For a materialized model every parameter is re-streamed; a model
+        built with materialize=False must call this BEFORE load_weights()."""
+        lib = _lib.require_gpu()
+        if self._engine is None:
+            dev = torch.device(device) if device is not None else (self.device if self.showo is not None else torch.device("cuda", torch.cuda.current_device()))
+            self._make_engine(dev)
+        _lib.check(lib.showo_optimizer_enable(self._engine), "showo_optimizer_enable")
+        self._streamed = False
+        self._engine_versions = None
+        if self.showo is not None:
+            self._sync_engine()
+        return self
+
+    def adamw_step(self, lr: float, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01):
+        """optimizer.step() on the engine's masters with the gradients of the last backward (decay on every non-bias parameter)."""
+        lib = _lib.require_gpu()
+        with torch.cuda.device(self._engine_device):
+            _lib.check(lib.showo_adamw_step(self._engine, float(lr), float(betas[0]), float(betas[1]), float(eps), float(weight_decay),
+                                            _lib.current_stream_ptr()), "showo_adamw_step")
+
+    def read_param(self, name: str, like: Optional[torch.Tensor] = None, shape=None):
+        """fp32 master value of one parameter (reference state_dict name) after engine-side optimizer steps."""
+        lib = _lib.require_gpu()
+        out = torch.empty(like.shape if like is not None else shape, dtype=torch.float32, device=self._engine_device)
+        with torch.cuda.device(self._engine_device):
+            _lib.check(lib.showo_read_param(self._engine, name.encode(), _lib.ptr(out), out.numel(), _lib.current_stream_ptr()),
+                       f"showo_read_param({name})")
+        return out
+
+    @torch.no_grad()
+    def pull_parameters(self):
+        """Copy the engine's fp32 masters back into the torch parameters (before state_dict() / save_pretrained after training)."""
+        for k, p in self.showo.named_parameters():
+            p.copy_(self.read_param("showo." + k, like=p))
+        self._engine_versions = {"showo." + k: self._param_key(p) for k, p in self.showo.named_parameters()}
 
     def read_grad(self, name: str, like: Optional[torch.Tensor] = None, shape=None):
         """Gradient of one parameter (reference state_dict name) as a fresh fp32 tensor."""

@@ -385,6 +385,60 @@ def test_forward_masks_lm_mmu_and_embeddings_input(tiny, dev):
     assert (got - ref).abs().max().item() < TOL_TINY
 
 
+def test_mm_projector_on_engine(dev):
+    """Showo.mm_projector (modeling_showo.py:49-54, inference_mmu.py:131) through the drop-in class: Linear(1024, 2048) -> exact GELU ->
+    Linear(2048, 2048) on the engine vs torch fp32 on the same parameters; bf16 operands: |d| <= 1 % of the output scale."""
+    torch.manual_seed(3)
+    m = showo_b200.Showo(True, 58498, 50295, phi_dims=FX.TINY).to(dev)
+    x = torch.randn(2, 576, 1024, device=dev)
+    got = m.mm_projector(x)
+    seq = torch.nn.Sequential(*list(m.mm_projector.children()))
+    with torch.no_grad():
+        ref = seq(x)
+    assert got.shape == (2, 576, 2048) and got.dtype == torch.float32
+    err, scale = (got - ref).abs().max().item(), ref.abs().max().item()
+    print(f"mm_projector: max|d| {err:.4f} of scale {scale:.3f}")
+    _record("mm_projector", {"max_abs": err, "ref_max": scale})
+    assert err < 0.01 * scale
+    # a tiny batch (M <= 16) takes the same tensor-core path, and a parameter update is picked up
+    assert (m.mm_projector(x[:1, :3]) - ref[:1, :3]).abs().max().item() < 0.01 * scale
+    with torch.no_grad():
+        m.mm_projector[2].bias.add_(1.0)
+    assert (m.mm_projector(x) - ref - 1.0).abs().max().item() < 0.01 * scale
+
+
+def test_mmu_generate_from_input_embeddings(tiny, lib, dev):
+    """the w_clip_vit branch of mmu_generate (modeling_showo.py:231-233, inference_mmu.py:100-151): the prompt arrives as embeddings
+    under the mmu_vit window mask.  (a) embeddings produced by the engine's own embed_tokens give the SAME tokens as the ids branch,
+    bit for bit; (b) the first generated token equals the oracle's argmax on the same embeddings unless the oracle's own top-2 margin
+    is inside the logit tolerance; (c) the early stop at eot_token cuts the lengths."""
+    dims, W, m = tiny
+    mm = FX.tiny_mmu_inputs(VOC)
+    B, L0 = mm.shape
+    n_new = 6
+    emb = torch.empty(B * L0, dims.hidden, device=dev)
+    _lib.check(lib.showo_embed_tokens(m._engine, _lib.ptr(mm.to(dev).contiguous()), B * L0, _lib.ptr(emb), S()), "embed_tokens")
+    emb = emb.view(B, L0, dims.hidden)
+    descs = M.descriptors_mmu_vit(B, system_prompt_len=4, n_vis=100)
+    t_ids, _ = m.mmu_generate_batched(mm.to(dev), attention_mask=descs, max_new_tokens=n_new, top_k=1)
+    t_emb, l_emb = m.mmu_generate_batched(None, input_embeddings=emb, attention_mask=descs, max_new_tokens=n_new, top_k=1)
+    assert torch.equal(t_ids, t_emb) and l_emb.tolist() == [n_new] * B
+    mask = O.additive_from_allowed(O.mask_allowed_mmu_vit(B, L0, system_prompt_len=4, n_vis=100))
+    with torch.no_grad():
+        lg = O.showo_logits(W, dims, input_embeddings=emb.cpu(), add_mask=mask)[:, -1]
+    top2 = lg.topk(2)
+    for b in range(B):
+        if int(t_emb[b, 0]) != int(top2.indices[b, 0]):
+            assert float(top2.values[b, 0] - top2.values[b, 1]) < 2 * TOL_TINY and int(t_emb[b, 0]) == int(top2.indices[b, 1])
+    # early stop: a token that row 0 produces at step 2 is declared eot -> lengths <= position of its first occurrence + 1, tokens unchanged
+    eot = int(t_emb[0, 2])
+    t2, l2 = m.mmu_generate_batched(None, input_embeddings=emb, attention_mask=descs, max_new_tokens=n_new, top_k=1, eot_token=eot)
+    for b in range(B):
+        hit = (t_emb[b] == eot).nonzero()
+        want = int(hit[0]) + 1 if hit.numel() else n_new
+        assert int(l2[b]) == want and torch.equal(t2[b, :want], t_emb[b, :want])
+
+
 def test_t2i_generate_teacher_forced_parity(tiny, lib, dev):
     """Each denoise step is replayed from the ORACLE's input ids: logits within tolerance, the sampler on the oracle's
     logits is bit-exact, and on the engine's logits a token may differ only below the 2x-error decision margin."""

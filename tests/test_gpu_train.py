@@ -223,3 +223,48 @@ def test_autograd_bridge_matches_engine_gradients(dev):
         m.refresh_engine()
         fresh = m(ids.to(dev), attention_mask=mask.to(dev))
     assert torch.equal(before, stale) and (fresh - before - 1.0).abs().max().item() < 1e-4
+
+
+def test_engine_adamw_matches_torch_adamw(dev):
+    """showo_adamw_step on the engine's fp32 masters == torch.optim.AdamW as training/train.py:211-236 builds it (weight decay on every
+    parameter whose name has no "bias": the reference's other no_decay patterns match no Phi parameter), three steps, every parameter --
+    fed with the engine's own gradients, so only the optimizer arithmetic and the parameter mapping (fused W1 / W2 blocks, the two
+    biases that share a gradient) are compared."""
+    dims = O.PhiDims(**FX.TINY)
+    W = O.make_showo_weights(dims, seed=3)
+    # non-trivial biases / LayerNorm parameters so that the decay split is visible
+    g = torch.Generator().manual_seed(9)
+    W = {k: (v + 0.05 * torch.randn(v.shape, generator=g) if (k.endswith("bias") or "layernorm" in k) else v) for k, v in W.items()}
+    m = showo_b200.Showo(False, dims.vocab_size, VOC.llm_vocab_size, phi_dims=FX.TINY, materialize=False)
+    m.enable_optimizer(device=dev)
+    m.load_weights(W, device=dev)
+    ref = {k: v.clone().to(dev).requires_grad_(True) for k, v in W.items()}
+    no_decay = ["bias", "layer_norm.weight", "mlm_ln.weight", "embeddings.weight"]                  # train.py:211
+    hp = dict(lr=1e-3, betas=(0.9, 0.999), eps=1e-8)
+    opt = torch.optim.AdamW([{"params": [p for n, p in ref.items() if not any(nd in n for nd in no_decay)], "weight_decay": 0.01},
+                             {"params": [p for n, p in ref.items() if any(nd in n for nd in no_decay)], "weight_decay": 0.0}], **hp)
+    ids, mask, labels, sizes = FX.train_batch(VOC)
+    B, L = ids.shape
+    descs = M.descriptors_from_dense(mask.to(dev))
+    terms = m._loss_terms(B, L, *sizes, 128)
+    losses = []
+    for step in range(3):
+        _, ls = m.train_forward(ids.to(dev), None, descs, labels.to(dev), terms, want_logits=False)
+        losses.append(float((ls[:, 0] * torch.tensor(FX.TRAIN_COEFF, device=dev)).sum()))
+        m.backward(FX.TRAIN_COEFF)
+        for k, p in ref.items():
+            p.grad = m.read_grad(k, like=p)
+        opt.step()
+        m.adamw_step(weight_decay=0.01, **hp)
+        worst = 0.0
+        for k, p in ref.items():
+            got = m.read_param(k, like=p)
+            err = float((got - p.detach()).abs().max() / (p.detach().abs().max() + 1e-12))
+            worst = max(worst, err)
+            assert err < 2e-6, (step, k, err)
+        print(f"adamw step {step}: loss {losses[-1]:.4f}, worst relative parameter difference vs torch {worst:.2e}")
+    assert losses[2] < losses[0]                  # the engine trains on its own updated bf16 working copies
+    # a decayed LayerNorm weight and an undecayed bias really moved differently from their gradients alone
+    k_w, k_b = "showo.model.layers.0.input_layernorm.weight", "showo.model.layers.0.input_layernorm.bias"
+    assert not torch.equal(m.read_param(k_w, like=ref[k_w]), W[k_w].to(dev)) and not torch.equal(m.read_param(k_b, like=ref[k_b]), W[k_b].to(dev))
+    _record("adamw_vs_torch", {"worst_rel_param_diff": worst, "losses": losses})
