@@ -76,6 +76,21 @@ __device__ __forceinline__ TcUnit tc_unit(int u, int tiles, int H) {
     const int t = u % tiles, sh = u / tiles;
     return TcUnit{sh / H, sh % H, t * 128};
 }
+// the units of one CTA (u = blockIdx.x, + gridDim.x, ...) decoded incrementally: the stride is split once into its (tile, head,
+// sequence) digits, so a step is three adds with carries instead of four integer divisions
+struct TcUnitWalk {
+    int t, h, seq, dt, dh, ds, tiles, H;
+    __device__ __forceinline__ TcUnitWalk(int u0, int stride, int tiles_, int H_) : tiles(tiles_), H(H_) {
+        t = u0 % tiles_; const int sh = u0 / tiles_; h = sh % H_; seq = sh / H_;
+        dt = stride % tiles_; const int s2 = stride / tiles_; dh = s2 % H_; ds = s2 / H_;
+    }
+    __device__ __forceinline__ TcUnit get() const { return TcUnit{seq, h, t * 128}; }
+    __device__ __forceinline__ void step() {
+        t += dt; if (t >= tiles) { t -= tiles; ++h; }
+        h += dh; if (h >= H) { h -= H; ++seq; }
+        seq += ds;
+    }
+};
 // first key a tile may attend to, rounded down to the 16-byte granule of the V^T box: rows at or behind the left padding never
 // see a pad column, so their key loop starts at pad_end instead of 0 (t2i: 60-126 of the 387 keys are pads)
 __device__ __forceinline__ int tc_key_begin(const showo_seq_mask_t& m, int q_lo) { return q_lo >= m.pad_end ? (m.pad_end & ~7) : 0; }
@@ -96,7 +111,8 @@ constexpr int kTailParts = kTcThreads / 64;                    // key slices of 
 struct TailSmem {
     static constexpr size_t k_off = 0;                                                   // [128][128 B]
     static constexpr size_t v_off = (size_t)kTailChunk * 128;                            // [64][kTailVStride]
-    static constexpr size_t sc_off = v_off + (size_t)64 * kTailVStride;                  // float [kTailMax][128]
+    static constexpr size_t buf_bytes = v_off + (size_t)64 * kTailVStride;               // one K + V^T chunk; two of them (double buffer)
+    static constexpr size_t sc_off = 2 * buf_bytes;                                      // float [kTailMax][128]
     static constexpr size_t q_off = sc_off + (size_t)kTailMax * kTailChunk * 4;          // float [kTailMax][64]
     static constexpr size_t part_off = q_off + (size_t)kTailMax * 64 * 4;                // float [kTailParts][kTailMax][64]
     static constexpr size_t stat_off = part_off + (size_t)kTailParts * kTailMax * 64 * 4;   // float m[4], l[4], alpha[4]; int item
@@ -105,8 +121,6 @@ struct TailSmem {
 static_assert(TailSmem::total <= 32768 + 2 * kTcStages * 8192 + 32768, "the tail phase reuses the pipeline's tile buffers");
 
 __device__ __forceinline__ void tc_tail_phase(const AttnArgs& a, uint8_t* smem, uint64_t* bar, int n_tail, int row_begin, int* work_ctr) {
-    uint8_t* Ks = smem + TailSmem::k_off;
-    uint8_t* Vs = smem + TailSmem::v_off;
     float* sc_s = reinterpret_cast<float*>(smem + TailSmem::sc_off);
     float* q_s = reinterpret_cast<float*>(smem + TailSmem::q_off);
     float* part = reinterpret_cast<float*>(smem + TailSmem::part_off);
@@ -118,7 +132,20 @@ __device__ __forceinline__ void tc_tail_phase(const AttnArgs& a, uint8_t* smem, 
     const int n_items = a.n_seq * a.H;
     const float scl = a.scale * 1.4426950408889634f;
     const int d = tid & 63, slice = tid >> 6;
-    uint32_t phase = 0;
+    uint32_t phase[2] = {0u, 0u};
+    // a chunk's copies: threads 0..63 bring one V^T row each, thread 64 the K rows; every issuer arrives with its own byte count
+    // (barrier count 65), so no CTA barrier is needed between the announcement and the copies
+    auto issue_chunk = [&](int buf, const bf16* kbase, const bf16* vbase, int c0, int nk) {
+        uint8_t* Kb = smem + (size_t)buf * TailSmem::buf_bytes + TailSmem::k_off;
+        uint8_t* Vb = smem + (size_t)buf * TailSmem::buf_bytes + TailSmem::v_off;
+        if (tid < 64) {
+            mbar_arrive_expect_tx(&bar[buf], (uint32_t)nk * 2u);
+            bulk_g2s(Vb + (size_t)tid * kTailVStride, vbase + (int64_t)tid * a.Lmax + c0, (uint32_t)nk * 2u, &bar[buf]);
+        } else if (tid == 64) {
+            mbar_arrive_expect_tx(&bar[buf], (uint32_t)nk * 128u);
+            bulk_g2s(Kb, kbase + (int64_t)c0 * 64, (uint32_t)nk * 128u, &bar[buf]);
+        }
+    };
     for (;;) {
         __syncthreads();                         // the previous item's smem (and s_item) is no longer read
         if (tid == 0) {
@@ -146,17 +173,18 @@ __device__ __forceinline__ void tc_tail_phase(const AttnArgs& a, uint8_t* smem, 
         float acc[kTailMax];
 #pragma unroll
         for (int r = 0; r < kTailMax; ++r) acc[r] = 0.f;
-        for (int c0 = kb8; c0 < k_end; c0 += kTailChunk) {
-            const int nk = min(kTailChunk, ((k_end - c0) + 7) & ~7);        // keys of this chunk (multiple of 8, within Lmax)
-            __syncthreads();                     // the previous chunk's tiles are no longer read; q_s is written
-            if (tid == 0) {
-                mbar_arrive_expect_tx(bar, (uint32_t)nk * 128u + 64u * (uint32_t)nk * 2u);
-                bulk_g2s(Ks, kbase + (int64_t)c0 * 64, (uint32_t)nk * 128u, bar);
-            }
-            __syncthreads();                     // the expect_tx precedes every complete_tx of the row copies
-            if (tid < 64) bulk_g2s(Vs + (size_t)tid * kTailVStride, vbase + (int64_t)tid * a.Lmax + c0, (uint32_t)nk * 2u, bar);
-            mbar_wait(bar, phase);
-            phase ^= 1u;
+        auto chunk_keys = [&](int c0) { return min(kTailChunk, ((k_end - c0) + 7) & ~7); };     // multiple of 8, within Lmax
+        if (kb8 < k_end) issue_chunk(0, kbase, vbase, kb8, chunk_keys(kb8));
+        int ci = 0;
+        for (int c0 = kb8; c0 < k_end; c0 += kTailChunk, ++ci) {
+            const int nk = chunk_keys(c0);
+            const int buf = ci & 1;
+            __syncthreads();                     // chunk ci - 1 (the other buffer) is no longer read; q_s / the statistics are written
+            if (c0 + kTailChunk < k_end) issue_chunk(buf ^ 1, kbase, vbase, c0 + kTailChunk, chunk_keys(c0 + kTailChunk));   // next chunk in flight
+            const uint8_t* Ks = smem + (size_t)buf * TailSmem::buf_bytes + TailSmem::k_off;
+            const uint8_t* Vs = smem + (size_t)buf * TailSmem::buf_bytes + TailSmem::v_off;
+            mbar_wait(&bar[buf], phase[buf]);
+            phase[buf] ^= 1u;
             // ---- scores: two threads per key (32 dims each); 16-byte piece (c ^ key): consecutive keys hit different bank groups
             if (tid < 2 * kTailChunk) {
                 const int kk = tid >> 1, hf = tid & 1;
@@ -302,7 +330,7 @@ omni_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         for (int s = 0; s < 2; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
         for (int s = 0; s < kTcStages; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 256); mbar_init(&pv_done[s], 1); mbar_init(&o_free[s], 256); }
-        mbar_init(bars + 22, 1);                     // tail phase: bulk copies of a K / V^T chunk
+        mbar_init(bars + 22, 65); mbar_init(bars + 23, 65);   // tail phase: the bulk copies of a K / V^T chunk (64 row copies + 1), two buffers
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc<256>(tmem_slot);
@@ -321,8 +349,9 @@ omni_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     if (warp == 0) {
         if (lane == 0) {          // ================================================================= TMA producer
             uint32_t kv_it = 0, u_it = 0;
-            for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++u_it) {
-                const TcUnit un = tc_unit(u, tiles, a.H);
+            TcUnitWalk walk(blockIdx.x, gridDim.x, tiles, a.H);
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++u_it, walk.step()) {
+                const TcUnit un = walk.get();
                 const showo_seq_mask_t msk = mask_of(un.seq);
                 const int q_lo = a.pos0 + un.q0, q_hi = q_lo + 127;
                 const int k_lo = tc_key_begin(msk, q_lo);
@@ -362,10 +391,11 @@ omni_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             // g + 1 opens the next unit, so the tensor core has the new unit's first scores ready while the softmax warps finish
             // the old one.  A cursor walks (unit, block); `cur` is the block whose QK is in flight, `nxt` the one after it.
             struct Cursor { int u; uint32_t u_it, rem; int k_lo; bool valid; };
+            TcUnitWalk walk(blockIdx.x, gridDim.x, tiles, a.H);          // always positioned on unit c.u of the cursor below
             auto load_unit = [&](Cursor& c) {           // position c on the first live block of unit c.u (skipping empty units)
                 for (;;) {
                     if (c.u >= n_units) { c.valid = false; return; }
-                    const TcUnit un = tc_unit(c.u, tiles, a.H);
+                    const TcUnit un = walk.get();
                     const showo_seq_mask_t msk = mask_of(un.seq);
                     const int q_lo = a.pos0 + un.q0;
                     c.k_lo = tc_key_begin(msk, q_lo);
@@ -373,7 +403,7 @@ omni_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                     mbar_wait_sleep(&q_full[c.u_it & 1], (c.u_it >> 1) & 1, sleep_ns);
                     if (c.rem != 0) { c.valid = true; return; }
                     mbar_arrive(&q_empty[c.u_it & 1]);   // nothing visible: the softmax warps write zeros
-                    c.u += gridDim.x; ++c.u_it;
+                    c.u += gridDim.x; ++c.u_it; walk.step();
                 }
             };
             uint32_t g = 0;
@@ -410,7 +440,7 @@ omni_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                     const bool g_last = cur.rem == 0;
                     if (g_last) {
                         umma_commit(&q_empty[cur.u_it & 1]);   // the unit's last QK is in flight: its Q buffer is free once it completes
-                        cur.u += gridDim.x; ++cur.u_it;
+                        cur.u += gridDim.x; ++cur.u_it; walk.step();
                         load_unit(cur);
                     }
                     const bool have_next = cur.valid;
@@ -484,8 +514,9 @@ omni_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             }
             if (half == 0 && pend.lse != nullptr) *pend.lse = l > 0.f ? pend.m * sc + log2f(l) : 1.0e30f;
         };
-        for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++u_it) {
-            const TcUnit un = tc_unit(u, tiles, a.H);
+        TcUnitWalk walk(blockIdx.x, gridDim.x, tiles, a.H);
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++u_it, walk.step()) {
+            const TcUnit un = walk.get();
             const showo_seq_mask_t msk = mask_of(un.seq);
             const int q_lo = a.pos0 + un.q0, q_hi = q_lo + 127;
             const int k_lo = tc_key_begin(msk, q_lo);

@@ -217,3 +217,26 @@ def test_clip_vision_tower_delegate_selects_penultimate_patch_features():
     assert all(not p.requires_grad for p in tower.parameters())
     fl = tower([x[0], x[1]])
     assert torch.allclose(torch.cat(fl), f, atol=1e-6)
+
+
+def test_train_inputs_host_side_contract():
+    """show-o_b200/train_inputs.py without a GPU: the schedule -> kernel code mapping, the refusal of what the device path does not
+    provide (python-`random` branches of the reference), and no CPU fallback for the producer itself."""
+    import torch
+    from showo_b200 import ShowoError, get_mask_chedule, train_inputs as TI
+
+    class Cfg(dict):
+        __getattr__ = dict.get
+    assert TI._schedule_code(get_mask_chedule("cosine")) == (0, 0.0)
+    assert TI._schedule_code(get_mask_chedule("linear")) == (1, 0.0)
+    assert TI._schedule_code(get_mask_chedule("pow2.5")) == (2, 2.5)
+    assert TI._schedule_code(get_mask_chedule("sigmoid"))[0] == 3 and TI._schedule_code(lambda t: t)[0] == 3
+    codes = torch.zeros(2, 16, dtype=torch.int64)
+    with pytest.raises(NotImplementedError):
+        TI.mask_or_random_replace_tokens(codes, 99, Cfg(training=Cfg(mask_contiguous_region_prob=0.3)), get_mask_chedule("cosine"))
+    with pytest.raises(NotImplementedError):
+        TI.mask_or_random_replace_tokens(codes, 99, Cfg(training=Cfg(predict_all_tokens=True)), get_mask_chedule("cosine"))
+    with pytest.raises(NotImplementedError):
+        TI.mask_or_random_replace_tokens(codes, 99, Cfg(training=Cfg(eval_mask_ratios=[0.5])), get_mask_chedule("cosine"), is_train=False)
+    with pytest.raises(ShowoError):                       # CPU tensors: the producer only exists on the device
+        TI.mask_or_random_replace_tokens(codes, 99, Cfg(training=Cfg()), get_mask_chedule("cosine"))
