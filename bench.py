@@ -49,9 +49,9 @@ def measured_peaks():
 
 
 def ncu_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/r1_traffic.json)."""
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full captures (profiles/r2_traffic.json)."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["gemm_tcgen05_kernel"]
+        t = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))["gemm_tcgen05_kernel"]
         return {k: {"dram_bytes": v["dram_bytes"], "algorithmic_bytes": v["algorithmic_bytes"]} for k, v in t.items()}
     except Exception:
         return None
