@@ -346,6 +346,12 @@ __device__ __forceinline__ float gelu_new_f(float x) {
     asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
     return 0.5f * x * (1.0f + t);
 }
+// d gelu_new(x) / dx
+__device__ __forceinline__ float gelu_new_grad(float x) {
+    const float c = 0.7978845608028654f, k = 0.044715f;
+    const float t = tanhf(c * (x + k * x * x * x));
+    return 0.5f * (1.f + t) + 0.5f * x * (1.f - t * t) * c * (1.f + 3.f * k * x * x);
+}
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);

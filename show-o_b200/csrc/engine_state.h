@@ -39,6 +39,9 @@ struct LayerW {
     float* b_dense = nullptr; float* b_fc2 = nullptr;
     float* ln_g = nullptr; float* ln_b = nullptr;
     float* qg = nullptr; float* qb = nullptr; float* kg = nullptr; float* kb = nullptr;
+    // input LayerNorm folded into the fused projection (engine.cu ln_fold_enabled, layers >= 1): w1f = bf16(W1 * gamma),
+    // ln_c[n] = sum_j w1f[n][j], ln_d[n] = b1[n] + sum_j beta[j] W1[n][j]
+    bf16* w1f = nullptr; float* ln_c = nullptr; float* ln_d = nullptr;
 };
 
 struct showo_engine {
@@ -59,6 +62,8 @@ struct showo_engine {
     int cap_rows = 0, cap_seq = 0, cap_L = 0; int64_t cap_logit_elems = 0;
     float* x = nullptr; bf16* xh = nullptr; bf16* buf = nullptr;
     bf16* w1_slab = nullptr; bf16* w2_slab = nullptr;    // all layers' W1 / W2 back to back (one tensor map each)
+    bf16* w1f_slab = nullptr; float* ln_cd = nullptr;    // LayerNorm-folded copies of W1 and their c / d vectors (LayerW::w1f)
+    float* ln_part = nullptr;                             // [cap_rows][D / 64][mean, M2]: slot statistics of the residual stream
     bf16* kcache = nullptr; bf16* vtcache = nullptr;     // [NL][cap_seq][H][cap_L][64] each
     showo_seq_mask_t* d_masks = nullptr;
     float* logits_ws = nullptr; float* conf_ws = nullptr; int* sampled_ws = nullptr;

@@ -191,6 +191,18 @@ static int gemm_bn(const GemmArgs& a, GemmEpi epi, cudaStream_t st) {
     GemmParams p{};
     p.M = a.M; p.N = a.N; p.K = a.K;
     p.out = a.out; p.ldc = a.ldc; p.bias = a.bias; p.resid = a.resid; p.ldr = a.ldr; p.gelu_from = a.gelu_from;
+    if (epi == GEMM_BIAS_BF16 && a.gelu_mode != 0) {
+        SHOWO_CHECK(a.gelu_out != nullptr && (a.gelu_mode == 1 || a.gelu_pre != nullptr) && a.gelu_from % 32 == 0 && a.N % 32 == 0 &&
+                    a.gelu_out_ld % 8 == 0 && a.gelu_pre_ld % 8 == 0 && a.ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(a.gelu_out) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.gelu_pre) & 15) == 0,
+                    "gemm: the split gelu epilogues need 32-column aligned regions and 16-byte aligned rows");
+        p.gelu_mode = a.gelu_mode; p.gelu_out = a.gelu_out; p.gelu_out_ld = a.gelu_out_ld; p.gelu_pre = a.gelu_pre; p.gelu_pre_ld = a.gelu_pre_ld;
+    }
+    if (epi == GEMM_RESID_F32 && a.ln_part != nullptr) {
+        SHOWO_CHECK(a.ln_xb != nullptr && a.N % 64 == 0 && (a.ln_xb_ld % 8) == 0 && (a.ldc * 4) % 16 == 0 && (a.ldr * 4) % 16 == 0,
+                    "gemm: the LayerNorm-statistics epilogue needs N % 64 == 0 and 16-byte aligned rows");
+        p.ln_xb = a.ln_xb; p.ln_xb_ld = a.ln_xb_ld; p.ln_part_out = a.ln_part;
+    }
     const int tiles = cdiv(cdiv(a.M, 128), CL) * cdiv(a.N, BN);
     if constexpr (CG == 2) {
         // stream-K for the residual GEMM when the tiles do not fill whole waves of clusters (dense|fc2: 136 tiles on 74 clusters)
@@ -246,6 +258,8 @@ static int gemm_qkv_bn(const GemmArgs& a, const QkvFuse& f, cudaStream_t st) {
     p.qkv_D = f.D; p.qkv_H = f.H; p.qkv_rows_per_seq = f.rows_per_seq; p.qkv_pos0 = f.pos0; p.qkv_Lmax = f.Lmax;
     p.q_gamma = f.q_gamma; p.q_beta = f.q_beta; p.k_gamma = f.k_gamma; p.k_beta = f.k_beta; p.qk_eps = f.eps;
     p.cos_tab = f.cos_tab; p.sin_tab = f.sin_tab; p.kcache = f.kcache; p.vtcache = f.vtcache;
+    p.ln_part_in = f.ln_part; p.ln_c = f.ln_c; p.ln_eps = f.ln_eps;
+    if (f.ln_part != nullptr) SHOWO_CHECK(f.ln_c != nullptr && a.K % 64 == 0, "gemm_qkv: folded LayerNorm needs c_n and K % 64 == 0");
     return launch<BN, EPI_QKV_BF16, A_PLAIN, BK, CL, CG>(ma, mb, p, cdiv(cdiv(a.M, 128), CL) * cdiv(a.N, BN), st);
 }
 

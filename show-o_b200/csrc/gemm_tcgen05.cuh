@@ -40,6 +40,7 @@ struct GemmParams {
     const void* resid;      // EPI_RESID_F32: f32 [M, ldr]; EPI_CONV_BF16: bf16 [M, ldr] or nullptr
     int64_t ldr;
     int gelu_from;          // EPI_BIAS_BF16: columns >= gelu_from get gelu_new; pass N for none
+    int gelu_mode; __nv_bfloat16* gelu_out; int64_t gelu_out_ld; const __nv_bfloat16* gelu_pre; int64_t gelu_pre_ld;   // kernels.h GemmArgs
     // conv mode
     int conv_H, conv_W;     // output spatial size (== input spatial size; stride-1, 'same' padding)
     int conv_TH, conv_TW;   // patch: TH*TW == 128
@@ -55,6 +56,9 @@ struct GemmParams {
     // range, so that 136 tiles on 74 clusters cost 1.84 tile times instead of 2.  A tile cut between two clusters: the cluster holding
     // its TAIL k blocks meets it FIRST in its range and parks the raw fp32 accumulators in sk_ws[unit][cta rank][col][row]; the
     // cluster holding its HEAD k blocks meets it LAST, adds the parked partial (fixed order: deterministic) and runs the epilogue.
+    // LayerNorm folding (kernels.h QkvFuse / GemmArgs): producer side (EPI_RESID_F32) and consumer side (EPI_QKV_BF16)
+    __nv_bfloat16* ln_xb; int64_t ln_xb_ld; float* ln_part_out;
+    const float* ln_part_in; const float* ln_c; float ln_eps;
     float* sk_ws;           // nullptr: classic tile loop
     int* sk_flags;          // [units][2] one flag per (tile, CTA rank), zero between launches
 };
@@ -297,6 +301,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 m = (int64_t)tm * BM + row_in_tile;
                 row_ok = m < p.M;
             }
+            // folded LayerNorm (EPI_QKV_BF16): this row's mean / rstd from the slot statistics the previous residual GEMM wrote
+            // ([slot][row], lanes contiguous), read while the tile's MMAs are still running; one pass, sums shifted by slot 0's mean
+            float ln_rstd = 1.f, ln_mrs = 0.f;
+            if constexpr (EPI == EPI_QKV_BF16) {
+                if (p.ln_part_in != nullptr && row_ok) {
+                    const int slots = p.K >> 6;
+                    const float2* ps = reinterpret_cast<const float2*>(p.ln_part_in) + m;
+                    const float k0 = __ldcg(ps).x;
+                    float s1 = 0.f, s2 = 0.f, sm = 0.f;
+#pragma unroll 8
+                    for (int t = 0; t < slots; ++t) {
+                        const float2 v = __ldcg(ps + (int64_t)t * p.M);
+                        const float dm = v.x - k0;
+                        s1 += dm; s2 = fmaf(dm, dm, s2); sm += v.y;
+                    }
+                    const float inv = 1.f / (float)slots;
+                    const float mu = k0 + s1 * inv;
+                    const float var = (sm + 64.f * (s2 - s1 * s1 * inv)) / (float)p.K;
+                    ln_rstd = rsqrtf(fmaxf(var, 0.f) + p.ln_eps);
+                    ln_mrs = mu * ln_rstd;
+                }
+            }
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr0 = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16);
@@ -357,6 +383,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     float f[64];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) { f[j] = __uint_as_float(v0[j]); f[32 + j] = __uint_as_float(v1[j]); }
+                    if (p.ln_part_in != nullptr) {        // y = rstd acc - (mu rstd) c_n   (+ d_n below, passed as the bias)
+#pragma unroll
+                        for (int j = 0; j < 64; j += 4) {
+                            const float4 c4 = __ldg(reinterpret_cast<const float4*>(p.ln_c + n0 + j));
+                            f[j] = f[j] * ln_rstd - ln_mrs * c4.x; f[j + 1] = f[j + 1] * ln_rstd - ln_mrs * c4.y;
+                            f[j + 2] = f[j + 2] * ln_rstd - ln_mrs * c4.z; f[j + 3] = f[j + 3] * ln_rstd - ln_mrs * c4.w;
+                        }
+                    }
 #pragma unroll
                     for (int j = 0; j < 64; j += 4) {
                         const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
@@ -414,6 +448,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     }
                 }
             } else {
+            float ln_mean_lo = 0.f, ln_m2_lo = 0.f;        // statistics of the first 32-column half of the current 64-column slot
 #pragma unroll 1
             for (int c = 0; c < BN; c += 32) {
                 uint32_t v[32];
@@ -446,11 +481,43 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     }
                 }
                 if constexpr (EPI == EPI_BIAS_BF16) {
-                    if (n0 >= p.gelu_from) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = gelu_new_f(f[j]);
-                    }
                     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.ldc + n0;
+                    if (n0 >= p.gelu_from) {
+                        if (p.gelu_mode == 0) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) f[j] = gelu_new_f(f[j]);
+                        } else if (full && out_vec_ok) {
+                            // training step (kernels.h GemmArgs::gelu_mode); both variants work on the bf16-rounded value, which is what
+                            // the stand-alone gelu_fwd / gelu_bwd passes they replace read back from memory
+                            __nv_bfloat16* go = p.gelu_out + m * p.gelu_out_ld + (n0 - p.gelu_from);
+                            float gv[32];
+                            if (p.gelu_mode == 1) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) gv[j] = gelu_new_f(__bfloat162float(__float2bfloat16(f[j])));
+                            } else {
+                                const __nv_bfloat16* gp = p.gelu_pre + m * p.gelu_pre_ld + (n0 - p.gelu_from);
+#pragma unroll
+                                for (int j = 0; j < 32; j += 8) {
+                                    const uint4 pr = *reinterpret_cast<const uint4*>(gp + j);
+                                    const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&pr);
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q) {
+                                        const float2 x = __bfloat1622float2(p2[q]);
+                                        gv[j + 2 * q] = __bfloat162float(__float2bfloat16(f[j + 2 * q])) * gelu_new_grad(x.x);
+                                        gv[j + 2 * q + 1] = __bfloat162float(__float2bfloat16(f[j + 2 * q + 1])) * gelu_new_grad(x.y);
+                                    }
+                                }
+                            }
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8) {
+                                uint4 pk;
+                                pk.x = pack_bf16(gv[j], gv[j + 1]); pk.y = pack_bf16(gv[j + 2], gv[j + 3]);
+                                pk.z = pack_bf16(gv[j + 4], gv[j + 5]); pk.w = pack_bf16(gv[j + 6], gv[j + 7]);
+                                *reinterpret_cast<uint4*>(go + j) = pk;
+                            }
+                            if (p.gelu_mode == 2) continue;            // the raw d act is not kept
+                        }
+                    }
                     if (full && out_vec_ok) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 8) {
@@ -502,8 +569,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
                             const float4 r4 = *reinterpret_cast<const float4*>(r + j);
-                            float4 o4 = make_float4(f[j] + r4.x, f[j + 1] + r4.y, f[j + 2] + r4.z, f[j + 3] + r4.w);
-                            *reinterpret_cast<float4*>(o + j) = o4;
+                            f[j] += r4.x; f[j + 1] += r4.y; f[j + 2] += r4.z; f[j + 3] += r4.w;
+                            *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                        }
+                        if (p.ln_part_out != nullptr) {
+                            // the next layer's LayerNorm is folded into its projection GEMM: it reads these rows raw, in bf16, and
+                            // needs their statistics -- (mean, M2) of every 64-column slot, two 32-column chunks merged (shifted sums)
+                            __nv_bfloat16* xb = p.ln_xb + m * p.ln_xb_ld + n0;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8) {
+                                uint4 pk;
+                                pk.x = pack_bf16(f[j], f[j + 1]); pk.y = pack_bf16(f[j + 2], f[j + 3]);
+                                pk.z = pack_bf16(f[j + 4], f[j + 5]); pk.w = pack_bf16(f[j + 6], f[j + 7]);
+                                *reinterpret_cast<uint4*>(xb + j) = pk;
+                            }
+                            const float kk = f[0];
+                            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) { const float dd = f[j] - kk; s1 += dd; s2 = fmaf(dd, dd, s2); }
+                            const float mean32 = kk + s1 * (1.f / 32.f), m2_32 = s2 - s1 * s1 * (1.f / 32.f);
+                            if ((c & 32) == 0) { ln_mean_lo = mean32; ln_m2_lo = m2_32; }
+                            else {
+                                const float dm = mean32 - ln_mean_lo;
+                                reinterpret_cast<float2*>(p.ln_part_out)[(int64_t)(n0 >> 6) * p.M + m] =
+                                    make_float2(0.5f * (mean32 + ln_mean_lo), ln_m2_lo + m2_32 + 16.f * dm * dm);
+                            }
                         }
                     } else {
                         for (int j = 0; j < 32; ++j)

@@ -292,6 +292,12 @@ static int gemm_skinny2(const GemmArgs& a, int epi, const QkvFuse* qf, int tiles
         SHOWO_CHECK(a.N % 128 == 0 && a.N <= 2048 && a.ldc == a.N, "gemm_skinny: fused LayerNorm needs a contiguous hidden size <= 2048");
         p.ln_out = a.ln_out; p.ln_gamma = a.ln_gamma; p.ln_beta = a.ln_beta; p.ln_eps = a.ln_eps;
     }
+    if (epi == SK_RESID_F32 && a.ln_part != nullptr) {
+        SHOWO_CHECK(a.ln_xb != nullptr && a.N % 64 == 0 && a.ln_xb_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(a.ln_xb) & 15) == 0,
+                    "gemm_skinny: the LayerNorm-statistics epilogue needs N % 64 == 0 and 16-byte aligned bf16 rows");
+        p.ln_xb = a.ln_xb; p.ln_xb_ld = a.ln_xb_ld; p.ln_part_out = a.ln_part;
+    }
+    if (epi == SK_QKV && qf && qf->ln_part != nullptr) SHOWO_CHECK(qf->ln_c != nullptr, "gemm_skinny: folded LayerNorm needs c_n");
     if (epi == SK_ARGMAX) SHOWO_CHECK(a.argmax_keys != nullptr, "gemm_skinny: argmax epilogue needs a key buffer");
     SHOWO_TRY(ensure_skinny_ws((size_t)sc.grid * 2 * 1024, (size_t)tiles + 1, st));
     p.partials = g_partials; p.tickets = g_tickets;
@@ -320,13 +326,16 @@ static int gemm_skinny2(const GemmArgs& a, int epi, const QkvFuse* qf, int tiles
     return 0;
 }
 
+bool skinny_ln_fold_ok(int K) { return skinny_variant() == 2 && K % kSk2ChunkK == 0; }
+
 int gemm_skinny(const GemmArgs& a, int epi, const QkvFuse* qf, cudaStream_t st) {
     SHOWO_CHECK(a.M >= 1 && a.M <= 16, "gemm_skinny: M must be in [1,16]");
     SHOWO_CHECK(a.K % 64 == 0 && a.lda % 8 == 0 && a.ldb % 8 == 0, "gemm_skinny: K must be a multiple of 64, lda/ldb of 8");
     const int tiles = cdiv(a.N, kSkTileN);
     if (skinny_variant() == 2 && a.K % kSk2ChunkK == 0)
         return gemm_skinny2(a, epi, qf, tiles, st);
-    SHOWO_CHECK(a.ln_out == nullptr, "gemm_skinny: the fused LayerNorm needs the TMA-streamed kernel (K % 128 == 0)");
+    SHOWO_CHECK(a.ln_out == nullptr && a.ln_part == nullptr && !(qf && qf->ln_part),
+                "gemm_skinny: the fused / folded LayerNorm needs the TMA-streamed kernel (K % 128 == 0)");
     // enough CTAs to cover the SMs a few times over, K per split a multiple of 64 and <= 2048 (X slab <= 64 KB of smem)
     int splits = 1;
     // at least one full wave of CTAs, X slab <= 64 KB of smem; fewer, longer-streaming CTAs beat many short ones

@@ -20,11 +20,19 @@ struct GemmArgs {
     const float* bias;
     const float* resid; int64_t ldr;  // GEMM_RESID_F32
     int gelu_from;                    // GEMM_BIAS_BF16: gelu_new on columns >= gelu_from (N = none)
+    // GEMM_BIAS_BF16, training step: gelu_mode 1 = columns >= gelu_from are written raw to out AND as gelu_new(bf16 value) to
+    // gelu_out[m, n - gelu_from] (the forward keeps the pre-activation for the backward); gelu_mode 2 = columns >= gelu_from are
+    // multiplied by gelu_new'(gelu_pre[m, n - gelu_from]) and written to gelu_out[m, n - gelu_from] instead of out (the dgrad GEMM of
+    // fc2 producing d fc1 directly)
+    int gelu_mode = 0; bf16* gelu_out = nullptr; int64_t gelu_out_ld = 0; const bf16* gelu_pre = nullptr; int64_t gelu_pre_ld = 0;
     int block_n;                      // 0 = auto, else 64 / 128 / 256
     // decode-path extras (gemm_skinny only): fused input LayerNorm of fp32 rows, greedy argmax epilogue
     unsigned long long* argmax_keys = nullptr;
     // decode path: bytes the NEXT kernel of the chain will stream (its weights), pulled into L2 while this kernel runs
     const void* l2_prefetch = nullptr; size_t l2_prefetch_bytes = 0;
+    // GEMM_RESID_F32 feeding a LayerNorm-folded GEMM (QkvFuse::ln_part): also write the new residual rows as bf16 to ln_xb and their
+    // per-row statistics over every 64-column slot to ln_part ([N / 64][M rows][mean, M2])
+    bf16* ln_xb = nullptr; int64_t ln_xb_ld = 0; float* ln_part = nullptr;
     // decode path, GEMM_RESID_F32 with M <= 16: the CTA finishing the last tile also writes LayerNorm(out rows) as bf16 to ln_out
     bf16* ln_out = nullptr; const float* ln_gamma = nullptr; const float* ln_beta = nullptr; float ln_eps = 0.f;
 };
@@ -37,9 +45,15 @@ struct QkvFuse {
     const float* q_gamma; const float* q_beta; const float* k_gamma; const float* k_beta; float eps;
     const float* cos_tab; const float* sin_tab;
     bf16* kcache; bf16* vtcache;
+    // LayerNorm folded into this GEMM (inference path, layers >= 1): A is the RAW residual stream in bf16, the weight rows are
+    // pre-multiplied by the LayerNorm gamma, and the epilogue applies   y = rstd (acc - mu c_n) + d_n   with the row statistics
+    // the previous layer's residual GEMM left in ln_part ([K / 64][M rows][mean, M2] over 64-column slots), c_n = sum_j W'[n][j],
+    // d_n = sum_j beta_j W[n][j] + bias_n (passed as the GEMM's bias).  nullptr: the classic LayerNorm'ed A operand.
+    const float* ln_part = nullptr; const float* ln_c = nullptr; float ln_eps = 0.f;
 };
 int gemm_qkv_bf16(const GemmArgs& a, const QkvFuse& f, cudaStream_t st);
 // weight-streaming path for M <= 16 rows (decode); epi: 0 bias->bf16(+gelu), 1 resid+bias->f32, 2 bias->f32, 3 fused qkv (gemv.cu)
+bool skinny_ln_fold_ok(int K);        // the skinny GEMM in use can run the folded-LayerNorm epilogues for this K
 int gemm_skinny(const GemmArgs& a, int epi, const QkvFuse* qf, cudaStream_t st);
 // stream-K fix-up workspace shared by the streamed skinny GEMM and the decode megakernel: partial tiles [grid][2][16x64]
 // fp32 and self-resetting per-tile tickets

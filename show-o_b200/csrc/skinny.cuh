@@ -18,6 +18,8 @@ struct SkinnyParams {
     // SK_RESID_F32 (the layer's second GEMM, x += ...): the CTA that finishes the LAST feature tile also runs the next LayerNorm over
     // the M rows (phi.py:776 / :1065) and writes its bf16 output -- the stand-alone 16-row LayerNorm launch cost 6 us per layer
     bf16* ln_out; const float* ln_gamma; const float* ln_beta; float ln_eps; int* ln_ctr;
+    // SK_RESID_F32 feeding a LayerNorm-folded projection (kernels.h GemmArgs::ln_part): raw bf16 copy of the new rows + slot statistics
+    bf16* ln_xb; int64_t ln_xb_ld; float* ln_part_out;
 };
 
 __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -39,11 +41,36 @@ template <int EPI>
 __device__ __forceinline__ void skinny_epilogue(const SkinnyParams& p, float (&f)[8], int n0, int tid) {
     const int r = tid >> 3, cq = (tid & 7) * 8;
     const int n = n0 + cq;
+    const bool row_ok = r < p.M;
+    if constexpr (EPI == SK_QKV) {
+        if (p.qf.ln_part != nullptr) {
+            // LayerNorm folded into this GEMM (kernels.h QkvFuse): the row's statistics from the 64-column slots the previous
+            // residual GEMM wrote, the row's 8 lanes taking every 8th slot;   y = rstd acc - (mu rstd) c_n   (+ d_n as the bias)
+            const int slots = p.K >> 6, l8 = tid & 7;
+            const float2* ps = reinterpret_cast<const float2*>(p.qf.ln_part) + r;          // [slot][M]
+            const float k0 = row_ok ? __ldcg(ps).x : 0.f;
+            float s1 = 0.f, s2 = 0.f, sm = 0.f;
+            if (row_ok)
+                for (int t = l8; t < slots; t += 8) {
+                    const float2 v = __ldcg(ps + (int64_t)t * p.M);
+                    const float dm = v.x - k0;
+                    s1 += dm; s2 = fmaf(dm, dm, s2); sm += v.y;
+                }
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+                s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); sm += __shfl_xor_sync(0xffffffffu, sm, o);
+            }
+            const float inv = 1.f / (float)slots;
+            const float mu = k0 + s1 * inv;
+            const float rstd = rsqrtf(fmaxf((sm + 64.f * (s2 - s1 * s1 * inv)) / (float)p.K, 0.f) + p.qf.ln_eps), mrs = mu * rstd;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) if (n + j < p.N) f[j] = f[j] * rstd - mrs * __ldg(p.qf.ln_c + n + j);
+        }
+    }
     if (p.bias) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) if (n + j < p.N) f[j] += __ldg(p.bias + n + j);
     }
-    const bool row_ok = r < p.M;
     if constexpr (EPI == SK_QKV) {
         const QkvFuse& q = p.qf;
         const int region = n0 / q.D;                       // 64-feature tile == one head of k / v / q, or 64 fc1 columns
@@ -124,6 +151,30 @@ __device__ __forceinline__ void skinny_epilogue(const SkinnyParams& p, float (&f
             }
             return;
         }
+        if constexpr (EPI == SK_RESID_F32) {
+            if (p.ln_part_out != nullptr) {
+                // the next layer's LayerNorm is folded into its projection: leave bf16(new residual row) and the (mean, M2) of this
+                // 64-column slot (the row's 8 lanes hold it; N % 64 == 0 is checked by the host)
+                float xs[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) xs[j] = row_ok ? f[j] + p.resid[(int64_t)r * p.ldr + n + j] : 0.f;
+                float s = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s += xs[j];
+                s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4);
+                const float mean = s * (1.f / 64.f);
+                float v = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { const float dd = xs[j] - mean; v = fmaf(dd, dd, v); }
+                v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 4);
+                if (row_ok) {
+                    uint4 pk;
+                    pk.x = pack_bf16(xs[0], xs[1]); pk.y = pack_bf16(xs[2], xs[3]); pk.z = pack_bf16(xs[4], xs[5]); pk.w = pack_bf16(xs[6], xs[7]);
+                    *reinterpret_cast<uint4*>(p.ln_xb + (int64_t)r * p.ln_xb_ld + n) = pk;
+                    if ((tid & 7) == 0) reinterpret_cast<float2*>(p.ln_part_out)[(int64_t)(n0 >> 6) * p.M + r] = make_float2(mean, v);
+                }
+            }
+        }
         if (!row_ok) return;
         if constexpr (EPI == SK_BIAS_BF16) {
             bf16* o = reinterpret_cast<bf16*>(p.out) + (int64_t)r * p.ldc + n;
@@ -134,7 +185,7 @@ __device__ __forceinline__ void skinny_epilogue(const SkinnyParams& p, float (&f
             float* o = reinterpret_cast<float*>(p.out) + (int64_t)r * p.ldc + n;
             const float* rs = p.resid + (int64_t)r * p.ldr + n;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) if (n + j < p.N) o[j] = f[j] + rs[j];
+            for (int j = 0; j < 8; ++j) if (n + j < p.N) { f[j] += rs[j]; o[j] = f[j]; }
         } else {
             float* o = reinterpret_cast<float*>(p.out) + (int64_t)r * p.ldc + n;
 #pragma unroll

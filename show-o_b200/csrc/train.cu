@@ -99,6 +99,53 @@ __global__ void __launch_bounds__(256) ln_bwd_dx_kernel(const float* __restrict_
         }
 }
 
+// the same, one CTA of 256 threads per row (D <= 4096): a few registers per thread instead of a whole row per warp, so 8 CTAs / 64
+// warps are resident per SM and the load, reduce and store phases of different rows overlap (the warp-per-row version at D = 2048 holds
+// 149 registers, one 8-warp CTA per SM: 154 us per call for 303 MB of traffic)
+__global__ void __launch_bounds__(256) ln_bwd_dx_row_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                            const float2* __restrict__ stats, const float* __restrict__ gamma,
+                                                            float* __restrict__ dx_io, int accumulate, int D) {
+    __shared__ float rs[2][8];
+    const int row = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)row * D);
+    const float4* dr = reinterpret_cast<const float4*>(dy + (int64_t)row * D);
+    const float4* g4 = reinterpret_cast<const float4*>(gamma);
+    float4* orow = reinterpret_cast<float4*>(dx_io + (int64_t)row * D);
+    const float2 st = stats[row];
+    const int nvec = D >> 2;                  // float4 per row, <= 4 per thread
+    float4 xh[4], gd[4], prev[4];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int v = tid + i * 256;
+        if (v < nvec) {
+            const float4 xv = xr[v], dv = dr[v], g = __ldg(g4 + v);
+            if (accumulate) prev[i] = orow[v];
+            xh[i] = make_float4((xv.x - st.x) * st.y, (xv.y - st.x) * st.y, (xv.z - st.x) * st.y, (xv.w - st.x) * st.y);
+            gd[i] = make_float4(dv.x * g.x, dv.y * g.y, dv.z * g.z, dv.w * g.w);
+            s1 += (gd[i].x + gd[i].y) + (gd[i].z + gd[i].w);
+            s2 += (gd[i].x * xh[i].x + gd[i].y * xh[i].y) + (gd[i].z * xh[i].z + gd[i].w * xh[i].w);
+        }
+    }
+    s1 = warp_sum(s1); s2 = warp_sum(s2);
+    if (lane == 0) { rs[0][warp] = s1; rs[1][warp] = s2; }
+    __syncthreads();
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { m1 += rs[0][w]; m2 += rs[1][w]; }
+    m1 /= (float)D; m2 /= (float)D;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int v = tid + i * 256;
+        if (v < nvec) {
+            float4 o = make_float4(st.y * (gd[i].x - m1 - xh[i].x * m2), st.y * (gd[i].y - m1 - xh[i].y * m2),
+                                   st.y * (gd[i].z - m1 - xh[i].z * m2), st.y * (gd[i].w - m1 - xh[i].w * m2));
+            if (accumulate) { o.x += prev[i].x; o.y += prev[i].y; o.z += prev[i].z; o.w += prev[i].w; }
+            orow[v] = o;
+        }
+    }
+}
+
 // partial[blockIdx.y][0][c] = sum_r dy[r,c] * xhat[r,c], partial[blockIdx.y][1][c] = sum_r dy[r,c] over this block's rows
 __global__ void __launch_bounds__(256) ln_bwd_param_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                            const float2* __restrict__ stats, int n_rows, int D,
@@ -205,103 +252,120 @@ __global__ void __launch_bounds__(256) qk_rope_train_kernel(QkTrainArgs a) {
     }
 }
 
-// backward of rotary (transpose of the rotation) and of LayerNorm(64); one warp per (row, head), the block walks all heads
+// backward of rotary (transpose of the rotation) and of LayerNorm(64).  Eight lanes per (position, head) -- lane l8 holds dims
+// 8 l8 .. 8 l8 + 7 as one 16-byte vector -- so a warp covers four heads of a position per step, the 64-wide reductions are three
+// shuffles, and the four 16-byte loads of a step are issued together (the first version, one warp per (position, head) with 4-byte
+// loads behind five-shuffle reductions, was a latency chain: 307 us per layer at 8 x 1155 rows for 227 MB of traffic).
+constexpr int kQkBwdPos = 16;            // positions per CTA (two per warp)
 __global__ void __launch_bounds__(256) qk_rope_bwd_kernel(QkTrainArgs a) {
-    __shared__ float red[8][8][32];
-    // 8 positions per CTA, one per warp (a warp walks the heads of its position): 4x the CTAs of a 32-position block -- the kernel is a
-    // chain of warp reductions per (position, head), so it is resident warps that hide the shuffle latency (307 -> see profiles)
-    const int blocks_per_seq = (a.L + 7) >> 3;
+    __shared__ float red[8][256];
+    const int blocks_per_seq = (a.L + kQkBwdPos - 1) / kQkBwdPos;
     const int seq = blockIdx.x / blocks_per_seq, rb = blockIdx.x % blocks_per_seq;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, l8 = lane & 7, hs = lane >> 3;
     const int D = a.D;
-    const float2 qg = reinterpret_cast<const float2*>(a.qg)[lane], kg = reinterpret_cast<const float2*>(a.kg)[lane];
-    float acc[8];
+    const bf16* __restrict__ pre = a.pre; const bf16* __restrict__ dqp = a.dq; const bf16* __restrict__ dkp = a.dk;
+    bf16* __restrict__ dpre = a.dpre;
+    float gq[8], gk[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    for (int h = 0; h < a.H; ++h) {
-        {
-            const int pos = rb * 8 + warp;
-            if (pos >= a.L) continue;
-            const int64_t m = (int64_t)seq * a.L + pos;
-            float2 c = make_float2(1.f, 1.f), s = make_float2(0.f, 0.f);
-            if (lane < 16) {
-                c = reinterpret_cast<const float2*>(a.cos_tab + (int64_t)pos * 32)[lane];
-                s = reinterpret_cast<const float2*>(a.sin_tab + (int64_t)pos * 32)[lane];
+    for (int j = 0; j < 8; ++j) { gq[j] = __ldg(a.qg + 8 * l8 + j); gk[j] = __ldg(a.kg + 8 * l8 + j); }
+    float acc[4][8];                     // q gamma, q beta, k gamma, k beta of this lane's 8 dims
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+    auto sum8 = [](float v) {
+        v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 4);
+        return v;
+    };
+    for (int pp = 0; pp < kQkBwdPos / 8; ++pp) {
+        const int pos = rb * kQkBwdPos + warp * (kQkBwdPos / 8) + pp;
+        if (pos >= a.L) break;           // warp-uniform
+        const int64_t m = (int64_t)seq * a.L + pos;
+        // rotary dims [0, 32) = lanes l8 < 4; the partner of dim i is i ^ 16 = lane l8 ^ 2; cos / sin tables hold cat(freqs, freqs)
+        float cs[8], sn[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { cs[j] = 1.f; sn[j] = 0.f; }
+        if (l8 < 4) {
+#pragma unroll
+            for (int j = 0; j < 8; j += 4) {
+                const float4 c4 = __ldg(reinterpret_cast<const float4*>(a.cos_tab + (int64_t)pos * 32 + 8 * l8 + j));
+                const float4 s4 = __ldg(reinterpret_cast<const float4*>(a.sin_tab + (int64_t)pos * 32 + 8 * l8 + j));
+                cs[j] = c4.x; cs[j + 1] = c4.y; cs[j + 2] = c4.z; cs[j + 3] = c4.w;
+                sn[j] = s4.x; sn[j + 1] = s4.y; sn[j + 2] = s4.z; sn[j + 3] = s4.w;
             }
-            const float sgn = lane < 8 ? 1.f : -1.f;          // transpose of the forward rotation
+        }
+        const float sgn = l8 < 2 ? 1.f : -1.f;               // transpose of the forward rotation
+#pragma unroll 2
+        for (int hb = 0; hb < a.H; hb += 4) {
+            const bool hv = hb + hs < a.H;                    // H % 4 != 0: the spare head slots run on head H - 1 and drop the result
+            const int h = hv ? hb + hs : a.H - 1;
+            const int64_t oq = m * a.ld + 2 * D + h * 64 + 8 * l8, ok = m * a.ld + h * 64 + 8 * l8;
+            uint4 u[4];
+            u[0] = *reinterpret_cast<const uint4*>(dqp + m * D + h * 64 + 8 * l8);
+            u[1] = *reinterpret_cast<const uint4*>(pre + oq);
+            u[2] = *reinterpret_cast<const uint4*>(dkp + m * D + h * 64 + 8 * l8);
+            u[3] = *reinterpret_cast<const uint4*>(pre + ok);
 #pragma unroll
             for (int t = 0; t < 2; ++t) {                     // t = 0: q, t = 1: k
-                const bf16* gsrc = (t == 0 ? a.dq : a.dk) + m * D + h * 64;
-                const bf16* raw = a.pre + m * a.ld + (t == 0 ? 2 * D : 0) + h * 64;
-                float2 dz = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(gsrc)[lane]);
-                const float px = __shfl_xor_sync(0xffffffffu, dz.x, 8), py = __shfl_xor_sync(0xffffffffu, dz.y, 8);
-                if (lane < 16) { dz.x = dz.x * c.x + sgn * px * s.x; dz.y = dz.y * c.y + sgn * py * s.y; }
-                float2 xr = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(raw)[lane]);
-                const float mu = warp_sum(xr.x + xr.y) * (1.f / 64.f);
-                xr.x -= mu; xr.y -= mu;
-                const float rstd = rsqrtf(warp_sum(xr.x * xr.x + xr.y * xr.y) * (1.f / 64.f) + a.eps);
-                const float2 xh = make_float2(xr.x * rstd, xr.y * rstd);
-                acc[4 * t + 0] += dz.x * xh.x; acc[4 * t + 1] += dz.y * xh.y;      // d gamma (dims 2l, 2l+1)
-                acc[4 * t + 2] += dz.x; acc[4 * t + 3] += dz.y;                    // d beta
-                const float2 gm = t == 0 ? qg : kg;
-                const float2 gd = make_float2(dz.x * gm.x, dz.y * gm.y);
-                const float m1 = warp_sum(gd.x + gd.y) * (1.f / 64.f);
-                const float m2 = warp_sum(gd.x * xh.x + gd.y * xh.y) * (1.f / 64.f);
-                const float ox = rstd * (gd.x - m1 - xh.x * m2), oy = rstd * (gd.y - m1 - xh.y * m2);
-                reinterpret_cast<__nv_bfloat162*>(a.dpre + m * a.ld + (t == 0 ? 2 * D : 0) + h * 64)[lane] = __floats2bfloat162_rn(ox, oy);
+                float dz[8], xr[8];
+                const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(&u[2 * t]);
+                const __nv_bfloat162* x2 = reinterpret_cast<const __nv_bfloat162*>(&u[2 * t + 1]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 gv = __bfloat1622float2(g2[j]), xv = __bfloat1622float2(x2[j]);
+                    dz[2 * j] = gv.x; dz[2 * j + 1] = gv.y; xr[2 * j] = xv.x; xr[2 * j + 1] = xv.y;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float pr = __shfl_xor_sync(0xffffffffu, dz[j], 2);
+                    dz[j] = dz[j] * cs[j] + sgn * pr * sn[j];          // lanes l8 >= 4: c = 1, s = 0
+                }
+                float sx = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) sx += xr[j];
+                const float mu = sum8(sx) * (1.f / 64.f);
+                float sv = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { xr[j] -= mu; sv = fmaf(xr[j], xr[j], sv); }
+                const float rstd = rsqrtf(sum8(sv) * (1.f / 64.f) + a.eps);
+                float s1 = 0.f, s2 = 0.f, gd[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    xr[j] *= rstd;                                       // xhat
+                    if (hv) {
+                        acc[2 * t][j] = fmaf(dz[j], xr[j], acc[2 * t][j]);   // d gamma
+                        acc[2 * t + 1][j] += dz[j];                          // d beta
+                    }
+                    gd[j] = dz[j] * (t == 0 ? gq[j] : gk[j]);
+                    s1 += gd[j]; s2 = fmaf(gd[j], xr[j], s2);
+                }
+                const float m1 = sum8(s1) * (1.f / 64.f), m2 = sum8(s2) * (1.f / 64.f);
+                uint4 o;
+                o.x = pack_bf16(rstd * (gd[0] - m1 - xr[0] * m2), rstd * (gd[1] - m1 - xr[1] * m2));
+                o.y = pack_bf16(rstd * (gd[2] - m1 - xr[2] * m2), rstd * (gd[3] - m1 - xr[3] * m2));
+                o.z = pack_bf16(rstd * (gd[4] - m1 - xr[4] * m2), rstd * (gd[5] - m1 - xr[5] * m2));
+                o.w = pack_bf16(rstd * (gd[6] - m1 - xr[6] * m2), rstd * (gd[7] - m1 - xr[7] * m2));
+                if (hv) *reinterpret_cast<uint4*>(dpre + (t == 0 ? oq : ok)) = o;
             }
         }
     }
+    // partial[block][tensor][dim], tensors q gamma, q beta, k gamma, k beta: the four head slots of a warp, then the eight warps
 #pragma unroll
-    for (int j = 0; j < 8; ++j) red[warp][j][lane] = acc[j];
+    for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float v = acc[t][j];
+            v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if (hs == 0) red[warp][t * 64 + 8 * l8 + j] = v;
+        }
     __syncthreads();
-    // partial[block][tensor][dim]: tensors q gamma, q beta, k gamma, k beta; dim 2l / 2l+1 from accumulators (0,1) / (2,3)
-    const int t = threadIdx.x;                 // 256 threads = 4 tensors x 64 dims
-    const int tensor = t >> 6, dim = t & 63, ln = dim >> 1, odd = dim & 1;
-    const int j = (tensor >> 1) * 4 + (tensor & 1) * 2 + odd;
     float v = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) v += red[w][j][ln];
-    a.partial[(int64_t)blockIdx.x * 256 + t] = v;
+    for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+    a.partial[(int64_t)blockIdx.x * 256 + threadIdx.x] = v;
 }
 
-// ------------------------------------------------------------------------------------------------ gelu_new forward / backward
-__global__ void __launch_bounds__(256) gelu_fwd_kernel(const bf16* __restrict__ src, int64_t ld_s, bf16* __restrict__ dst, int64_t ld_d,
-                                                       int64_t rows, int cols) {
-    const int cv = cols >> 3;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows * cv; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i / cv; const int c = (int)(i % cv) * 8;
-        const uint4 u = *reinterpret_cast<const uint4*>(src + r * ld_s + c);
-        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-        uint4 o; uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(h2[j]); ow[j] = pack_bf16(gelu_new_f(f.x), gelu_new_f(f.y)); }
-        *reinterpret_cast<uint4*>(dst + r * ld_d + c) = o;
-    }
-}
-__device__ __forceinline__ float gelu_new_grad(float x) {
-    const float c = 0.7978845608028654f, k = 0.044715f;
-    const float t = tanhf(c * (x + k * x * x * x));
-    return 0.5f * (1.f + t) + 0.5f * x * (1.f - t * t) * c * (1.f + 3.f * k * x * x);
-}
-__global__ void __launch_bounds__(256) gelu_bwd_kernel(const bf16* __restrict__ dact, int64_t ld_a, const bf16* __restrict__ pre, int64_t ld_p,
-                                                       bf16* __restrict__ dst, int64_t ld_d, int64_t rows, int cols) {
-    const int cv = cols >> 3;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows * cv; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i / cv; const int c = (int)(i % cv) * 8;
-        const uint4 ua = *reinterpret_cast<const uint4*>(dact + r * ld_a + c);
-        const uint4 up = *reinterpret_cast<const uint4*>(pre + r * ld_p + c);
-        const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&ua);
-        const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&up);
-        uint4 o; uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float2 g = __bfloat1622float2(a2[j]), x = __bfloat1622float2(p2[j]);
-            ow[j] = pack_bf16(g.x * gelu_new_grad(x.x), g.y * gelu_new_grad(x.y));
-        }
-        *reinterpret_cast<uint4*>(dst + r * ld_d + c) = o;
-    }
-}
+// (gelu_new forward / backward live in the tcgen05 GEMM's epilogue: kernels.h GemmArgs::gelu_mode)
 // dst[r, c] = src[r, c] for a column block (bf16, 16-byte vectors)
 __global__ void __launch_bounds__(256) copy_cols_bf16_kernel(const bf16* __restrict__ src, int64_t ld_s, bf16* __restrict__ dst, int64_t ld_d,
                                                              int64_t rows, int cols) {
@@ -485,10 +549,6 @@ static GradLayout grad_layout(const showo_engine* e) {
     return g;
 }
 
-static int launch_grid(int64_t work_items, int threads) {
-    const int64_t b = (work_items + threads - 1) / threads;
-    return (int)(b < 148 * 16 ? (b < 1 ? 1 : b) : 148 * 16);
-}
 static int layernorm_train(const float* x, const float* g, const float* b, float eps, bf16* out, float2* stats, int rows, int D, cudaStream_t st) {
     const int grid = cdiv(rows, 8);
     if (D <= 512) layernorm_train_kernel<4><<<grid, 256, 0, st>>>(x, g, b, eps, out, stats, rows, D);
@@ -517,6 +577,7 @@ static int layernorm_backward(TrainState* t, const float* dy, const float* x, co
     SHOWO_CUDA_OK(cudaMemcpyAsync(gb, t->partials + (size_t)S * 2 * D + D, (size_t)D * 4, cudaMemcpyDeviceToDevice, st));
     const int grid = cdiv(rows, 8);
     if (D <= 512) ln_bwd_dx_kernel<4><<<grid, 256, 0, st>>>(dy, x, stats, gamma, dx_io, accumulate ? 1 : 0, rows, D);
+    else if (D <= 4096 && D % 4 == 0) ln_bwd_dx_row_kernel<<<rows, 256, 0, st>>>(dy, x, stats, gamma, dx_io, accumulate ? 1 : 0, D);
     else ln_bwd_dx_kernel<16><<<grid, 256, 0, st>>>(dy, x, stats, gamma, dx_io, accumulate ? 1 : 0, rows, D);
     note_launch(3);
     SHOWO_CUDA_OK(cudaGetLastError());
@@ -729,15 +790,16 @@ int showo_train_forward(showo_engine_t* e, const int64_t* ids_dev, const float* 
         SHOWO_TRY(layernorm_train(x, w.ln_g, w.ln_b, e->cfg.ln_eps, xh, t->stats + (size_t)l * M, M, D, st));
         GemmArgs g1{};
         g1.A = xh; g1.lda = D; g1.B = w.w1; g1.ldb = D; g1.M = M; g1.N = W1N; g1.K = D; g1.out = pre; g1.ldc = W1N; g1.bias = w.b1;
-        g1.gelu_from = W1N; if (M <= 16) g1.block_n = 64;
+        // the fc1 columns are kept raw (the backward's gelu' reads them) and written as gelu_new(.) into the second GEMM's operand
+        g1.gelu_from = 3 * (int)D; g1.gelu_mode = 1; g1.gelu_out = a2 + D; g1.gelu_out_ld = W2K;
+        if (M <= 16) g1.block_n = 64;
         SHOWO_TRY(gemm_bf16(g1, GEMM_BIAS_BF16, st));
         QkTrainArgs q{};
         q.pre = pre; q.ld = W1N; q.n_seq = B; q.L = L; q.H = H; q.D = D; q.qg = w.qg; q.qb = w.qb; q.kg = w.kg; q.kb = w.kb;
         q.eps = e->cfg.ln_eps; q.cos_tab = e->cos_tab; q.sin_tab = e->sin_tab;
         q.qrot = t->qrot + (size_t)l * mD; q.krot = t->krot + (size_t)l * mD; q.kcache = e->kcache; q.vtcache = e->vtcache; q.Lmax = e->cap_L;
         qk_rope_train_kernel<<<dim3(B * cdiv(L, 32), H), 256, 0, st>>>(q);
-        gelu_fwd_kernel<<<launch_grid((int64_t)M * (e->F / 8), 256), 256, 0, st>>>(pre + 3 * D, W1N, a2 + D, W2K, M, e->F);
-        note_launch(2);
+        note_launch(1);
         SHOWO_CUDA_OK(cudaGetLastError());
         AttnArgs a{};
         a.q = t->qrot + (size_t)l * mD; a.ld = D; a.n_seq = B; a.H = H; a.rows_per_seq = L; a.pos0 = 0;
@@ -780,7 +842,7 @@ int showo_train_forward(showo_engine_t* e, const int64_t* ids_dev, const float* 
 // phase -1: loss -> dlogits -> head + final LayerNorm;  phase l in [0, NL): decoder layer l (in DEcreasing order);  phase -2: embedding
 static int backward_phase(showo_engine_t* e, int phase, const float* loss_grads_dev, float* dembeds_out_dev, cudaStream_t st) {
     TrainState* t = e->train;
-    const int M = t->M, B = t->B, L = t->L, D = e->D, H = e->H, W1N = e->W1N, W2K = e->W2K, V = e->V, NL = e->NL, F = e->F;
+    const int M = t->M, B = t->B, L = t->L, D = e->D, H = e->H, W1N = e->W1N, W2K = e->W2K, V = e->V, NL = e->NL;
     const int64_t Mp = (int64_t)(M + 127) / 128 * 128, Vp = t->Vp;
     const size_t mD = (size_t)M * D;
     const GradLayout gl = grad_layout(e);
@@ -818,8 +880,14 @@ static int backward_phase(showo_engine_t* e, int phase, const float* loss_grads_
         // d W2 = dx^T * [attn | act]
         SHOWO_TRY(transpose_to_bf16<bf16>(a2, W2K, M, W2K, t->tB, Mp, nullptr, 0, st));
         SHOWO_TRY(gemm_plain(t->tA, Mp, t->tB, Mp, D, W2K, (int)Mp, GL + gl.w2, W2K, true, st));
-        // d [attn | act] = dx * W2
-        SHOWO_TRY(gemm_plain(t->dxb, D, t->w2t + (size_t)l * W2K * D, D, M, W2K, D, t->dA2, W2K, false, st));
+        // d [attn | act] = dx * W2; the act columns leave the epilogue as d fc1 = d act * gelu_new'(fc1) in dpre[:, 3D:]
+        {
+            GemmArgs g{};
+            g.A = t->dxb; g.lda = D; g.B = t->w2t + (size_t)l * W2K * D; g.ldb = D; g.M = M; g.N = (int)W2K; g.K = D; g.out = t->dA2; g.ldc = W2K;
+            g.gelu_from = D; g.gelu_mode = 2; g.gelu_out = t->dpre + 3 * D; g.gelu_out_ld = W1N; g.gelu_pre = pre + 3 * D; g.gelu_pre_ld = W1N;
+            if (M <= 16) g.block_n = 64;
+            SHOWO_TRY(gemm_bf16(g, GEMM_BIAS_BF16, st));
+        }
         // attention backward: d q_rot, d k_rot -> dqk, d v -> dpre[:, D:2D]
         AttnBwdArgs ab{};
         ab.q = t->qrot + (size_t)l * mD; ab.q_ld = D; ab.k = t->krot + (size_t)l * mD; ab.k_ld = D; ab.v = pre + D; ab.v_ld = W1N;
@@ -831,13 +899,12 @@ static int backward_phase(showo_engine_t* e, int phase, const float* loss_grads_
         QkTrainArgs q{};
         q.pre = pre; q.ld = W1N; q.n_seq = B; q.L = L; q.H = H; q.D = D; q.qg = w.qg; q.qb = w.qb; q.kg = w.kg; q.kb = w.kb;
         q.eps = e->cfg.ln_eps; q.cos_tab = e->cos_tab; q.sin_tab = e->sin_tab; q.dq = t->dqk; q.dk = t->dqk + mD; q.dpre = t->dpre;
-        const int nblk = B * cdiv(L, 8);
+        const int nblk = B * cdiv(L, kQkBwdPos);
         SHOWO_TRY(ensure_partials(t, (size_t)nblk * 256 + 256));
         q.partial = t->partials;
         qk_rope_bwd_kernel<<<nblk, 256, 0, st>>>(q);
         reduce_partials_kernel<<<cdiv(256, 32), 256, 0, st>>>(t->partials, nblk, 256, GL + gl.qg);      // qg | qb | kg | kb are adjacent
-        gelu_bwd_kernel<<<launch_grid((int64_t)M * (F / 8), 256), 256, 0, st>>>(t->dA2 + D, W2K, pre + 3 * D, W1N, t->dpre + 3 * D, W1N, M, F);
-        note_launch(3);
+        note_launch(2);
         SHOWO_CUDA_OK(cudaGetLastError());
         // d W1 = dpre^T * xh, d b1 = column sums of dpre
         SHOWO_TRY(transpose_to_bf16<bf16>(t->dpre, W1N, M, W1N, t->tA, Mp, nullptr, 0, st));

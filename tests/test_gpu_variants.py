@@ -27,6 +27,8 @@ VARIANTS = {
     "decode_attention_per_thread": ({"SHOWO_DECODE_ATTN": "1"}, DECODE_K),
     "decode_ln_fused": ({"SHOWO_DECODE_LN_FUSED": "1"}, DECODE_K),
     "decode_l2_prefetch": ({"SHOWO_L2_PREFETCH": "1"}, DECODE_K),
+    "ln_fold_off": ({"SHOWO_LN_FOLD": "0"}, DECODE_K),
+    "ln_fold_all_paths": ({"SHOWO_LN_FOLD": "2"}, GEMM_K + " or forward_masks or t2i or " + DECODE_K),
     "no_pdl": ({"SHOWO_PDL": "0"}, "forward_tiny or mmu_generate_batched or teacher_forced"),
 }
 
