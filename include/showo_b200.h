@@ -231,7 +231,9 @@ SHOWO_API int64_t magvit_kernel_launches(magvit_engine_t* m);
 
 /* ---------------------------------------------------------------- raw kernels, exported for the parity tests */
 /* C[M,N] (+epilogue) = A[M,K] bf16 * B[N,K]^T bf16 on tcgen05; epi 0: bf16 out = acc+bias (gelu_new on cols >=
- * gelu_from), 1: f32 out = resid + acc + bias, 2: f32 out = acc + bias.  block_n 0 = auto. */
+ * gelu_from), 1: f32 out = resid + acc + bias, 2: f32 out = acc + bias.  block_n 0 = auto.
+ * epi 3: the weight-gradient form C[M,N] f32 = A^T B (+ bias[n]) with A = [K, lda >= M] and B = [K, ldb >= N] row-major (the
+ * contraction index is the row of both; MN-major tcgen05 operands, no transposed copies). */
 SHOWO_API int showo_gemm_bf16(const void* A_dev, int64_t lda, const void* B_dev, int64_t ldb, int M, int N, int K, void* out_dev,
                     int64_t ldc, const float* bias_dev, const float* resid_dev, int64_t ldr, int gelu_from, int epi,
                     int block_n, void* stream);

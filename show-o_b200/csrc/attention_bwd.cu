@@ -76,7 +76,7 @@ __device__ __forceinline__ void mma_tile_kn(float (&acc)[8][4], const uint32_t (
 }
 
 // ------------------------------------------------------------------------------------------------ dK, dV
-__global__ void __launch_bounds__(128) attn_bwd_dkdv_kernel(AttnBwdArgs a) {
+__global__ void __launch_bounds__(128, 3) attn_bwd_dkdv_kernel(AttnBwdArgs a) {
     __shared__ __align__(16) bf16 Qs[2][64][kPad];
     __shared__ __align__(16) bf16 Ds[2][64][kPad];
     __shared__ float Ls[2][64], Es[2][64];
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dkdv_kernel(AttnBwdArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------ dQ
-__global__ void __launch_bounds__(128) attn_bwd_dq_kernel(AttnBwdArgs a) {
+__global__ void __launch_bounds__(128, 3) attn_bwd_dq_kernel(AttnBwdArgs a) {
     __shared__ __align__(16) bf16 Ks[2][64][kPad];
     __shared__ __align__(16) bf16 Vs[2][64][kPad];
 

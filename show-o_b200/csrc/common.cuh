@@ -321,11 +321,25 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr) {
     d |= (uint64_t)(kRowBytes == 128 ? 2 : 4) << 61;
     return d;
 }
+// MN-major operand (the tile's M or N index is the contiguous one: a [k][mn] box with 128-byte rows of 64 mn values, TMA SWIZZLE_128B):
+// the canonical layout is ((8,n),(8,k)) : ((1,LBO),(8,SBO)) in 16-byte units (cute mma_traits_sm100.hpp make_umma_desc<Major::MN>) --
+// 64 mn values contiguous, the next 64-wide mn atom LBO bytes on, 8 k rows of 128 bytes per swizzle atom, the next 8 k rows SBO on.
+__device__ __forceinline__ uint64_t umma_desc_mnmajor(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;             // SWIZZLE_128B
+    return d;
+}
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 (1<<4), a=b=bf16 (1<<7, 1<<10), K-major both,
 // N>>3 at [17,23), M>>4 at [24,29).
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// the same with both operands MN-major (a_major bit 15, b_major bit 16)
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_mn(int M, int N) { return umma_idesc_bf16(M, N) | (1u << 15) | (1u << 16); }
 
 // ---- cp.async (LDGSTS)
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {

@@ -839,7 +839,8 @@ int showo_gemm_bf16(const void* A_dev, int64_t lda, const void* B_dev, int64_t l
     g.A = (const bf16*)A_dev; g.lda = lda; g.B = (const bf16*)B_dev; g.ldb = ldb; g.M = M; g.N = N; g.K = K;
     g.out = out_dev; g.ldc = ldc; g.bias = bias_dev; g.resid = resid_dev; g.ldr = ldr; g.gelu_from = gelu_from;
     g.block_n = block_n;
-    SHOWO_CHECK(epi >= 0 && epi <= 2, "gemm: epi must be 0, 1 or 2");
+    if (epi == 3) return gemm_bf16_tn(g, (cudaStream_t)stream);        // token-major operands: C = A^T B, A = [K, lda], B = [K, ldb]
+    SHOWO_CHECK(epi >= 0 && epi <= 2, "gemm: epi must be 0, 1, 2 or 3");
     return gemm_bf16(g, (GemmEpi)epi, (cudaStream_t)stream);
 }
 

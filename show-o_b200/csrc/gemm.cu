@@ -220,6 +220,23 @@ static int gemm_bn(const GemmArgs& a, GemmEpi epi, cudaStream_t st) {
     SHOWO_CHECK(false, "bad epilogue");
 }
 
+int gemm_bf16_tn(const GemmArgs& a, cudaStream_t st) {
+    SHOWO_CHECK(a.M > 0 && a.N > 0 && a.K > 0, "gemm_tn: empty problem");
+    SHOWO_CHECK((a.lda % 8) == 0 && (a.ldb % 8) == 0 && (reinterpret_cast<uintptr_t>(a.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.B) & 15) == 0,
+                "gemm_tn: lda/ldb must be multiples of 8 elements and A/B 16-byte aligned");
+    constexpr int BN = 256, BK = 128, CL = 2, CG = 2;
+    CUtensorMap ma, mb;
+    uint64_t da[2] = {(uint64_t)a.M, (uint64_t)a.K}, sa[1] = {(uint64_t)a.lda * 2};
+    uint64_t db[2] = {(uint64_t)a.N, (uint64_t)a.K}, sb[1] = {(uint64_t)a.ldb * 2};
+    uint32_t box[2] = {64, 64};
+    SHOWO_TRY(make_map(&ma, a.A, 2, da, sa, box, 128));
+    SHOWO_TRY(make_map(&mb, a.B, 2, db, sb, box, 128));
+    GemmParams p{};
+    p.M = a.M; p.N = a.N; p.K = a.K; p.out = a.out; p.ldc = a.ldc; p.bias = a.bias; p.gelu_from = a.N;
+    const int tiles = cdiv(cdiv(a.M, 128), CL) * cdiv(a.N, BN);
+    return launch<BN, EPI_BIAS_F32, A_MN, BK, CL, CG>(ma, mb, p, tiles, st);
+}
+
 int gemm_bf16(const GemmArgs& a, GemmEpi epi, cudaStream_t st) {
     SHOWO_CHECK(a.M > 0 && a.N > 0 && a.K > 0, "gemm: empty problem");
     if (a.M <= 16 && a.K % 64 == 0 && a.block_n == 0) return gemm_skinny(a, (int)epi, nullptr, st);   // decode: HBM-bound weight streaming

@@ -29,7 +29,9 @@
 namespace showo {
 
 enum { EPI_BIAS_BF16 = 0, EPI_RESID_F32 = 1, EPI_BIAS_F32 = 2, EPI_CONV_BF16 = 3, EPI_QKV_BF16 = 4 };
-enum { A_PLAIN = 0, A_CONV3 = 1 };
+// A_MN: BOTH operands are [k][features] row-major (features contiguous) -- the weight-gradient GEMM dW = dY^T X contracting over
+// the tokens reads dY and X as they lie, through MN-major shared-memory descriptors (no transposed copies)
+enum { A_PLAIN = 0, A_CONV3 = 1, A_MN = 2 };
 
 struct GemmParams {
     int M, N, K;
@@ -133,7 +135,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int tiles_n = (p.N + BN - 1) / BN;
     // Work unit = CL m-tiles (one per CTA of the cluster) that share one B tile: each CTA TMA-loads 1/CL of the B tile and
     // multicasts it to the whole cluster, which cuts the L2->SM traffic per flop (the measured limiter at CL = 1).
-    static_assert(CL == 1 || (AMODE == A_PLAIN && (BN % CL) == 0), "clusters only for the plain GEMM");
+    static_assert(CL == 1 || ((AMODE == A_PLAIN || AMODE == A_MN) && (BN % CL) == 0), "clusters only for the plain GEMM");
+    static_assert(AMODE != A_MN || (CG == 2 && BK_ == 128), "token-major operands are wired for the CTA-pair, BK = 128 configuration");
     const int crank = (CL > 1) ? (int)cluster_ctarank() : 0;
     const int tiles_mc = (tiles_m + CL - 1) / CL;
     const int num_units = tiles_mc * tiles_n;
@@ -191,11 +194,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     if constexpr (CG == 2) {
                         // both CTAs load their A tile and their half of B; all bytes are credited to the LEADER barrier
                         if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+                        if constexpr (AMODE == A_MN) {
+                            // 64 k x 64 feature boxes (8 KB, rows of 128 swizzled bytes): box (h, q) = k half h, feature atom q
+#pragma unroll
+                            for (int h = 0; h < BK / 64; ++h)
+#pragma unroll
+                                for (int q = 0; q < 2; ++q) {
+                                    tma_load_2d_cg2(smem_a + stage * Cfg::kAB + (h * 2 + q) * 8192, &tmap_a, &full_bar[stage], tm * BM + q * 64,
+                                                    kb * BK + h * 64);
+                                    tma_load_2d_cg2(smem_b + stage * Cfg::kBB + (h * 2 + q) * 8192, &tmap_b, &full_bar[stage],
+                                                    tn * BN + crank * (BN / 2) + q * 64, kb * BK + h * 64);
+                                }
+                        } else {
 #pragma unroll
                         for (int h = 0; h < BK / 64; ++h) {      // a stage = BK/64 sub-tiles of 64 k (one 128B swizzle atom wide)
                             tma_load_2d_cg2(smem_a + stage * Cfg::kAB + h * (BM * 128), &tmap_a, &full_bar[stage], kb * BK + h * 64, tm * BM);
                             tma_load_2d_cg2(smem_b + stage * Cfg::kBB + h * ((BN / 2) * 128), &tmap_b, &full_bar[stage], kb * BK + h * 64,
                                             tn * BN + crank * (BN / 2));
+                        }
                         }
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
                         continue;
@@ -226,7 +242,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
     } else if (warp == 1) {
         // ===================================================== MMA issuer
-        constexpr uint32_t idesc = umma_idesc_bf16(BM * CG, BN);     // cta_group::2: one M = 256 instruction for the pair
+        constexpr uint32_t idesc = (AMODE == A_MN) ? umma_idesc_bf16_mn(BM * CG, BN)
+                                                   : umma_idesc_bf16(BM * CG, BN);     // cta_group::2: one M = 256 instruction for the pair
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
@@ -248,8 +265,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
                         constexpr int kRowB = (BK >= 64) ? 128 : BK * 2;            // bytes per smem row (swizzle width)
-                        const uint64_t da = umma_desc_kmajor<kRowB>(a_addr + (k >> 2) * (BM * 128) + (k & 3) * 32);
-                        const uint64_t db = umma_desc_kmajor<kRowB>(b_addr + (k >> 2) * ((BN / CG) * 128) + (k & 3) * 32);
+                        uint64_t da, db;
+                        if constexpr (AMODE == A_MN) {
+                            // 16 k = two 8-row swizzle atoms (SBO 1024) of the 64-row box k >> 2; the second feature atom is the next box (LBO)
+                            da = umma_desc_mnmajor(a_addr + (k >> 2) * 16384 + (k & 3) * 2048, 8192, 1024);
+                            db = umma_desc_mnmajor(b_addr + (k >> 2) * 16384 + (k & 3) * 2048, 8192, 1024);
+                        } else {
+                            da = umma_desc_kmajor<kRowB>(a_addr + (k >> 2) * (BM * 128) + (k & 3) * 32);
+                            db = umma_desc_kmajor<kRowB>(b_addr + (k >> 2) * ((BN / CG) * 128) + (k & 3) * 32);
+                        }
                         if constexpr (CG == 2) umma_bf16_cg2(d_tmem, da, db, idesc, ((kb - kb_begin) | k) != 0);
                         else umma_bf16(d_tmem, da, db, idesc, ((kb - kb_begin) | k) != 0);
                     }

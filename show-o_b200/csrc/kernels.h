@@ -53,6 +53,10 @@ struct QkvFuse {
 };
 int gemm_qkv_bf16(const GemmArgs& a, const QkvFuse& f, cudaStream_t st);
 // weight-streaming path for M <= 16 rows (decode); epi: 0 bias->bf16(+gelu), 1 resid+bias->f32, 2 bias->f32, 3 fused qkv (gemv.cu)
+// C[M, N] (fp32) = A^T B with A = [K][lda >= M] and B = [K][ldb >= N] row-major bf16 (both "token-major": the contraction index is the
+// row): the weight-gradient GEMM dW = dY^T X reading dY and X as they lie (MN-major UMMA operands).  Rows past K, features past M / N
+// are zero-filled by the TMA unit.  Uses out / ldc of GemmArgs.
+int gemm_bf16_tn(const GemmArgs& a, cudaStream_t st);
 bool skinny_ln_fold_ok(int K);        // the skinny GEMM in use can run the folded-LayerNorm epilogues for this K
 int gemm_skinny(const GemmArgs& a, int epi, const QkvFuse* qf, cudaStream_t st);
 // stream-K fix-up workspace shared by the streamed skinny GEMM and the decode megakernel: partial tiles [grid][2][16x64]

@@ -423,6 +423,37 @@ __global__ void __launch_bounds__(256) rowsum_bf16_kernel(const bf16* __restrict
     if (lane == 0) out[r] = s;
 }
 
+// partial[blockIdx.y][c] = sum over this block's rows of src[r, c]  (c < C; the row stride ld is a multiple of 4 so the 8-byte loads of
+// the last, partly valid column group stay inside the row); reduce_partials_kernel finishes in a fixed order
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict__ src, int64_t ld, int R, int C, float* __restrict__ partial) {
+    __shared__ float sm[8][32][5];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 128 + tx * 4;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (c < C)
+        for (int r = blockIdx.y * 8 + ty; r < R; r += 8 * gridDim.y) {
+            const uint2 u = *reinterpret_cast<const uint2*>(src + (int64_t)r * ld + c);
+            const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+            const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+            a0 += f0.x; a1 += f0.y; a2 += f1.x; a3 += f1.y;
+        }
+    sm[ty][tx][0] = a0; sm[ty][tx][1] = a1; sm[ty][tx][2] = a2; sm[ty][tx][3] = a3;
+    __syncthreads();
+    if (ty < 4) {                      // thread (ty, tx) finishes column c + ty
+        float v = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v += sm[j][tx][ty];
+        if (c + ty < C) partial[(int64_t)blockIdx.y * C + c + ty] = v;
+    }
+}
+__global__ void __launch_bounds__(256) train_f32_to_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t n4) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = reinterpret_cast<const float4*>(src)[i];
+        uint2 o; o.x = pack_bf16(v.x, v.y); o.y = pack_bf16(v.z, v.w);
+        reinterpret_cast<uint2*>(dst)[i] = o;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ cross-entropy backward
 struct CeBwdArgs {
     const float* logits; const int64_t* labels; int L, V; int64_t Vp;
@@ -605,6 +636,34 @@ static int gemm_plain(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, in
     g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.M = M; g.N = N; g.K = K; g.out = out; g.ldc = ldc; g.gelu_from = N;
     if (M <= 16) g.block_n = 64;          // keep the training path on the tcgen05 kernel whatever the row count
     return gemm_bf16(g, f32_out ? GEMM_BIAS_F32 : GEMM_BIAS_BF16, st);
+}
+
+// SHOWO_WGRAD_MN=0: the first version of the weight-gradient GEMMs (explicit transposed bf16 copies of dY and X, K-major operands)
+static bool wgrad_mn() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SHOWO_WGRAD_MN"); v = (e && atoi(e) == 0) ? 0 : 1; }
+    return v == 1;
+}
+// dW[n_out, n_in] (fp32) = dY^T X over the M tokens and dbias[n_out] = column sums of dY, with dY = [M, ld_y], X = [M, ld_x] bf16.
+// Default: the tcgen05 GEMM reads both operands as they lie (MN-major descriptors, gemm_bf16_tn) -- no transposed copies.
+static int wgrad(TrainState* t, const bf16* dY, int64_t ld_y, int n_out, const bf16* X, int64_t ld_x, int n_in, int M, int64_t Mp,
+                 float* dW, int64_t ld_w, float* dbias, cudaStream_t st) {
+    if (wgrad_mn()) {
+        GemmArgs g{};
+        g.A = dY; g.lda = ld_y; g.B = X; g.ldb = ld_x; g.M = n_out; g.N = n_in; g.K = M; g.out = dW; g.ldc = ld_w;
+        SHOWO_TRY(gemm_bf16_tn(g, st));
+        const int S = 32;
+        SHOWO_TRY(ensure_partials(t, (size_t)S * n_out));
+        colsum_bf16_kernel<<<dim3(cdiv(n_out, 128), S), 256, 0, st>>>(dY, ld_y, M, n_out, t->partials);
+        reduce_partials_kernel<<<cdiv(n_out, 32), 256, 0, st>>>(t->partials, S, n_out, dbias);
+        note_launch(2);
+        SHOWO_CUDA_OK(cudaGetLastError());
+        return 0;
+    }
+    SHOWO_TRY(transpose_to_bf16<bf16>(dY, ld_y, M, (int)((n_out + 1) / 2 * 2), t->tA, Mp, nullptr, 0, st));
+    SHOWO_TRY(transpose_to_bf16<bf16>(X, ld_x, M, n_in, t->tB, Mp, nullptr, 0, st));
+    SHOWO_TRY(gemm_plain(t->tA, Mp, t->tB, Mp, n_out, n_in, (int)Mp, dW, ld_w, true, st));
+    return rowsum_bf16(t->tA, Mp, n_out, M, dbias, st);
 }
 
 static int ensure_train(showo_engine* e, int M, cudaStream_t st) {
@@ -859,10 +918,7 @@ static int backward_phase(showo_engine_t* e, int phase, const float* loss_grads_
     // d xh_f = dlogits * Wh                                     [M, D] fp32
     SHOWO_TRY(gemm_plain(t->dlogits, Vp, t->head_wt, Vp, M, D, (int)Vp, t->dxh, D, true, st));
     // d Wh = dlogits^T * xh_f, d bh = column sums of dlogits
-    SHOWO_TRY(transpose_to_bf16<bf16>(t->dlogits, Vp, M, (int)Vp, t->tA, Mp, nullptr, 0, st));
-    SHOWO_TRY(transpose_to_bf16<bf16>(t->xh + (size_t)NL * mD, D, M, D, t->tB, Mp, nullptr, 0, st));
-    SHOWO_TRY(gemm_plain(t->tA, Mp, t->tB, Mp, V, D, (int)Mp, G + gl.head_w, D, true, st));
-    SHOWO_TRY(rowsum_bf16(t->tA, Mp, V, M, G + gl.head_b, st));
+    SHOWO_TRY(wgrad(t, t->dlogits, Vp, V, t->xh + (size_t)NL * mD, D, D, M, Mp, G + gl.head_w, D, G + gl.head_b, st));
     // final LayerNorm
     SHOWO_TRY(layernorm_backward(t, t->dxh, t->xs + (size_t)NL * mD, t->stats + (size_t)NL * M, e->fln_g, t->dx, false, G + gl.fln_g,
                                  G + gl.fln_b, M, D, st));
@@ -875,11 +931,10 @@ static int backward_phase(showo_engine_t* e, int phase, const float* loss_grads_
         const bf16* pre = t->pre + (size_t)l * M * W1N;
         const bf16* a2 = t->a2 + (size_t)l * M * W2K;
         // dx (fp32) -> bf16 row-major + transposed; d b2 = column sums
-        SHOWO_TRY(transpose_to_bf16<float>(t->dx, D, M, D, t->tA, Mp, t->dxb, D, st));
-        SHOWO_TRY(rowsum_bf16(t->tA, Mp, D, M, GL + gl.b2, st));
+        train_f32_to_bf16_kernel<<<148 * 8, 256, 0, st>>>(t->dx, t->dxb, (int64_t)mD / 4);
+        note_launch();
         // d W2 = dx^T * [attn | act]
-        SHOWO_TRY(transpose_to_bf16<bf16>(a2, W2K, M, W2K, t->tB, Mp, nullptr, 0, st));
-        SHOWO_TRY(gemm_plain(t->tA, Mp, t->tB, Mp, D, W2K, (int)Mp, GL + gl.w2, W2K, true, st));
+        SHOWO_TRY(wgrad(t, t->dxb, D, D, a2, W2K, W2K, M, Mp, GL + gl.w2, W2K, GL + gl.b2, st));
         // d [attn | act] = dx * W2; the act columns leave the epilogue as d fc1 = d act * gelu_new'(fc1) in dpre[:, 3D:]
         {
             GemmArgs g{};
@@ -907,10 +962,7 @@ static int backward_phase(showo_engine_t* e, int phase, const float* loss_grads_
         note_launch(2);
         SHOWO_CUDA_OK(cudaGetLastError());
         // d W1 = dpre^T * xh, d b1 = column sums of dpre
-        SHOWO_TRY(transpose_to_bf16<bf16>(t->dpre, W1N, M, W1N, t->tA, Mp, nullptr, 0, st));
-        SHOWO_TRY(transpose_to_bf16<bf16>(t->xh + (size_t)l * mD, D, M, D, t->tB, Mp, nullptr, 0, st));
-        SHOWO_TRY(gemm_plain(t->tA, Mp, t->tB, Mp, W1N, D, (int)Mp, GL + gl.w1, D, true, st));
-        SHOWO_TRY(rowsum_bf16(t->tA, Mp, W1N, M, GL + gl.b1, st));
+        SHOWO_TRY(wgrad(t, t->dpre, W1N, W1N, t->xh + (size_t)l * mD, D, D, M, Mp, GL + gl.w1, D, GL + gl.b1, st));
         // d xh = dpre * W1, then LayerNorm backward into the residual gradient
         SHOWO_TRY(gemm_plain(t->dpre, W1N, t->w1t + (size_t)l * D * W1N, W1N, M, D, W1N, t->dxh, D, true, st));
         SHOWO_TRY(layernorm_backward(t, t->dxh, t->xs + (size_t)l * mD, t->stats + (size_t)l * M, w.ln_g, t->dx, true, GL + gl.ln_g,

@@ -92,6 +92,28 @@ def test_gemm_tcgen05_against_fp32(lib, dev, Mm, N, K, bn):
     assert (outr - (ref + res)).abs().max().item() < 1e-3
 
 
+@pytest.mark.parametrize("Mf,Nf,K", [(2048, 10240, 9240), (640, 128, 100), (128, 384, 77), (58498, 256, 300), (14336, 2048, 1155)])
+def test_gemm_token_major_operands_against_fp32(lib, dev, Mf, Nf, K):
+    """weight-gradient form dW = dY^T X: both operands [tokens, features] as they lie (MN-major UMMA descriptors), ragged token counts,
+    feature counts that leave tiles partly empty, row strides wider than the feature count."""
+    g = torch.Generator(device=dev).manual_seed(Mf + Nf + K)
+    lda, ldb = (Mf + 7) // 8 * 8 + 8, Nf + 16
+    A = torch.zeros(K, lda, device=dev, dtype=torch.bfloat16)
+    Bx = torch.zeros(K, ldb, device=dev, dtype=torch.bfloat16)
+    A[:, :Mf] = (torch.randn(K, Mf, device=dev, generator=g) * 0.1).bfloat16()
+    Bx[:, :Nf] = (torch.randn(K, Nf, device=dev, generator=g) * 0.5).bfloat16()
+    A[:, Mf:] = 7.0                                   # the pad columns must not leak into the product
+    Bx[:, Nf:] = 7.0
+    ref = A[:, :Mf].float().t() @ Bx[:, :Nf].float()
+    out = torch.full((Mf, Nf), float("nan"), device=dev)
+    _lib.check(lib.showo_gemm_bf16(_lib.ptr(A), lda, _lib.ptr(Bx), ldb, Mf, Nf, K, _lib.ptr(out), Nf, None, None, 0, Nf, 3, 0, S()))
+    assert not torch.isnan(out).any()
+    assert (out - ref).abs().max().item() < 2e-3 * max(1.0, (K / 256) ** 0.5)
+    out2 = torch.full((Mf, Nf), float("nan"), device=dev)
+    _lib.check(lib.showo_gemm_bf16(_lib.ptr(A), lda, _lib.ptr(Bx), ldb, Mf, Nf, K, _lib.ptr(out2), Nf, None, None, 0, Nf, 3, 0, S()))
+    assert torch.equal(out, out2)
+
+
 @pytest.mark.parametrize("Mm,N,K", [(16, 2048, 10240), (16, 58498, 2048), (3, 1000, 256), (16, 14336, 2048), (1, 64, 64),
                                     (9, 2048, 2048)])
 def test_skinny_weight_streaming_gemm(lib, dev, Mm, N, K):

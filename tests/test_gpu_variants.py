@@ -27,6 +27,7 @@ VARIANTS = {
     "decode_attention_per_thread": ({"SHOWO_DECODE_ATTN": "1"}, DECODE_K),
     "decode_ln_fused": ({"SHOWO_DECODE_LN_FUSED": "1"}, DECODE_K),
     "decode_l2_prefetch": ({"SHOWO_L2_PREFETCH": "1"}, DECODE_K),
+    "wgrad_transposed_copies": ({"SHOWO_WGRAD_MN": "0"}, None),
     "ln_fold_off": ({"SHOWO_LN_FOLD": "0"}, DECODE_K),
     "ln_fold_all_paths": ({"SHOWO_LN_FOLD": "2"}, GEMM_K + " or forward_masks or t2i or " + DECODE_K),
     "no_pdl": ({"SHOWO_PDL": "0"}, "forward_tiny or mmu_generate_batched or teacher_forced"),
@@ -39,8 +40,9 @@ def runs():
     for name, (env, k) in VARIANTS.items():
         e = dict(os.environ)
         e.update(env)
-        cmd = [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-q", "-x", "-m", "gpu", "-k", k,
-               "-p", "no:cacheprovider"]
+        # k = None: the variant concerns the training step -> tests/test_gpu_train.py as a whole
+        cmd = [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py" if k else "test_gpu_train.py"), "-q", "-x",
+               "-m", "gpu", "-p", "no:cacheprovider"] + (["-k", k] if k else [])
         procs[name] = subprocess.Popen(cmd, cwd=ROOT, env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     out = {}
     for name, p in procs.items():
