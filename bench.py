@@ -455,11 +455,17 @@ class _BenchTokenizer:
 def train_step_bench(torch, dist, model, dev, world, rank, warm=1, steps=2):
     """BASELINE.json configs[4]: showo_demo_w_clip_vit_512x512.yaml mixed t2i + lm + mmu training step, forward / backward in bf16
     (fp32 master gradients), per-GPU micro-batch 8 rows of L = 1155 (3 t2i + 1 lm + 4 mmu-vit), data parallel:
-    the t2i rows come from the device-side producer (showo_t2i_train_prep), the fp32 gradients (5.8 GB) are all-reduced per layer
-    on a side stream while the earlier layers' backward runs; the step ends with the engine's AdamW (showo_adamw_step: fp32 masters and
-    moments, decay on non-bias parameters like training/train.py:211-236) which also rewrites the bf16 working weights."""
+    the t2i rows come from the device-side producer (showo_t2i_train_prep); the mmu rows are [mmu, 28 system ids, soi] || 576 visual
+    positions || [eoi, 548 text ids] whose visual positions carry mm_projector(N(0,1) [4, 576, 1024]) (the CLIP tower is frozen and
+    excluded, its features are synthetic) -- handed to the engine as the mixed ids / embeddings input; the backward returns the
+    gradient of those positions and showo_mm_projector_backward turns it into the projector's gradients.  The fp32 gradients (5.8 GB +
+    the projector's 25 MB) are all-reduced per layer on a side stream while the earlier layers' backward runs; the step ends with the
+    engine's AdamW (showo_adamw_step: fp32 masters and moments, decay on non-bias parameters like training/train.py:211-236, projector
+    included) which also rewrites the bf16 working weights."""
     from showo_b200 import train_inputs as TI
     L5, N5, B_T2I, B_LM, B_MMU = 1155, 1024, 3, 1, 4
+    SYS, NVIS = 28, 576
+    V0 = 1 + SYS + 1                                             # first visual position
     g = torch.Generator().manual_seed(777 + rank)
     up = TI.UniversalPrompting(_BenchTokenizer(), max_text_len=P_TXT - 1, ignore_id=-100, cond_dropout_prob=0.1)
 
@@ -469,17 +475,27 @@ def train_step_bench(torch, dist, model, dev, world, rank, warm=1, steps=2):
     codes = (torch.randint(0, CODEBOOK, (B_T2I, N5), generator=g) + 50305).to(dev)
     texts = [torch.randint(0, 50256, (int(torch.randint(8, 65, (1,), generator=g)),), generator=g).tolist() for _ in range(B_T2I)]
     lm_ids = torch.randint(0, 50257, (B_LM, L5), generator=g).to(dev)
-    mmu_ids = torch.randint(0, 50257, (B_MMU, L5), generator=g).to(dev)
+    mmu_ids = torch.randint(0, 50257, (B_MMU, L5), generator=g)
     mmu_lab = torch.full((B_MMU, L5), -100, dtype=torch.int64)
-    mmu_lab[:, L5 - 548:] = mmu_ids[:, L5 - 548:].cpu()
-    mmu_lab = mmu_lab.to(dev)
+    mmu_lab[:, L5 - 548:] = mmu_ids[:, L5 - 548:]
+    mmu_ids[:, V0:V0 + NVIS] = -1                                # visual positions: their vectors come from the projector
+    mmu_ids, mmu_lab = mmu_ids.to(dev), mmu_lab.to(dev)
+    feats = torch.randn(B_MMU, NVIS, 1024, generator=g).to(dev)  # synthetic CLIP-ViT features
+    B = B_T2I + B_LM + B_MMU
+    emb_full = torch.zeros(B, L5, D, device=dev)                 # only the ids < 0 positions are read
+    vis_rows = (slice(B_T2I + B_LM, B), slice(V0, V0 + NVIS))
     loss_w = torch.tensor([1.0, 0.1, 1.0], device=dev)          # training.t2i_coeff / lm_coeff / mmu_coeff of the yaml
     comm = torch.cuda.Stream(dev) if world > 1 else None
     # optimizer state in the engine (fp32 masters + Adam moments): enable, then hand the weights over again so that their fp32 values are kept
     from showo_b200 import _lib
     lib = _lib.require_gpu()
     model.enable_optimizer()
+    gp = torch.Generator(device=dev).manual_seed(4)
+    proj = {"mm_projector.0.weight": torch.randn(2048, 1024, device=dev, generator=gp) * 0.02, "mm_projector.0.bias": torch.zeros(2048, device=dev),
+            "mm_projector.2.weight": torch.randn(2048, 2048, device=dev, generator=gp) * 0.02, "mm_projector.2.bias": torch.zeros(2048, device=dev)}
     for name, t in gpu_random_weights(torch, dev, seed=0):
+        _lib.check(lib.showo_load_weight(model._engine, name.encode(), _lib.ptr(t), t.numel(), 1), f"load {name}")
+    for name, t in proj.items():
         _lib.check(lib.showo_load_weight(model._engine, name.encode(), _lib.ptr(t), t.numel(), 1), f"load {name}")
     _lib.check(lib.showo_weights_complete(model._engine), "weights_complete")
     model._streamed = True
@@ -489,14 +505,16 @@ def train_step_bench(torch, dist, model, dev, world, rank, warm=1, steps=2):
         ids_t2i, lab_t2i, _, descs_t2i = up.t2i_train_rows(texts, codes, V - 1, cfg, showo_b200_cosine())
         ids = torch.cat([ids_t2i, lm_ids, mmu_ids])
         labels = torch.cat([lab_t2i, lm_ids, mmu_lab])
-        descs = [tuple(r) for r in descs_t2i.tolist()] + [(0, 0, 0, 0, 0)] * B_LM + [(0, 0, 0, 30, 606)] * B_MMU
+        descs = [tuple(r) for r in descs_t2i.tolist()] + [(0, 0, 0, 0, 0)] * B_LM + [(0, 0, 0, V0, V0 + NVIS)] * B_MMU
         terms = model._loss_terms(ids.shape[0], L5, B_T2I, B_LM, B_MMU, P_TXT - 1)
-        _, losses = model.train_forward(ids, None, descs, labels, terms, want_logits=False)
+        emb_full[vis_rows] = model._project(feats)               # model.mm_projector(images_embeddings), train_w_clip_vit.py:599-601
+        _, losses = model.train_forward(ids, emb_full, descs, labels, terms, want_logits=False)
         if world > 1:
-            done = model.backward_overlapped(loss_w, comm_stream=comm)
+            done = model.backward_overlapped(loss_w, comm_stream=comm, input_grad_like=emb_full, projector_rows=vis_rows)
             torch.cuda.current_stream().wait_event(done)
         else:
-            model.backward(loss_w)
+            demb = model.backward(loss_w, want_input_grad_like=emb_full)
+            model.mm_projector_backward(demb[vis_rows])
         model.adamw_step(lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)      # optimizer.params of the yaml
         return losses
     for _ in range(warm):
@@ -514,19 +532,20 @@ def train_step_bench(torch, dist, model, dev, world, rank, warm=1, steps=2):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item()) / steps
-    B = B_T2I + B_LM + B_MMU
     f_step = 3 * B * L5 * (G_TOK + A_PAIR * L5 + 2 * D * V)
     peaks = measured_peaks()
     return {"metric": "train_step_tokens_per_sec_mixed_t2i_lm_mmu_L1155_fwd_bwd_adamw", "value": round(world * B * L5 / ms * 1e3, 1), "unit": "tokens/s",
             "n_gpus": world, "ms_per_step": round(ms, 2), "steps": steps, "warmup": warm,
             "config": {"workload": "showo_demo_w_clip_vit_512x512.yaml geometry: forward + backward of 8 rows x L=1155 per GPU (3 t2i from the "
-                                   "device-side producer + 1 lm + 4 mmu-vit), bf16 operands / fp32 gradients, per-layer gradient all-reduce "
-                                   "(fp32, 5.8 GB) overlapped with backward for N > 1, then the engine-side AdamW step (fp32 masters + moments)",
+                                   "device-side producer + 1 lm + 4 mmu-vit whose 576 visual positions are mm_projector(synthetic CLIP "
+                                   "features), projector forward + backward included), bf16 operands / fp32 gradients, per-layer gradient "
+                                   "all-reduce (fp32, 5.8 GB) overlapped with backward for N > 1, then the engine-side AdamW step (fp32 "
+                                   "masters + moments, backbone + projector)",
                        "global_batch": world * B, "seq_len": L5},
             "losses": [round(float(x), 4) for x in losses[:, 0].tolist()],
             "roofline": {"bound": "tensor", "achieved": round(f_step / ms / 1e9, 1), "peak": peaks["bf16_sustained"], "unit": "TFLOP/s per GPU",
                          "frac": round(f_step / ms / 1e9 / peaks["bf16_sustained"], 4), "algorithmic_tflop_per_step": round(f_step / 1e12, 2),
-                         "kernel": "whole step (3 x forward FLOPs, SURVEY 8d config 5)"}}
+                         "kernel": "whole step (3 x forward FLOPs of the backbone, SURVEY 8d config 5; the projector's 0.09 TFLOP are not counted)"}}
 
 
 def showo_b200_cosine():

@@ -145,6 +145,14 @@ SHOWO_API int showo_mmu_sample(const float* logits_dev, int64_t ld, int B, int V
  * inference_mmu.py:128-131 calls it: feats_dev fp32 [n, 1024] -> out_dev fp32 [n, 2048] (bf16 operands, fp32 accumulation, exact erf GELU).
  * Weights arrive through showo_load_weight under "mm_projector.0.weight" / ".0.bias" / ".2.weight" / ".2.bias" (optional set). */
 SHOWO_API int showo_mm_projector(showo_engine_t* e, const float* feats_dev, int64_t n, float* out_dev, void* stream);
+/* Its backward, for the rows of the LAST showo_mm_projector call (training/train_w_clip_vit.py:599-601 trains the projector through
+ * `input_embeddings`; the CLIP features themselves are frozen, :199-203): dy_dev fp32 [n, 2048] = the rows of showo_backward's
+ * dembeds_out that the projector's output occupied.  Gradients (fp32) go to an engine-owned buffer [0.weight | 0.bias | 2.weight |
+ * 2.bias] = 6,295,552 elements: read per tensor with showo_read_grad("mm_projector.*"), all-reduce in place through
+ * showo_mm_projector_grad_buffer; showo_adamw_step updates the four tensors (weights decayed, biases not) whenever a projector
+ * backward has run since the previous step. */
+SHOWO_API int showo_mm_projector_backward(showo_engine_t* e, const float* dy_dev, int64_t n, void* stream);
+SHOWO_API int showo_mm_projector_grad_buffer(showo_engine_t* e, float** base_dev, int64_t* numel);
 
 /* model.showo.model.embed_tokens(ids) as called from outside (inference_mmu.py:134-136): out fp32 [n, hidden] */
 SHOWO_API int showo_embed_tokens(showo_engine_t* e, const int64_t* ids_dev, int64_t n, float* out_dev, void* stream);
@@ -153,7 +161,11 @@ SHOWO_API int showo_embed_tokens(showo_engine_t* e, const int64_t* ids_dev, int6
  * Showo.forward with labels under autograd (models/modeling_showo.py:59-102): the same logits and cross-entropy terms as
  * showo_forward + showo_cross_entropy, with every layer's activations kept in engine-owned buffers for showo_backward.
  * terms_host: 3 x {b0, nb, t0, nt, shift} (t2i, lm, mmu) exactly as in showo_cross_entropy.  logits_out_dev [B, L, vocab]
- * fp32 may be NULL (the logits then stay in an engine buffer).  losses_out_dev: float[3][2] = {mean, counted rows}. */
+ * fp32 may be NULL (the logits then stay in an engine buffer).  losses_out_dev: float[3][2] = {mean, counted rows}.
+ * Inputs: ids_dev alone, embeds_dev alone ([B, L, hidden] fp32), or BOTH = the mixed rows of training/train_w_clip_vit.py:532-537:
+ * positions with ids >= 0 are looked up in the embedding table, positions with ids < 0 take embeds_dev[b, t, :] (the mm_projector
+ * output); the backward then scatters the embedding gradient of the former and hands the gradient of the latter back in
+ * showo_backward's dembeds_out_dev. */
 SHOWO_API int showo_train_forward(showo_engine_t* e, const int64_t* ids_dev, const float* embeds_dev, int B, int L,
                         const showo_seq_mask_t* masks_host, const int64_t* labels_dev, const int32_t* terms_host,
                         int64_t ignore_index, float* logits_out_dev, float* losses_out_dev, void* stream);

@@ -64,6 +64,8 @@ _PROTOS = {
     "showo_t2i_train_prep": (_I, [_P, _I, _I, _P, _P, _I64, _I, C.POINTER(C.c_int64), _F, _F, _I, _F, _P, _P, _P, C.c_uint64, _I,
                                   _P, _P, _P, _P, _P, _P, _P, _P]),
     "showo_mm_projector": (_I, [_P, _P, _I64, _P, _P]),
+    "showo_mm_projector_backward": (_I, [_P, _P, _I64, _P]),
+    "showo_mm_projector_grad_buffer": (_I, [_P, C.POINTER(_P), C.POINTER(_I64)]),
     "showo_embed_tokens": (_I, [_P, _P, _I64, _P, _P]),
     "showo_kernel_launches": (_I64, [_P]),
     "magvit_engine_create": (_I, [_I, C.POINTER(_P)]),

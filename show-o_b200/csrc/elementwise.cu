@@ -120,16 +120,49 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ src, bf16* __restri
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) dst[i] = __float2bfloat16(src[i]);
 }
-// nn.GELU() (exact, erf form) in place on bf16 -- the activation of Showo.mm_projector (modeling_showo.py:51)
-__global__ void gelu_erf_bf16_kernel(bf16* __restrict__ x, int64_t n) {
+// nn.GELU() (exact, erf form) on bf16 -- the activation of Showo.mm_projector (modeling_showo.py:51), out of place:
+// the pre-activation is kept for the backward
+__global__ void gelu_erf_bf16_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int64_t n) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const float v = __bfloat162float(x[i]);
-        x[i] = __float2bfloat16(0.5f * v * (1.f + erff(v * 0.70710678118654752f)));
+        const float v = __bfloat162float(src[i]);
+        dst[i] = __float2bfloat16(0.5f * v * (1.f + erff(v * 0.70710678118654752f)));
     }
 }
-int gelu_erf_bf16(bf16* x, int64_t n, cudaStream_t st) {
+int gelu_erf_bf16(const bf16* src, bf16* dst, int64_t n, cudaStream_t st) {
     const int grid = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
-    gelu_erf_bf16_kernel<<<grid > 0 ? grid : 1, 256, 0, st>>>(x, n);
+    gelu_erf_bf16_kernel<<<grid > 0 ? grid : 1, 256, 0, st>>>(src, dst, n);
+    note_launch();
+    SHOWO_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+// d/dv [v Phi(v)] = Phi(v) + v phi(v),  Phi(v) = (1 + erf(v / sqrt 2)) / 2,  phi(v) = exp(-v^2 / 2) / sqrt(2 pi)
+__global__ void gelu_erf_bwd_bf16_kernel(bf16* __restrict__ d_io, const bf16* __restrict__ pre, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = __bfloat162float(pre[i]);
+        const float g = 0.5f * (1.f + erff(v * 0.70710678118654752f)) + v * 0.3989422804014327f * __expf(-0.5f * v * v);
+        d_io[i] = __float2bfloat16(__bfloat162float(d_io[i]) * g);
+    }
+}
+int gelu_erf_bwd_bf16(bf16* d_io, const bf16* pre, int64_t n, cudaStream_t st) {
+    const int grid = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+    gelu_erf_bwd_bf16_kernel<<<grid > 0 ? grid : 1, 256, 0, st>>>(d_io, pre, n);
+    note_launch();
+    SHOWO_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+// rows of a mixed ids / embeddings input: ids[r] < 0 marks a row whose vector comes from the caller (the mm_projector output of
+// train_w_clip_vit.py:532-537), every other row keeps what embed_gather put there
+__global__ void __launch_bounds__(128) embed_override_kernel(const int64_t* __restrict__ ids, const float* __restrict__ embeds,
+                                                             float* __restrict__ x, int n_rows, int D) {
+    const int r = blockIdx.x;
+    if (r >= n_rows || ids[r] >= 0) return;
+    const float4* s = reinterpret_cast<const float4*>(embeds + (int64_t)r * D);
+    float4* d = reinterpret_cast<float4*>(x + (int64_t)r * D);
+    for (int i = threadIdx.x; i < D / 4; i += blockDim.x) d[i] = s[i];
+}
+int embed_override(const int64_t* ids, const float* embeds, float* x, int n_rows, int D, cudaStream_t st) {
+    SHOWO_CHECK(D % 4 == 0, "embed_override: D must be a multiple of 4");
+    embed_override_kernel<<<n_rows, 128, 0, st>>>(ids, embeds, x, n_rows, D);
     note_launch();
     SHOWO_CUDA_OK(cudaGetLastError());
     return 0;

@@ -411,6 +411,7 @@ int showo_engine_destroy(showo_engine_t* e) {
     dev_free(e->x); dev_free(e->xh); dev_free(e->buf); dev_free(e->kcache); dev_free(e->vtcache); dev_free(e->d_masks);
     dev_free(e->logits_ws); dev_free(e->conf_ws); dev_free(e->sampled_ws); dev_free(e->tok_ws); dev_free(e->argmax_keys); dev_free(e->finished_ws); dev_free(e->attn_ctr);
     dev_free(e->mmp_w0); dev_free(e->mmp_b0); dev_free(e->mmp_w2); dev_free(e->mmp_b2); dev_free(e->mmp_in); dev_free(e->mmp_mid);
+    dev_free(e->mmp_pre); dev_free(e->mmp_grads); dev_free(e->mmp_w2t); dev_free(e->mmp_dy); dev_free(e->mmp_dmid);
     if (e->train) train_state_destroy(e->train);
     if (e->opt) opt_state_destroy(e->opt);
     delete e;
@@ -483,7 +484,8 @@ int showo_load_weight(showo_engine_t* e, const char* name_c, const float* data, 
         else if (k == "self_attn.k_layernorm.bias") rc = copy_f32(w.kb, 64);
         else { set_last_error("unknown weight name " + name); rc = -2; }
     } else if (name.compare(0, 13, "mm_projector.") == 0) {
-        // optional (w_clip_vit): not part of the backbone's required set, not touched by the engine-side optimizer
+        // optional (w_clip_vit): not part of the backbone's required set; with the optimizer enabled its fp32 values are kept as
+        // masters too (train.cu: the four tensors are updated by showo_adamw_step whenever showo_mm_projector_backward has run)
         constexpr int64_t kIn = 1024, kMid = 2048, kOut = 2048;
         if (!e->mmp_w0) {
             SHOWO_TRY(dev_alloc(&e->mmp_w0, (size_t)(kMid * kIn))); SHOWO_TRY(dev_alloc(&e->mmp_b0, (size_t)kMid));
@@ -495,8 +497,10 @@ int showo_load_weight(showo_engine_t* e, const char* name_c, const float* data, 
         else if (name == "mm_projector.2.bias") rc = copy_f32(e->mmp_b2, kOut);
         else { set_last_error("unknown weight name " + name); rc = -2; }
         if (rc) return rc;
+        if (e->opt) SHOWO_TRY(opt_store_master(e, name, src, numel, st));
         SHOWO_CUDA_OK(cudaStreamSynchronize(st));
         e->loaded.insert(name);
+        ++e->mmp_version;
         return 0;
     } else {
         set_last_error("unknown weight name " + name);
@@ -810,18 +814,20 @@ int showo_mm_projector(showo_engine_t* e, const float* feats_dev, int64_t n, flo
     cudaStream_t st = (cudaStream_t)stream;
     if (n > e->mmp_cap) {
         SHOWO_CUDA_OK(cudaStreamSynchronize(st));
-        dev_free(e->mmp_in); dev_free(e->mmp_mid);
+        dev_free(e->mmp_in); dev_free(e->mmp_mid); dev_free(e->mmp_pre);
         SHOWO_TRY(dev_alloc(&e->mmp_in, (size_t)n * kIn));
         SHOWO_TRY(dev_alloc(&e->mmp_mid, (size_t)n * kMid));
+        SHOWO_TRY(dev_alloc(&e->mmp_pre, (size_t)n * kMid));
         e->mmp_cap = n;
     }
+    e->mmp_n = n;                                     // showo_mm_projector_backward differentiates THIS call
     SHOWO_TRY(f32_to_bf16(feats_dev, e->mmp_in, n * kIn, st));
     GemmArgs g0{};
     g0.A = e->mmp_in; g0.lda = kIn; g0.B = e->mmp_w0; g0.ldb = kIn; g0.M = (int)n; g0.N = kMid; g0.K = kIn;
-    g0.out = e->mmp_mid; g0.ldc = kMid; g0.bias = e->mmp_b0; g0.gelu_from = kMid;          // no gelu_new here: nn.GELU() is the erf form
+    g0.out = e->mmp_pre; g0.ldc = kMid; g0.bias = e->mmp_b0; g0.gelu_from = kMid;          // no gelu_new here: nn.GELU() is the erf form
     g0.block_n = 128;                                 // keeps the M <= 16 case off the decode path's fp32-only epilogues
     SHOWO_TRY(gemm_bf16(g0, GEMM_BIAS_BF16, st));
-    SHOWO_TRY(gelu_erf_bf16(e->mmp_mid, n * kMid, st));
+    SHOWO_TRY(gelu_erf_bf16(e->mmp_pre, e->mmp_mid, n * kMid, st));      // the pre-activation stays for the backward
     GemmArgs g1{};
     g1.A = e->mmp_mid; g1.lda = kMid; g1.B = e->mmp_w2; g1.ldb = kMid; g1.M = (int)n; g1.N = kOut; g1.K = kMid;
     g1.out = out_dev; g1.ldc = kOut; g1.bias = e->mmp_b2; g1.block_n = 128;

@@ -72,6 +72,12 @@ struct showo_engine {
     // Showo.mm_projector (w_clip_vit): Linear(1024, 2048) -> GELU -> Linear(2048, 2048), modeling_showo.py:49-54
     bf16* mmp_w0 = nullptr; float* mmp_b0 = nullptr; bf16* mmp_w2 = nullptr; float* mmp_b2 = nullptr;
     bf16* mmp_in = nullptr; bf16* mmp_mid = nullptr; int64_t mmp_cap = 0;
+    // its training side (train.cu: showo_mm_projector_backward, training/train_w_clip_vit.py:599-601): the pre-GELU activations of the
+    // last forward call, fp32 gradients [w0 | b0 | w2 | b2] (6,295,552 elements), a transposed copy of w2 for the dgrad GEMM
+    bf16* mmp_pre = nullptr; int64_t mmp_n = 0; int64_t mmp_version = 0;
+    float* mmp_grads = nullptr; bool mmp_grads_valid = false;
+    bf16* mmp_w2t = nullptr; int64_t mmp_w2t_version = -1;
+    bf16* mmp_dy = nullptr; bf16* mmp_dmid = nullptr; int64_t mmp_bwd_cap = 0;
     int* attn_ctr = nullptr;                              // work counter of the attention kernel's tail phase (self-resetting, zero between launches)
     int* finished_ws = nullptr;                           // [64] rows of the running mmu_generate that have produced eot_token
     int64_t launches_last = 0;

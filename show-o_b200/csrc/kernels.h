@@ -109,7 +109,11 @@ int layernorm_bf16(const float* x, const float* gamma, const float* beta, float 
 int embed_gather(const int64_t* ids, int64_t ids_stride, int pos0, const bf16* table, float* x, int n_rows,
                  int rows_per_seq, int D, int vocab, cudaStream_t st);
 int f32_to_bf16(const float* src, bf16* dst, int64_t n, cudaStream_t st);
-int gelu_erf_bf16(bf16* x, int64_t n, cudaStream_t st);     // nn.GELU() exact form, in place
+int gelu_erf_bf16(const bf16* src, bf16* dst, int64_t n, cudaStream_t st);     // nn.GELU() exact (erf) form, out of place
+// d_io[i] *= gelu_erf'(pre[i]): the backward of nn.GELU() on bf16, in place on the incoming gradient
+int gelu_erf_bwd_bf16(bf16* d_io, const bf16* pre, int64_t n, cudaStream_t st);
+// x[r, :] = embeds[r, :] for every row r whose ids[r] < 0 (rows of a mixed ids / embeddings input that carry a caller-supplied vector)
+int embed_override(const int64_t* ids, const float* embeds, float* x, int n_rows, int D, cudaStream_t st);
 // mean cross-entropy (ignore_index rows skipped) of logits[b0 + b, t0 + t, :] vs labels[b0 + b, t0 + t + shift], b < nb, t < nt;
 // ws: 2 * nb * nt floats of scratch; out2: {mean loss, number of counted rows}
 int cross_entropy_mean(const float* logits, const int64_t* labels, int64_t L, int V, int b0, int nb, int t0, int nt, int shift,

@@ -777,11 +777,30 @@ static int named_grad(showo_engine* e, const std::string& name, float** ptr, int
 struct OptState {
     float *master = nullptr, *m = nullptr, *v = nullptr;
     int64_t n = 0, step = 0;
+    // Showo.mm_projector's four tensors in the layout of showo_engine::mmp_grads (allocated when they are handed over)
+    float *mmp_master = nullptr, *mmp_m = nullptr, *mmp_v = nullptr;
 };
 void opt_state_destroy(OptState* o) {
     if (!o) return;
     dev_free(o->master); dev_free(o->m); dev_free(o->v);
+    dev_free(o->mmp_master); dev_free(o->mmp_m); dev_free(o->mmp_v);
     delete o;
+}
+
+// Showo.mm_projector = Linear(1024, 2048) -> GELU -> Linear(2048, 2048) (modeling_showo.py:49-54): element offsets of its four tensors
+// inside the projector's gradient / master / moment buffers
+constexpr int64_t kMmpIn = 1024, kMmpMid = 2048, kMmpOut = 2048;
+constexpr int64_t kMmpW0 = 0, kMmpB0 = kMmpW0 + kMmpMid * kMmpIn, kMmpW2 = kMmpB0 + kMmpMid, kMmpB2 = kMmpW2 + kMmpOut * kMmpMid,
+                  kMmpTotal = kMmpB2 + kMmpOut;
+static bool is_mmp_name(const std::string& name) { return name.compare(0, 13, "mm_projector.") == 0; }
+static int mmp_slot(float* base_ptr, const std::string& name, float** ptr, int64_t* rows, int64_t* cols) {
+    SHOWO_CHECK(base_ptr != nullptr, "mm_projector: no buffer for " + name + " (weights not handed over / no backward has run)");
+    if (name == "mm_projector.0.weight") { *ptr = base_ptr + kMmpW0; *rows = kMmpMid; *cols = kMmpIn; return 0; }
+    if (name == "mm_projector.0.bias") { *ptr = base_ptr + kMmpB0; *rows = 1; *cols = kMmpMid; return 0; }
+    if (name == "mm_projector.2.weight") { *ptr = base_ptr + kMmpW2; *rows = kMmpOut; *cols = kMmpMid; return 0; }
+    if (name == "mm_projector.2.bias") { *ptr = base_ptr + kMmpB2; *rows = 1; *cols = kMmpOut; return 0; }
+    SHOWO_CHECK(false, "unknown parameter " + name);
+    return -2;
 }
 
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m,
@@ -804,6 +823,19 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ w, const
 
 int opt_store_master(showo_engine* e, const std::string& name, const float* src_dev, int64_t numel, cudaStream_t st) {
     float* dst; int64_t rows, cols, ld;
+    if (is_mmp_name(name)) {
+        OptState* o = e->opt;
+        if (!o->mmp_master) {
+            SHOWO_TRY(dev_alloc(&o->mmp_master, (size_t)kMmpTotal)); SHOWO_TRY(dev_alloc(&o->mmp_m, (size_t)kMmpTotal));
+            SHOWO_TRY(dev_alloc(&o->mmp_v, (size_t)kMmpTotal));
+            SHOWO_CUDA_OK(cudaMemsetAsync(o->mmp_m, 0, (size_t)kMmpTotal * 4, st));
+            SHOWO_CUDA_OK(cudaMemsetAsync(o->mmp_v, 0, (size_t)kMmpTotal * 4, st));
+        }
+        SHOWO_TRY(mmp_slot(o->mmp_master, name, &dst, &rows, &cols));
+        SHOWO_CHECK(rows * cols == numel, "optimizer: parameter " + name + " has the wrong size");
+        SHOWO_CUDA_OK(cudaMemcpyAsync(dst, src_dev, (size_t)numel * 4, cudaMemcpyDeviceToDevice, st));
+        return 0;
+    }
     SHOWO_TRY(named_slot(e, e->opt->master, true, name, &dst, &rows, &cols, &ld));
     SHOWO_CHECK(rows * cols == numel, "optimizer: parameter " + name + " has the wrong size");
     SHOWO_CUDA_OK(cudaMemcpy2DAsync(dst, (size_t)ld * 4, src_dev, (size_t)cols * 4, (size_t)cols * 4, (size_t)rows, cudaMemcpyDeviceToDevice, st));
@@ -820,7 +852,7 @@ int showo_train_forward(showo_engine_t* e, const int64_t* ids_dev, const float* 
                         const showo_seq_mask_t* masks_host, const int64_t* labels_dev, const int32_t* terms_host,
                         int64_t ignore_index, float* logits_out_dev, float* losses_out_dev, void* stream) {
     SHOWO_TRY(engine_check_ready(e));
-    SHOWO_CHECK((ids_dev != nullptr) != (embeds_dev != nullptr), "train_forward: exactly one of ids / embeds");
+    SHOWO_CHECK(ids_dev != nullptr || embeds_dev != nullptr, "train_forward: needs ids, embeds or both");
     SHOWO_CHECK(B > 0 && L > 0 && L <= e->cfg.max_pos && masks_host && labels_dev && terms_host && losses_out_dev,
                 "train_forward: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
@@ -837,6 +869,9 @@ int showo_train_forward(showo_engine_t* e, const int64_t* ids_dev, const float* 
     if (ids_dev) {
         SHOWO_CUDA_OK(cudaMemcpyAsync(t->ids, ids_dev, (size_t)M * 8, cudaMemcpyDeviceToDevice, st));
         SHOWO_TRY(embed_gather(ids_dev, L, 0, e->embed, t->xs, M, L, D, V, st));
+        // both given = mixed input (train_w_clip_vit.py:532-537): rows with ids < 0 take the caller's vector (mm_projector output);
+        // the backward's embedding scatter-add skips them and dembeds carries their gradient
+        if (embeds_dev) SHOWO_TRY(embed_override(ids_dev, embeds_dev, t->xs, M, D, st));
     } else {
         SHOWO_CUDA_OK(cudaMemcpyAsync(t->xs, embeds_dev, mD * 4, cudaMemcpyDeviceToDevice, st));
     }
@@ -1079,6 +1114,22 @@ int showo_adamw_step(showo_engine_t* e, float lr, float beta1, float beta2, floa
     SHOWO_TRY(upd(gl.fln_g, gl.fln_g, 1, D, D, true, nullptr, e->fln_g, D));
     SHOWO_TRY(upd(gl.fln_b, gl.fln_b, 1, D, D, false, nullptr, e->fln_b, D));
     SHOWO_TRY(upd(gl.embed, gl.embed, V, D, D, true, e->embed, nullptr, D));
+    if (o->mmp_master && e->mmp_grads && e->mmp_grads_valid) {
+        // Showo.mm_projector (train_w_clip_vit.py trains it with the same AdamW groups: weights decayed, biases not)
+        auto updp = [&](int64_t off, int64_t rows, int64_t cols, bool decay, bf16* out16, float* out32) {
+            const int64_t n = rows * cols;
+            const int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
+            adamw_kernel<<<grid, 256, 0, st>>>(o->mmp_master + off, e->mmp_grads + off, o->mmp_m + off, o->mmp_v + off, rows, cols, cols, lr, beta1,
+                                               beta2, eps, decay ? weight_decay : 0.f, bc1, bc2s, out16, out32, cols);
+            note_launch();
+        };
+        updp(kMmpW0, kMmpMid, kMmpIn, true, e->mmp_w0, nullptr);
+        updp(kMmpB0, 1, kMmpMid, false, nullptr, e->mmp_b0);
+        updp(kMmpW2, kMmpOut, kMmpMid, true, e->mmp_w2, nullptr);
+        updp(kMmpB2, 1, kMmpOut, false, nullptr, e->mmp_b2);
+        e->mmp_grads_valid = false;                    // consumed: a step without a projector backward leaves the projector alone
+        ++e->mmp_version;
+    }
     SHOWO_CUDA_OK(cudaGetLastError());
     return engine_refresh_derived(e, st);
 }
@@ -1087,6 +1138,8 @@ int showo_read_param(showo_engine_t* e, const char* name, float* out_dev, int64_
     SHOWO_CHECK(e && e->opt && name && out_dev, "read_param: needs an engine with the optimizer enabled");
     SHOWO_CUDA_OK(cudaSetDevice(e->device));
     float* p; int64_t rows, cols, ld;
+    if (is_mmp_name(name)) { SHOWO_TRY(mmp_slot(e->opt->mmp_master, name, &p, &rows, &cols)); ld = cols; }
+    else
     SHOWO_TRY(named_slot(e, e->opt->master, true, std::string(name), &p, &rows, &cols, &ld));
     SHOWO_CHECK(rows * cols == numel, std::string("read_param: ") + name + " has " + std::to_string(rows * cols) + " elements");
     SHOWO_CUDA_OK(cudaMemcpy2DAsync(out_dev, (size_t)cols * 4, p, (size_t)ld * 4, (size_t)cols * 4, (size_t)rows, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
@@ -1095,12 +1148,69 @@ int showo_read_param(showo_engine_t* e, const char* name, float* out_dev, int64_
 
 int showo_read_grad(showo_engine_t* e, const char* name, float* out_dev, int64_t numel, void* stream) {
     SHOWO_CHECK(e && name && out_dev, "read_grad: null argument");
-    SHOWO_CHECK(e->train && e->train->grads, "read_grad: no backward has run");
     SHOWO_CUDA_OK(cudaSetDevice(e->device));
     float* p = nullptr; int64_t rows = 0, cols = 0, ld = 0;
-    SHOWO_TRY(named_grad(e, name, &p, &rows, &cols, &ld));
+    if (is_mmp_name(name)) {
+        SHOWO_CHECK(e->mmp_grads && e->mmp_grads_valid, "read_grad: no showo_mm_projector_backward has run since the last optimizer step");
+        SHOWO_TRY(mmp_slot(e->mmp_grads, name, &p, &rows, &cols));
+        ld = cols;
+    } else {
+        SHOWO_CHECK(e->train && e->train->grads, "read_grad: no backward has run");
+        SHOWO_TRY(named_grad(e, name, &p, &rows, &cols, &ld));
+    }
     SHOWO_CHECK(numel == rows * cols, std::string("read_grad: ") + name + " has " + std::to_string(rows * cols) + " elements, got " + std::to_string(numel));
     return copy_f32_to_f32_rows(p, ld, out_dev, cols, (int)rows, (int)cols, (cudaStream_t)stream);
+}
+
+// Backward of Showo.mm_projector for the rows of the LAST showo_mm_projector call (train_w_clip_vit.py:599-601 differentiates it through
+// `input_embeddings`): dY [n, 2048] fp32 = the slice of showo_backward's dembeds that the projector's output occupied.
+//   dW2 = dY^T gelu(H),  db2 = colsum dY,  dH = (dY W2) o gelu'(H),  dW0 = dH^T X,  db0 = colsum dH      (H = X W0^T + b0)
+// The CLIP features X are not differentiated (the tower is frozen, train_w_clip_vit.py:199-203).  bf16 operands, fp32 accumulation,
+// fp32 gradients in e->mmp_grads = [w0 | b0 | w2 | b2].
+int showo_mm_projector_backward(showo_engine_t* e, const float* dy_dev, int64_t n, void* stream) {
+    SHOWO_CHECK(e && dy_dev && n > 0, "mm_projector_backward: bad arguments");
+    SHOWO_CUDA_OK(cudaSetDevice(e->device));
+    SHOWO_CHECK(showo_device_count() > 0, "no sm_100 CUDA device visible: libshowo_b200 has no CPU fallback");
+    SHOWO_CHECK(e->mmp_pre && e->mmp_n == n, "mm_projector_backward: differentiates the last showo_mm_projector call, which had " +
+                                                 std::to_string(e->mmp_n) + " rows (got " + std::to_string(n) + ")");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!e->train) e->train = new TrainState();
+    TrainState* t = e->train;
+    SHOWO_CHECK(wgrad_mn() || n <= t->cap_M, "mm_projector_backward: SHOWO_WGRAD_MN=0 needs a training forward of at least as many rows first");
+    if (!e->mmp_grads) SHOWO_TRY(dev_alloc(&e->mmp_grads, (size_t)kMmpTotal));
+    if (!e->mmp_w2t) SHOWO_TRY(dev_alloc(&e->mmp_w2t, (size_t)(kMmpMid * kMmpOut)));
+    if (n > e->mmp_bwd_cap) {
+        SHOWO_CUDA_OK(cudaStreamSynchronize(st));
+        dev_free(e->mmp_dy); dev_free(e->mmp_dmid);
+        SHOWO_TRY(dev_alloc(&e->mmp_dy, (size_t)(n * kMmpOut)));
+        SHOWO_TRY(dev_alloc(&e->mmp_dmid, (size_t)(n * kMmpMid)));
+        e->mmp_bwd_cap = n;
+    }
+    if (e->mmp_w2t_version != e->mmp_version) {       // w2t[j][o] = w2[o][j]: the dgrad GEMM's K-contiguous B operand
+        SHOWO_TRY(transpose_to_bf16<bf16>(e->mmp_w2, kMmpMid, (int)kMmpOut, (int)kMmpMid, e->mmp_w2t, kMmpOut, nullptr, 0, st));
+        e->mmp_w2t_version = e->mmp_version;
+    }
+    const int64_t l0 = launches_total();
+    const int M = (int)n;
+    const int64_t Mp = (int64_t)(M + 127) / 128 * 128;
+    float* G = e->mmp_grads;
+    SHOWO_TRY(f32_to_bf16(dy_dev, e->mmp_dy, n * kMmpOut, st));
+    SHOWO_TRY(wgrad(t, e->mmp_dy, kMmpOut, (int)kMmpOut, e->mmp_mid, kMmpMid, (int)kMmpMid, M, Mp, G + kMmpW2, kMmpMid, G + kMmpB2, st));
+    SHOWO_TRY(gemm_plain(e->mmp_dy, kMmpOut, e->mmp_w2t, kMmpOut, M, (int)kMmpMid, (int)kMmpOut, e->mmp_dmid, kMmpMid, false, st));
+    SHOWO_TRY(gelu_erf_bwd_bf16(e->mmp_dmid, e->mmp_pre, n * kMmpMid, st));
+    SHOWO_TRY(wgrad(t, e->mmp_dmid, kMmpMid, (int)kMmpMid, e->mmp_in, kMmpIn, (int)kMmpIn, M, Mp, G + kMmpW0, kMmpIn, G + kMmpB0, st));
+    e->mmp_grads_valid = true;
+    e->launches_last = launches_total() - l0;
+    return 0;
+}
+
+// the projector's gradient buffer ([w0 | b0 | w2 | b2] fp32): the extra bucket of the data-parallel gradient all-reduce
+int showo_mm_projector_grad_buffer(showo_engine_t* e, float** base_dev, int64_t* numel) {
+    SHOWO_CHECK(e && base_dev && numel, "mm_projector_grad_buffer: null argument");
+    SHOWO_CHECK(e->mmp_grads != nullptr, "mm_projector_grad_buffer: no showo_mm_projector_backward has run");
+    *base_dev = e->mmp_grads;
+    *numel = kMmpTotal;
+    return 0;
 }
 
 int showo_attention_bwd_test(const void* q_dev, const void* k_dev, const void* v_dev, const void* o_dev, const void* do_dev,

@@ -86,15 +86,39 @@ class _PhiForCausalLM(nn.Module):
 
 class _MMProjector(nn.Sequential):
     """Parameter container of Showo.mm_projector (modeling_showo.py:49-54) whose call runs on the engine (showo_mm_projector):
-    `model.mm_projector(images_embeddings)` as inference_mmu.py:131 does it.  Inference only (the reference trains it; its gradient is
-    not part of the engine's backward)."""
+    `model.mm_projector(images_embeddings)` as inference_mmu.py:131 does it.  Under autograd (training/train_w_clip_vit.py:599-601
+    trains the projector through `input_embeddings`) the call is differentiable: backward = showo_mm_projector_backward, the four
+    parameters receive their gradients; the CLIP features themselves are frozen in the reference and get none."""
 
     def __init__(self, owner):
         super().__init__(nn.Linear(1024, 2048), nn.GELU(), nn.Linear(2048, 2048))
         object.__setattr__(self, "_owner", owner)
 
     def forward(self, x):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            if x.requires_grad:
+                raise _lib.ShowoError("mm_projector: the gradient wrt the CLIP features is not provided (the vision tower is frozen in "
+                                      "train_w_clip_vit.py:199-203); detach the features")
+            names = ["mm_projector." + k for k, _ in self.named_parameters()]
+            return _ProjectStep.apply(self._owner, x, names, *self.parameters())
         return self._owner._project(x)
+
+
+class _ProjectStep(torch.autograd.Function):
+    """autograd bridge of Showo.mm_projector: forward = showo_mm_projector (keeps its activations), backward =
+    showo_mm_projector_backward + showo_read_grad.  Plumbing only."""
+
+    @staticmethod
+    def forward(ctx, model, x, names, *params):
+        ctx.model, ctx.names, ctx.params, ctx.dtype = model, names, params, x.dtype
+        return model._project(x)
+
+    @staticmethod
+    def backward(ctx, gy):
+        m = ctx.model
+        m.mm_projector_backward(gy)
+        grads = [m.read_grad(n, like=p) if p.requires_grad else None for n, p in zip(ctx.names, ctx.params)]
+        return (None, None, None, *grads)
 
 
 class _TrainStep(torch.autograd.Function):
@@ -365,9 +389,16 @@ class Showo(nn.Module):
         if input_embeddings is None:
             B, L = input_ids.shape
             ids, emb, dev = self._check_ids(input_ids, "Showo.train_forward"), None, input_ids.device
-        else:
+        elif input_ids is None:
             B, L, _ = input_embeddings.shape
             ids, emb, dev = None, input_embeddings.detach().float().contiguous(), input_embeddings.device
+        else:
+            # both = the mixed rows of train_w_clip_vit.py:532-537 without the torch-side embed / cat: positions with ids >= 0 are looked
+            # up in the engine's table, positions with ids < 0 take input_embeddings[b, t] (the mm_projector output)
+            B, L = input_ids.shape
+            if tuple(input_embeddings.shape[:2]) != (B, L):
+                raise ValueError(f"input_embeddings {tuple(input_embeddings.shape)} does not match input_ids {tuple(input_ids.shape)}")
+            ids, emb, dev = self._check_ids(input_ids, "Showo.train_forward"), input_embeddings.detach().float().contiguous(), input_ids.device
         descs = self._mask_descs(attention_mask, B)
         lab = self._check_ids(labels, "Showo.train_forward(labels)")
         logits = torch.empty(B, L, self.vocab_size, dtype=torch.float32, device=dev) if want_logits else None
@@ -414,27 +445,65 @@ class Showo(nn.Module):
         _lib.check(lib.showo_grad_range(self._engine, int(phase), C.byref(b), C.byref(e_)), "showo_grad_range")
         return int(b.value), int(e_.value)
 
-    def backward_overlapped(self, loss_grads, group=None, comm_stream=None, average: bool = True):
+    def backward_overlapped(self, loss_grads, group=None, comm_stream=None, average: bool = True, input_grad_like=None,
+                            projector_rows=None):
         """Data-parallel backward: runs the phases in order and all-reduces each phase's gradient range on `comm_stream` as soon
         as the phase has been enqueued (per-layer buckets; the layer's bytes move over NCCL while the next layer's backward runs).
+        `input_grad_like` ([B, L, hidden]) asks for the gradient wrt the input embeddings (kept in `self.last_input_grad`);
+        `projector_rows` (an index expression into it, e.g. (slice(4, 8), slice(30, 606))) names the positions the last mm_projector
+        call produced: its backward runs after the embedding phase and its 6.3 M gradients are the last bucket.
         Returns the CUDA event after which every gradient is reduced."""
         import torch.distributed as dist
         dev = self._engine_device
         cur = torch.cuda.current_stream(dev)
         comm = comm_stream or torch.cuda.Stream(dev)
         G = self.grad_buffer()
+        op = dist.ReduceOp.AVG if average else dist.ReduceOp.SUM
         phases = [-1] + list(range(self._dims.n_layers - 1, -1, -1)) + [-2]
+        demb = None
         for ph in phases:
-            self.backward_phase(ph, loss_grads)
+            out = self.backward_phase(ph, loss_grads, input_grad_like)
+            demb = out if out is not None else demb
             ready = torch.cuda.Event()
             ready.record(cur)
             b, e_ = self.grad_range(ph)
             with torch.cuda.stream(comm):
                 comm.wait_event(ready)
-                dist.all_reduce(G[b:e_], op=dist.ReduceOp.AVG if average else dist.ReduceOp.SUM, group=group)
+                dist.all_reduce(G[b:e_], op=op, group=group)
+        self.last_input_grad = demb
+        if projector_rows is not None:
+            if demb is None:
+                raise ValueError("projector_rows needs input_grad_like")
+            self.mm_projector_backward(demb[projector_rows])
+            ready = torch.cuda.Event()
+            ready.record(cur)
+            with torch.cuda.stream(comm):
+                comm.wait_event(ready)
+                dist.all_reduce(self.mm_projector_grad_buffer(), op=op, group=group)
         done = torch.cuda.Event()
         done.record(comm)
         return done
+
+    # ------------------------------------------------------------------ mm_projector (training/train_w_clip_vit.py:599-601)
+    def mm_projector_backward(self, grad_output: torch.Tensor):
+        """showo_mm_projector_backward for the rows of the LAST mm_projector call: grad_output [..., 2048] = the gradient wrt its output
+        (the projector's slice of `backward(..., want_input_grad_like=)`).  Gradients: read_grad("mm_projector.0.weight") ...,
+        mm_projector_grad_buffer() for the data-parallel all-reduce; adamw_step() then updates the four tensors as well."""
+        lib = _lib.require_gpu()
+        g = grad_output.detach().float().contiguous()
+        with torch.cuda.device(self._engine_device):
+            _lib.check(lib.showo_mm_projector_backward(self._engine, _lib.ptr(g), g.numel() // 2048, _lib.current_stream_ptr()),
+                       "showo_mm_projector_backward")
+
+    def mm_projector_grad_buffer(self) -> torch.Tensor:
+        """Zero-copy fp32 view of the projector's gradients [0.weight | 0.bias | 2.weight | 2.bias] (6,295,552 elements)."""
+        lib = _lib.require_gpu()
+        base, n = C.c_void_p(), C.c_int64()
+        _lib.check(lib.showo_mm_projector_grad_buffer(self._engine, C.byref(base), C.byref(n)), "showo_mm_projector_grad_buffer")
+
+        class _View:
+            __cuda_array_interface__ = {"shape": (int(n.value),), "typestr": "<f4", "data": (int(base.value), False), "version": 2}
+        return torch.as_tensor(_View(), device=self._engine_device)
 
     @torch.no_grad()
     def _project(self, x: torch.Tensor) -> torch.Tensor:
@@ -484,6 +553,10 @@ class Showo(nn.Module):
         for k, p in self.showo.named_parameters():
             p.copy_(self.read_param("showo." + k, like=p))
         self._engine_versions = {"showo." + k: self._param_key(p) for k, p in self.showo.named_parameters()}
+        if self.w_clip_vit:
+            for k, p in self.mm_projector.named_parameters():
+                p.copy_(self.read_param("mm_projector." + k, like=p))
+            self._engine_versions.update({"mm_projector." + k: self._param_key(p) for k, p in self.mm_projector.named_parameters()})
 
     def read_grad(self, name: str, like: Optional[torch.Tensor] = None, shape=None):
         """Gradient of one parameter (reference state_dict name) as a fresh fp32 tensor."""

@@ -268,3 +268,166 @@ def test_engine_adamw_matches_torch_adamw(dev):
     k_w, k_b = "showo.model.layers.0.input_layernorm.weight", "showo.model.layers.0.input_layernorm.bias"
     assert not torch.equal(m.read_param(k_w, like=ref[k_w]), W[k_w].to(dev)) and not torch.equal(m.read_param(k_b, like=ref[k_b]), W[k_b].to(dev))
     _record("adamw_vs_torch", {"worst_rel_param_diff": worst, "losses": losses})
+
+
+def test_mm_projector_backward_against_torch_autograd(dev):
+    """Showo.mm_projector under autograd (training/train_w_clip_vit.py:599-601 trains it through `input_embeddings`): the drop-in's
+    call is differentiable, its backward is showo_mm_projector_backward (two weight-gradient GEMMs on token-major operands, one dgrad
+    GEMM against the transposed 2.weight, exact-erf GELU derivative), and the four parameters receive gradients within bf16 tolerance of
+    torch fp32 autograd on the same parameters.  Row count 117: not a multiple of the GEMMs' 128-wide token block.  Then the
+    engine-side AdamW moves the four tensors exactly like torch.optim.AdamW (weights decayed, biases not)."""
+    torch.manual_seed(5)
+    m = showo_b200.Showo(True, 58498, 50295, phi_dims=FX.TINY).to(dev)
+    with torch.no_grad():
+        for p in m.mm_projector.parameters():
+            if p.dim() == 1:
+                p.add_(0.05 * torch.randn_like(p))
+    x = torch.randn(3, 39, 1024, device=dev)
+    gy = torch.randn(3, 39, 2048, device=dev) * 0.1
+    out = m.mm_projector(x)
+    assert out.requires_grad
+    (out * gy).sum().backward()
+    seq = torch.nn.Sequential(torch.nn.Linear(1024, 2048), torch.nn.GELU(), torch.nn.Linear(2048, 2048)).to(dev)
+    seq.load_state_dict({k: v.detach().clone() for k, v in m.mm_projector.state_dict().items()})
+    (seq(x) * gy).sum().backward()
+    table = {}
+    for (k, p), q in zip(m.mm_projector.named_parameters(), seq.parameters()):
+        assert p.grad is not None and torch.isfinite(p.grad).all(), k
+        table[k] = float((p.grad - q.grad).norm() / q.grad.norm())
+        assert torch.equal(p.grad, m.read_grad("mm_projector." + k, like=p)), k
+    print("mm_projector gradients, rel L2 vs torch fp32:", {k: round(v, 4) for k, v in table.items()})
+    _record("mm_projector_backward", table)
+    assert max(table.values()) < 0.02, table
+    with torch.no_grad():                       # no autograd: the plain engine call, same values
+        assert torch.equal(m.mm_projector(x), out.detach())
+    with pytest.raises(_lib.ShowoError):
+        m.mm_projector(x.clone().requires_grad_(True))      # the CLIP features are frozen in the reference: no gradient for them
+    with pytest.raises(_lib.ShowoError):
+        m.mm_projector_backward(gy[:2])                      # differentiates the LAST call: row count must match
+
+    # ---- optimizer: engine AdamW on the projector vs torch.optim.AdamW fed with the engine's gradients
+    m2 = showo_b200.Showo(True, 58498, 50295, phi_dims=FX.TINY).to(dev)
+    m2.load_state_dict(m.state_dict())
+    m2.enable_optimizer()
+    ref = {k: p.detach().clone().requires_grad_(True) for k, p in m2.mm_projector.named_parameters()}
+    hp = dict(lr=1e-3, betas=(0.9, 0.999), eps=1e-8)
+    opt = torch.optim.AdamW([{"params": [p for n, p in ref.items() if "bias" not in n], "weight_decay": 0.01},
+                             {"params": [p for n, p in ref.items() if "bias" in n], "weight_decay": 0.0}], **hp)
+    dims = O.PhiDims(**FX.TINY)
+    ids, mask, labels, sizes = FX.train_batch(VOC)
+    descs = M.descriptors_from_dense(mask.to(dev))
+    terms = m2._loss_terms(ids.shape[0], ids.shape[1], *sizes, 128)
+    for step in range(2):
+        m2.train_forward(ids.to(dev), None, descs, labels.to(dev), terms, want_logits=False)      # adamw_step wants backbone gradients too
+        m2.backward(FX.TRAIN_COEFF)
+        with torch.no_grad():
+            m2.mm_projector(x)
+        m2.mm_projector_backward(gy)
+        for k, p in ref.items():
+            p.grad = m2.read_grad("mm_projector." + k, like=p)
+        opt.step()
+        m2.adamw_step(weight_decay=0.01, **hp)
+        for k, p in ref.items():
+            got = m2.read_param("mm_projector." + k, like=p)
+            err = float((got - p.detach()).abs().max() / (p.detach().abs().max() + 1e-12))
+            assert err < 2e-6, (step, k, err)
+    # the projector's bf16 working copy follows the masters: its output moved, and matches torch on the updated parameters
+    seq.load_state_dict({k: p.detach() for k, p in ref.items()})
+    with torch.no_grad():
+        new = m2._project(x)
+        want = seq(x)
+    assert (new - want).abs().max().item() < 0.01 * want.abs().max().item() and not torch.equal(new, out.detach())
+    # a step without a projector backward leaves the projector alone
+    m2.train_forward(ids.to(dev), None, descs, labels.to(dev), terms, want_logits=False)
+    m2.backward(FX.TRAIN_COEFF)
+    before = m2.read_param("mm_projector.2.weight", like=ref["2.weight"])
+    m2.adamw_step(weight_decay=0.01, **hp)
+    assert torch.equal(before, m2.read_param("mm_projector.2.weight", like=ref["2.weight"]))
+
+
+def test_train_step_mixed_ids_and_embeddings_input(tiny_train, dev):
+    """showo_train_forward with BOTH ids and embeddings = the rows of train_w_clip_vit.py:532-537 without the torch-side embed / cat:
+    positions with ids >= 0 come from the engine's table, positions with ids < 0 take the caller's vector (the mm_projector output).
+    Losses, the embedding-table gradient (scatter-add over the ids >= 0 positions only) and the gradient handed back for the ids < 0
+    positions against the oracle differentiated by autograd with the same mixed input."""
+    dims, W, m = tiny_train
+    ids, mask, labels, sizes = FX.train_batch(VOC)
+    B, L = ids.shape
+    g = torch.Generator().manual_seed(17)
+    vis = torch.zeros(B, L, dtype=torch.bool)
+    vis[-sizes[2]:, 3:60] = True                                   # a visual span inside the mmu rows
+    given = torch.randn(B, L, dims.hidden, generator=g) * 0.02
+    ids_mixed = torch.where(vis, torch.full_like(ids, -1), ids)
+    labels = torch.where(vis, torch.full_like(labels, -100), labels)
+    descs = M.descriptors_from_dense(mask.to(dev))
+    terms = m._loss_terms(B, L, *sizes, 128)
+    _, losses = m.train_forward(ids_mixed.to(dev), given.to(dev), descs, labels.to(dev), terms, want_logits=False)
+    demb = m.backward(FX.TRAIN_COEFF, want_input_grad_like=given.to(dev)).cpu()
+    # oracle: the same mixed embeddings built in torch, differentiated wrt the table and the given vectors
+    Wg = {k: v.clone().requires_grad_(True) for k, v in W.items()}
+    gv = given.clone().requires_grad_(True)
+    emb = torch.where(vis[..., None], gv, Wg["showo.model.embed_tokens.weight"][ids])
+    logits = O.showo_logits(Wg, dims, input_embeddings=emb, add_mask=mask)
+    l = O.showo_losses(logits, labels, *sizes, 128)
+    (FX.TRAIN_COEFF[0] * l[0] + FX.TRAIN_COEFF[1] * l[1] + FX.TRAIN_COEFF[2] * l[2]).backward()
+    assert np.allclose(losses[:, 0].cpu().numpy(), [float(v) for v in l], rtol=2e-3)
+    k = "showo.model.embed_tokens.weight"
+    ge = m.read_grad(k, like=W[k]).cpu()
+    rel_e = float((ge - Wg[k].grad).norm() / Wg[k].grad.norm())
+    rel_v = float((demb[vis] - gv.grad[vis]).norm() / gv.grad[vis].norm())
+    print(f"mixed input: embedding-table gradient rel L2 {rel_e:.4f}, visual-span gradient rel L2 {rel_v:.4f}")
+    _record("mixed_input", {"embed_rel_l2": rel_e, "visual_rel_l2": rel_v})
+    assert rel_e < REL_L2_TOL and rel_v < REL_L2_TOL
+    k2 = "showo.model.layers.0.mlp.fc1.weight"
+    assert float((m.read_grad(k2, like=W[k2]).cpu() - Wg[k2].grad).norm() / Wg[k2].grad.norm()) < REL_L2_TOL
+
+
+def test_train_w_clip_vit_call_shape_end_to_end(dev):
+    """The training step as training/train_w_clip_vit.py:532-537,599-612 writes it, on a 1-layer model of the real width (the projector's
+    output is 2048 wide): `model.showo.model.embed_tokens(ids)` and `model.mm_projector(feats)` are called from outside, concatenated
+    into `input_embeddings`, `model(...)` returns the losses under autograd and `loss.backward()` reaches the backbone (showo_backward),
+    the projector (showo_mm_projector_backward, through the gradient of `input_embeddings`) and the embedding table (torch's own
+    nn.Embedding backward, as in the reference).  Compared with the oracle's forward differentiated by autograd on the same weights."""
+    dims = O.PhiDims(hidden=2048, n_layers=1, n_heads=32, ffn=2048)
+    W = O.make_showo_weights(dims, seed=8, w_clip_vit=True)
+    m = showo_b200.Showo(True, dims.vocab_size, VOC.llm_vocab_size, phi_dims=dict(hidden=2048, n_layers=1, n_heads=32, ffn=2048)).to(dev)
+    m.load_state_dict(W, strict=True)
+    B, sysl, n_vis, n_txt = 2, 4, 576, 40
+    L = 1 + sysl + 1 + n_vis + 1 + n_txt
+    r = FX.rng(31)
+    ids = torch.from_numpy(r.integers(0, 50257, size=(B, L)).astype("int64"))
+    feats = torch.from_numpy(r.standard_normal(size=(B, n_vis, 1024), dtype=np.float32))
+    labels = torch.full((B, L), -100, dtype=torch.int64)
+    labels[:, L - n_txt:] = ids[:, L - n_txt:]
+    b0 = 1 + sysl + 1
+    allowed = O.mask_allowed_mmu_vit(B, L, system_prompt_len=sysl, n_vis=n_vis)
+    mask = O.additive_from_allowed(allowed)
+
+    # ---- the drop-in, reference call shape
+    ids_d, feats_d = ids.to(dev), feats.to(dev)
+    emb_text = m.showo.model.embed_tokens(ids_d)
+    vis = m.mm_projector(feats_d)
+    input_embeddings = torch.cat([emb_text[:, :b0], vis, emb_text[:, b0 + n_vis:]], dim=1)
+    logits, l_t2i, l_lm, l_mmu = m(None, input_embeddings=input_embeddings, attention_mask=mask.to(dev), labels=labels.to(dev),
+                                   batch_size_t2i=0, batch_size_lm=0, batch_size_mmu=B, max_seq_length=128)
+    l_mmu.backward()
+    # ---- the oracle
+    Wg = {k: v.clone().requires_grad_(True) for k, v in W.items()}
+    e_ref = Wg["showo.model.embed_tokens.weight"][ids]
+    h = torch.nn.functional.gelu(feats @ Wg["mm_projector.0.weight"].T + Wg["mm_projector.0.bias"])
+    v_ref = h @ Wg["mm_projector.2.weight"].T + Wg["mm_projector.2.bias"]
+    lg = O.showo_logits(Wg, dims, input_embeddings=torch.cat([e_ref[:, :b0], v_ref, e_ref[:, b0 + n_vis:]], dim=1), add_mask=mask)
+    ref_l = O.showo_losses(lg, labels, 0, 0, B, 128)
+    ref_l[2].backward()
+    print("loss_mmu", float(l_mmu), "oracle", float(ref_l[2]))
+    assert abs(float(l_mmu) / float(ref_l[2]) - 1) < 2e-3
+    table = {}
+    p = dict(m.named_parameters())
+    for k in ("mm_projector.0.weight", "mm_projector.0.bias", "mm_projector.2.weight", "mm_projector.2.bias",
+              "showo.model.embed_tokens.weight", "showo.model.layers.0.self_attn.q_proj.weight", "showo.model.layers.0.mlp.fc2.weight",
+              "showo.lm_head.weight"):
+        assert p[k].grad is not None and torch.isfinite(p[k].grad).all(), k
+        table[k] = float((p[k].grad.cpu() - Wg[k].grad).norm() / Wg[k].grad.norm())
+    print("train_w_clip_vit flow, rel L2 vs oracle autograd:", {k: round(v, 4) for k, v in table.items()})
+    _record("train_w_clip_vit_flow", table)
+    assert max(table.values()) < REL_L2_TOL, table
