@@ -8,6 +8,7 @@ from .schedules import cosine_schedule, get_mask_chedule, linear_schedule, step_
 from .showo_model import Showo  # noqa: F401
 from .magvit_model import MAGVITv2  # noqa: F401
 from . import masks  # noqa: F401
+from . import editing  # noqa: F401  (inpainting / extrapolation flows of inference_t2i.py on top of t2i_generate)
 
 
 def __getattr__(name):          # CLIPVisionTower pulls in `transformers`: import it only when asked for

@@ -185,7 +185,42 @@ class UniversalPrompting:
                                          timesteps, rand, probs, _seed())
         return ids, lab, mp, descs
 
+    def t2i_gen_prompt(self, text_ids: Sequence[Sequence[int]], image_ids):
+        """:92-123, the rows of the generation scripts (inference_t2i.py:115,118,250,253): left-padded
+        [pad.. <|t2i|> bos text eos] (max_text_len wide, truncated with a closing eos when longer) + <|soi|> + image ids + <|eoi|>;
+        an empty caption is [bos] (the unconditional row).  Returns (input_ids [B, L], text attention masks [B, max_text_len]).
+        Host-side assembly on the caller's device, like the reference: this runs once per generation call, not per step."""
+        tk = self.text_tokenizer
+        dev = image_ids.device
+        T = self.max_text_len
+        rows, masks = [], []
+        for i, t in enumerate(text_ids):
+            t = [int(v) for v in t]
+            if len(t) == 0:
+                t = [tk.bos_token_id]
+            elif t[0] != tk.bos_token_id:
+                t = [tk.bos_token_id] + t
+            text_ids[i] = t                                   # the reference rewrites the caller's list the same way
+            ids = [int(self.sptids_dict["<|t2i|>"])] + t + [tk.eos_token_id]
+            if T >= len(ids):
+                n_pad = T - len(ids)
+                ids = [self.pad_id] * n_pad + ids
+                # the reference computes the pad count AFTER padding (T - len(padded) = 0): the mask row is all ones, kept
+                msk = [1] * len(ids)
+            else:
+                ids = ids[:T - 1] + [tk.eos_token_id]
+                msk = [1] * len(ids)
+            rows.append(torch.cat([torch.tensor(ids, dtype=torch.int64, device=dev), self.sptids_dict["<|soi|>"].to(dev),
+                                   image_ids[i].to(torch.int64), self.sptids_dict["<|eoi|>"].to(dev)]))
+            masks.append(torch.tensor(msk, dtype=torch.int64, device=dev))
+        return torch.stack(rows), torch.stack(masks)
+
     def __call__(self, input, task, padding=True, config=None):
         if task == "t2i":
             return self.t2i_prompt(input[0], input[1], input[2])
-        raise NotImplementedError(f"task {task!r}: only the t2i training rows are produced on the device (SURVEY 8 f-2)")
+        if task == "t2i_gen":
+            text = input[0]
+            if len(text) and isinstance(text[0], str):        # :426-428: the reference tokenises here
+                text = self.text_tokenizer(list(text))["input_ids"]
+            return self.t2i_gen_prompt([list(t) for t in text], input[1])
+        raise NotImplementedError(f"task {task!r}: only the t2i rows (training: on the device, generation: t2i_gen) are provided")

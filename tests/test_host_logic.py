@@ -6,6 +6,7 @@ import os
 import subprocess
 import sys
 
+import numpy as np
 import pytest
 import torch
 
@@ -240,3 +241,61 @@ def test_train_inputs_host_side_contract():
         TI.mask_or_random_replace_tokens(codes, 99, Cfg(training=Cfg(eval_mask_ratios=[0.5])), get_mask_chedule("cosine"), is_train=False)
     with pytest.raises(ShowoError):                       # CPU tensors: the producer only exists on the device
         TI.mask_or_random_replace_tokens(codes, 99, Cfg(training=Cfg()), get_mask_chedule("cosine"))
+
+
+# ------------------------------------------------------------------------------------------------ f-1: inpainting / extrapolation
+def _editing_case(name):
+    import editing_stubs as ES
+    from showo_b200 import editing, train_inputs as TI
+    case = ES.CASES[name]
+    cfg = ES.make_config(case)
+    up = TI.UniversalPrompting(ES.FakeTokenizer(), max_text_len=128, ignore_id=-100, cond_dropout_prob=0.1)
+    model, vq = ES.StubShowo(cfg.model.showo.num_vq_tokens), ES.StubVQ()
+    img = ES.pixels(case["seed"], case["R"])
+    if case["mode"] == "inpainting":
+        editing.inpaint(model, vq, up, [case["prompt"]] * case["B"], img, ES.mask_pixels(case["seed"] + 100, case["R"]), cfg, mask_token_id=ES.MASK_ID)
+    else:
+        prompts = [p for p in case["prompt"].split(" *** ") if p]
+        dirs = [d for d in case["direction"].split(" *** ") if d]
+        editing.extrapolate(model, vq, up, prompts, dirs, img, cfg, offset=case["offset"], mask_token_id=ES.MASK_ID)
+    return model, vq
+
+
+@pytest.mark.parametrize("name", ["inpaint_cfg", "inpaint_nocfg", "extra_right_right", "extra_left_left", "extra_up", "extra_up_up"])
+def test_editing_flows_equal_the_reference_script_blocks(name):
+    """show-o_b200/editing.py (inpainting, extrapolation) against tests/golden/editing.npz = the reference's own script lines
+    (inference_t2i.py:80-284) executed on the same stub models: every t2i_generate call receives the same input ids, unconditional ids
+    and omni-mask descriptors, and decode_code the same token grid and shape, bit for bit."""
+    import fixtures as FX
+    z = FX.load("editing.npz")
+    model, vq = _editing_case(name)
+    assert len(model.calls) == int(z[f"{name}_n_calls"])
+    for i, c in enumerate(model.calls):
+        assert np.array_equal(c["input_ids"].numpy(), z[f"{name}_ids{i}"]), (name, i)
+        if f"{name}_uncond{i}" in z.files:
+            assert np.array_equal(c["uncond_input_ids"].numpy(), z[f"{name}_uncond{i}"]), (name, i)
+        else:
+            assert c["uncond_input_ids"] is None
+        assert np.array_equal(np.asarray(c["attention_mask"], dtype=np.int32), z[f"{name}_descs{i}"]), (name, i)
+        assert c["kw"]["seq_len"] == model.N and c["kw"]["timesteps"] == 4
+    ids, shape = vq.decoded[-1]
+    assert np.array_equal(ids.numpy(), z[f"{name}_decoded"])
+    assert tuple(int(v) for v in z[f"{name}_shape"]) == (tuple(shape) if shape is not None else (-1, -1))
+
+
+def test_editing_downward_extrapolation_runs_where_the_reference_script_raises():
+    """inference_t2i.py:274-275 glues `image_left_part` along the row axis for the downward direction: the golden records that the
+    script raises; editing.extrapolate implements the evident intent (mirror image of 'up') and is checked against it by symmetry."""
+    import editing_stubs as ES
+    import fixtures as FX
+    from showo_b200 import editing
+    assert int(FX.load("editing.npz")["down_raises"]) == 1
+    g = torch.arange(2 * 8 * 8).reshape(2, 8, 8) % 8192
+    mid = 777
+    for off in (0, 1):
+        up_c = editing.extrapolation_canvas(g, "up", off, mid, 8)
+        dn_c = editing.extrapolation_canvas(g.flip(1), "down", off, mid, 8)
+        assert torch.equal(up_c, dn_c.flip(1))
+        gen = (torch.arange(2 * 64).reshape(2, 8, 8) * 3) % 8192
+        assert torch.equal(editing.extrapolation_merge(g, gen, "up", off, 8), editing.extrapolation_merge(g.flip(1), gen.flip(1), "down", off, 8).flip(1))
+        assert editing.extrapolation_merge(g, gen, "down", off, 8).shape == (2, 8 + 4 + off, 8)
