@@ -241,6 +241,27 @@ SHOWO_API int magvit_decode_code_u8(magvit_engine_t* m, const int64_t* ids_dev, 
 SHOWO_API int magvit_get_code(magvit_engine_t* m, const float* pixels_dev, int B, int R, int64_t* ids_out_dev, void* stream);
 SHOWO_API int64_t magvit_kernel_launches(magvit_engine_t* m);
 
+/* ---------------------------------------------------------------- CLIP ViT vision tower (models/clip_encoder.py:6-51)
+ * The frozen encoder in front of the w_clip_vit MMU path: CLIPVisionTower.forward = transformers' CLIPVisionModel(images,
+ * output_hidden_states=True).hidden_states[-2][:, 1:] (inference_mmu.py:100-131, training/train_w_clip_vit.py:532-537).  The network
+ * is third-party code (transformers, pinned 4.41.1 in requirements.txt; openai/clip-vit-large-patch14-336); oracle/clip_oracle.py
+ * restates it and is pinned to the live library.  head_dim must be 64, hidden a multiple of 128 (<= 2048). */
+typedef struct clip_engine clip_engine_t;
+typedef struct {
+    int32_t image_size, patch_size;   /* 336, 14 */
+    int32_t hidden, n_layers, n_heads, ffn;   /* 1024, 24, 16, 4096 */
+    float ln_eps;                     /* 1e-5 */
+} clip_config_t;
+SHOWO_API int clip_engine_create(const clip_config_t* cfg, int device, clip_engine_t** out);
+SHOWO_API int clip_engine_destroy(clip_engine_t* e);
+/* one fp32 tensor of CLIPVisionModel.state_dict() ("vision_model.encoder.layers.3.self_attn.q_proj.weight", ...) */
+SHOWO_API int clip_load_weight(clip_engine_t* e, const char* name, const float* data, int64_t numel, int is_device);
+SHOWO_API int clip_weights_complete(clip_engine_t* e);
+/* pixels_dev [B, 3, S, S] fp32 (image-processor output) -> out_dev fp32 [B, T - 1, hidden] (drop_cls != 0, the reference's
+ * select_feature 'patch') or [B, T, hidden] ('cls_patch'); select_layer indexes hidden_states like the reference (-2). */
+SHOWO_API int clip_forward(clip_engine_t* e, const float* pixels_dev, int B, int select_layer, int drop_cls, float* out_dev, void* stream);
+SHOWO_API int64_t clip_kernel_launches(clip_engine_t* e);
+
 /* ---------------------------------------------------------------- raw kernels, exported for the parity tests */
 /* C[M,N] (+epilogue) = A[M,K] bf16 * B[N,K]^T bf16 on tcgen05; epi 0: bf16 out = acc+bias (gelu_new on cols >=
  * gelu_from), 1: f32 out = resid + acc + bias, 2: f32 out = acc + bias.  block_n 0 = auto.

@@ -28,6 +28,11 @@ class Config(C.Structure):
                 ("codebook_size", C.c_int32)]
 
 
+class ClipConfig(C.Structure):
+    _fields_ = [("image_size", C.c_int32), ("patch_size", C.c_int32), ("hidden", C.c_int32), ("n_layers", C.c_int32),
+                ("n_heads", C.c_int32), ("ffn", C.c_int32), ("ln_eps", C.c_float)]
+
+
 _P = C.c_void_p
 _I = C.c_int
 _I64 = C.c_int64
@@ -76,6 +81,12 @@ _PROTOS = {
     "magvit_decode_code_u8": (_I, [_P, _P, _I, _I, _I, _P, _P]),
     "magvit_get_code": (_I, [_P, _P, _I, _I, _P, _P]),
     "magvit_kernel_launches": (_I64, [_P]),
+    "clip_engine_create": (_I, [C.POINTER(ClipConfig), _I, C.POINTER(_P)]),
+    "clip_engine_destroy": (_I, [_P]),
+    "clip_load_weight": (_I, [_P, C.c_char_p, _P, _I64, _I]),
+    "clip_weights_complete": (_I, [_P]),
+    "clip_forward": (_I, [_P, _P, _I, _I, _I, _P, _P]),
+    "clip_kernel_launches": (_I64, [_P]),
     "showo_gemm_bf16": (_I, [_P, _I64, _P, _I64, _I, _I, _I, _P, _I64, _P, _P, _I64, _I, _I, _I, _P]),
     "showo_attention_test": (_I, [_P, _I64, _I, _I, _I, _I, _P, _P, _P, _P, _F, _F, _I, _P, _P, _I, _I,
                                   C.POINTER(SeqMask), _P]),

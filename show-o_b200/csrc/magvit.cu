@@ -498,7 +498,11 @@ static int attnblock(magvit_engine* m, const std::string& p, int& X, int NB, int
 static int decode_impl(magvit_engine* m, const int64_t* ids, int B, int h, int w, float* out_nchw, uint8_t* out_u8,
                        cudaStream_t st) {
     SHOWO_CHECK(m && ids && B > 0 && h > 0 && w > 0, "magvit decode: bad arguments");
-    SHOWO_CHECK(h >= 8 && w >= 16 && (h % 8) == 0 && (w % 16) == 0, "magvit decode: grid must be a multiple of 8 x 16");
+    // any grid the extrapolation mode produces (inference_t2i.py:274-276, e.g. 16 x 25 with offset 1): the implicit-GEMM convolutions
+    // take partial 8 x 16 pixel tiles (TMA zero fill = the padding, stores masked); the mid-block attention reads its [hw, hw]
+    // probabilities as a bf16 GEMM operand, whose row stride has to be a multiple of 16 bytes
+    SHOWO_CHECK((w >= 16 || (w >= 1 && (w & (w - 1)) == 0)) && ((int64_t)h * w) % 8 == 0,
+                "magvit decode: grid width must be >= 16 (or a power of two) and h * w a multiple of 8");
     SHOWO_CUDA_OK(cudaSetDevice(m->device));
     SHOWO_TRY(magvit_weights_complete(m));
     const int64_t l0 = launches_total();

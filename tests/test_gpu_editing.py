@@ -125,7 +125,17 @@ def test_extrapolation_flow_end_to_end(engines, dev):
     d = (images[:1].cpu() - ref).abs()
     print(f"extrapolation: decode of the 16 x 32 grid vs oracle: max {d.max():.4f} mean {d.mean():.5f}")
     assert d.mean().item() < 0.012 and d.max().item() < 0.25
-    # upwards with an offset: 16x16 -> (16 + 8 + 2) x 16
+    # upwards with an offset: 16x16 -> (16 + 8 + 2) x 16; to the left with an odd offset: 16 x 25 -- grids that are no multiple of the
+    # convolution kernel's 8 x 16 pixel tile, decoded against the oracle
     grid_u, img_u = editing.extrapolate(m, vq, up, ["sky"], ["up"], image, cfg, offset=2, mask_token_id=VOC.mask_token_id)
     assert grid_u.shape == (2, 26, 16) and img_u.shape == (2, 3, 416, 256)
     assert torch.equal(grid_u[:, 10:, :], codes.expand(2, -1, -1))
+    grid_l, img_l = editing.extrapolate(m, vq, up, ["hills"], ["left"], image, cfg, offset=1, mask_token_id=VOC.mask_token_id)
+    assert grid_l.shape == (2, 16, 25) and img_l.shape == (2, 3, 256, 400)
+    assert torch.equal(grid_l[:, :, 9:], codes.expand(2, -1, -1))
+    for g_, im_ in ((grid_u, img_u), (grid_l, img_l)):
+        with torch.no_grad():
+            ref = MO.decode_code(g_[:1].reshape(1, -1).cpu(), MO.make_magvit_weights(1), shape=tuple(g_.shape[1:]))
+        d = (im_[:1].cpu() - ref).abs()
+        print(f"extrapolation: decode of the {g_.shape[1]} x {g_.shape[2]} grid vs oracle: max {d.max():.4f} mean {d.mean():.5f}")
+        assert d.mean().item() < 0.012 and d.max().item() < 0.25

@@ -203,21 +203,28 @@ def test_from_pretrained_reads_single_sharded_and_bin_checkpoints(tmp_path):
         check(dr)
 
 
-def test_clip_vision_tower_delegate_selects_penultimate_patch_features():
-    """`from models import ... CLIPVisionTower` surface (models/clip_encoder.py:39-51): penultimate layer, CLS dropped."""
+def test_clip_vision_tower_surface_without_gpu():
+    """`from models import ... CLIPVisionTower` surface (models/clip_encoder.py:6-82) of the engine-backed tower: construction from a
+    CLIPVisionConfig / dims, the reference's properties, weights kept under CLIPVisionModel.state_dict() names -- and no CPU fallback:
+    the forward raises without an sm_100 device."""
     from transformers import CLIPVisionConfig
-    from showo_b200 import CLIPVisionTower
-    cfg = CLIPVisionConfig(hidden_size=32, intermediate_size=64, num_hidden_layers=3, num_attention_heads=2, image_size=28, patch_size=14)
-    torch.manual_seed(0)
+    from oracle import clip_oracle as CO
+    from showo_b200 import CLIPVisionTower, ShowoError
+    cfg = CLIPVisionConfig(hidden_size=128, intermediate_size=256, num_hidden_layers=3, num_attention_heads=2, image_size=56, patch_size=14)
     tower = CLIPVisionTower(cfg)
-    x = torch.randn(2, 3, 28, 28)
-    f = tower(x)
-    assert f.shape == (2, 4, 32) and tower.num_patches == 4 and tower.hidden_size == 32
-    ref = tower.vision_tower(x, output_hidden_states=True).hidden_states[-2][:, 1:]
-    assert torch.equal(f, ref)
+    assert tower.num_patches == 16 and tower.num_patches_per_side == 4 and tower.hidden_size == 128 and tower.config is cfg
+    assert tower.select_layer == -2 and tower.select_feature == "patch" and not tower.is_loaded
+    assert tower.dummy_feature.shape == (1, 128) and tower.dtype == torch.float32
     assert all(not p.requires_grad for p in tower.parameters())
-    fl = tower([x[0], x[1]])
-    assert torch.allclose(torch.cat(fl), f, atol=1e-6)
+    tower.load_weights(CO.make_clip_weights(CO.ClipDims(image_size=56, patch_size=14, hidden=128, n_layers=3, n_heads=2, ffn=256)))
+    assert tower.is_loaded
+    if not torch.cuda.is_available():
+        with pytest.raises(ShowoError):
+            tower(torch.randn(1, 3, 56, 56))
+    with pytest.raises(ValueError):                       # head_dim must be 64 on the engine
+        CLIPVisionTower(CLIPVisionConfig(hidden_size=32, intermediate_size=64, num_hidden_layers=1, num_attention_heads=2, image_size=28, patch_size=14))
+    d = CLIPVisionTower(dict(image_size=336, patch_size=14, hidden=1024, n_layers=24, n_heads=16, ffn=4096))
+    assert d.num_patches == 576 and d.config.hidden_size == 1024
 
 
 def test_train_inputs_host_side_contract():

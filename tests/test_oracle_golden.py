@@ -220,3 +220,33 @@ def test_train_input_oracle_against_reference_golden():
                                                task=50300, soi=50296, eoi=50297, cond_dropout_prob=drop)
         assert np.array_equal(ids, z[f"{name}_ids"]) and np.array_equal(labels, z[f"{name}_labels"]) and np.array_equal(masks, z[f"{name}_masks"])
         assert np.array_equal(TO.t2i_descriptors(ids, 50295, 50296, 50297), z[f"{name}_descs"])
+
+
+# ------------------------------------------------------------------------------------------------ CLIP ViT tower oracle
+@pytest.mark.parametrize("geo", [dict(image_size=56, patch_size=14, hidden=128, n_layers=3, n_heads=2, ffn=256),
+                                 dict(image_size=70, patch_size=14, hidden=256, n_layers=4, n_heads=4, ffn=512)])
+def test_clip_oracle_equals_the_live_transformers_model(geo):
+    """oracle/clip_oracle.py restates transformers' CLIPVisionModel (the third-party network behind models/clip_encoder.py, pinned
+    4.41.1 in the reference's requirements): pinned here to the LIVE library of this image on the same state_dict -- every entry of
+    hidden_states to 1e-5, and the tower's feature selection (hidden_states[-2], CLS dropped) exactly as clip_encoder.py:29-37."""
+    transformers = pytest.importorskip("transformers")
+    from oracle import clip_oracle as CO
+    d = CO.ClipDims(**geo)
+    cfg = transformers.CLIPVisionConfig(hidden_size=d.hidden, intermediate_size=d.ffn, num_hidden_layers=d.n_layers, num_attention_heads=d.n_heads,
+                                        image_size=d.image_size, patch_size=d.patch_size)
+    assert cfg.hidden_act == "quick_gelu" and cfg.layer_norm_eps == d.ln_eps
+    m = transformers.CLIPVisionModel(cfg).eval()
+    W = CO.make_clip_weights(d, seed=2)
+    assert set(k for k in m.state_dict() if "position_ids" not in k) == set(W)
+    m.load_state_dict(W, strict=False)
+    x = torch.randn(2, 3, d.image_size, d.image_size, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        ref = m(x, output_hidden_states=True).hidden_states
+        got = CO.hidden_states(x, W, d)
+    assert len(ref) == len(got) == d.n_layers + 1
+    for a, b in zip(ref, got):
+        assert (a - b).abs().max().item() < 1e-5
+    with torch.no_grad():
+        f = CO.tower_features(x, W, d)
+    assert f.shape == (2, d.n_tokens - 1, d.hidden) and torch.equal(f, got[-2][:, 1:])
+    assert torch.equal(CO.tower_features(x, W, d, select_feature="cls_patch"), got[-2])
