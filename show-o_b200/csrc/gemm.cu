@@ -106,6 +106,14 @@ static int gemm_cta_group() {
     return v;
 }
 
+// SHOWO_GEMM_ORDER=0: always sweep M first (the first version); default 1 = sweep N first when A is the larger operand and the tiles
+// need more than one wave (GemmParams::n_fast)
+static bool gemm_order_auto() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SHOWO_GEMM_ORDER"); v = (e && atoi(e) == 0) ? 0 : 1; }
+    return v == 1;
+}
+
 // 2-D bf16 tensor map with 128B swizzle for other TMA users (attention_tc.cu): dims = {inner, rows}, row stride in bytes
 int make_tmap_2d(void* out_cutensormap, const void* ptr, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes,
                  uint32_t box_inner, uint32_t box_rows) {
@@ -204,6 +212,7 @@ static int gemm_bn(const GemmArgs& a, GemmEpi epi, cudaStream_t st) {
         p.ln_xb = a.ln_xb; p.ln_xb_ld = a.ln_xb_ld; p.ln_part_out = a.ln_part;
     }
     const int tiles = cdiv(cdiv(a.M, 128), CL) * cdiv(a.N, BN);
+    p.n_fast = (gemm_order_auto() && a.M > a.N && tiles > gemm_num_sms() / CL) ? 1 : 0;
     if constexpr (CG == 2) {
         // stream-K for the residual GEMM when the tiles do not fill whole waves of clusters (dense|fc2: 136 tiles on 74 clusters)
         const int clusters = std::min(tiles, gemm_num_sms() / CL), num_kb = cdiv(a.K, BK);
@@ -234,6 +243,7 @@ int gemm_bf16_tn(const GemmArgs& a, cudaStream_t st) {
     GemmParams p{};
     p.M = a.M; p.N = a.N; p.K = a.K; p.out = a.out; p.ldc = a.ldc; p.bias = a.bias; p.gelu_from = a.N;
     const int tiles = cdiv(cdiv(a.M, 128), CL) * cdiv(a.N, BN);
+    p.n_fast = (gemm_order_auto() && a.M > a.N && tiles > gemm_num_sms() / CL) ? 1 : 0;
     return launch<BN, EPI_BIAS_F32, A_MN, BK, CL, CG>(ma, mb, p, tiles, st);
 }
 

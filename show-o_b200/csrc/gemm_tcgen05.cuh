@@ -62,6 +62,12 @@ struct GemmParams {
     __nv_bfloat16* ln_xb; int64_t ln_xb_ld; float* ln_part_out;
     const float* ln_part_in; const float* ln_c; float ln_eps;
     float* sk_ws;           // nullptr: classic tile loop
+    // Tile order of the persistent loop.  0: consecutive units sweep M under one B tile (B is read from DRAM once; A once per group of
+    // concurrently processed B tiles unless it stays in L2) -- right when A is the smaller operand.  1: consecutive units sweep N over
+    // one A row block (A read once, B re-read per wave, from L2 when it fits) -- right when A is the larger operand (M > N: the
+    // layer's second GEMM, the weight gradients of wide layers, dgrad into a narrow layer).  Measured cause: dense|fc2 at
+    // 4128 x 2048 x 10240 moved 267 MB for 194 MB algorithmic in order 0 (A = 85 MB crossed DRAM once per wave).
+    int n_fast;
     int* sk_flags;          // [units][2] one flag per (tile, CTA rank), zero between launches
 };
 
@@ -180,7 +186,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             GemmSegCursor cur(sk, unit0, unit_stride, num_units, num_kb);
             int unit, kb_begin, kb_end;
             while (cur.next(unit, kb_begin, kb_end)) {
-                const int tm = (unit % tiles_mc) * CL + crank, tn = unit / tiles_mc;
+                const int tm = (p.n_fast ? unit / tiles_n : unit % tiles_mc) * CL + crank, tn = p.n_fast ? unit % tiles_n : unit / tiles_mc;
                 int img = 0, y0 = 0, x0 = 0;
                 if constexpr (AMODE == A_CONV3) {
                     const int tw = cdiv_dev(p.conv_W, p.conv_TW), th = cdiv_dev(p.conv_H, p.conv_TH);
@@ -303,7 +309,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         GemmSegCursor cur(sk, unit0, unit_stride, num_units, num_kb);
         int unit, kb_begin, kb_end;
         for (; cur.next(unit, kb_begin, kb_end); ++it) {
-            const int tm = (unit % tiles_mc) * CL + crank, tn = unit / tiles_mc;
+            const int tm = (p.n_fast ? unit / tiles_n : unit % tiles_mc) * CL + crank, tn = p.n_fast ? unit % tiles_n : unit / tiles_mc;
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             // stream-K: a segment without the tile's first k block parks its accumulators; one with the first but not the last

@@ -59,14 +59,14 @@ def test_clip_tower_small_geometries_against_the_oracle(dev, geo):
     err = (got - ref).abs()
     print(f"clip {geo['image_size']}px/{d.n_layers}L: max {err.max():.4f} mean {err.mean():.5f} (ref std {ref.std():.3f})")
     _record(f"clip_small_{geo['image_size']}", {"max_abs": float(err.max()), "mean_abs": float(err.mean()), "ref_std": float(ref.std())})
-    assert got.shape == ref.shape and err.max().item() < 0.08 and err.mean().item() < 0.01
+    assert got.shape == ref.shape and err.max().item() < 0.025 and err.mean().item() < 0.004      # observed 0.0106 / 0.0018
     # the other selections of clip_encoder.py:29-37 and every hidden_states index
     t.select_feature = "cls_patch"
-    assert (t(x.to(dev)).cpu() - hs[-2]).abs().max().item() < 0.08
+    assert (t(x.to(dev)).cpu() - hs[-2]).abs().max().item() < 0.025
     t.select_feature = "patch"
     for sel in (0, 1, -1):
         t.select_layer = sel
-        assert (t(x.to(dev)).cpu() - hs[sel][:, 1:]).abs().max().item() < 0.08, sel
+        assert (t(x.to(dev)).cpu() - hs[sel][:, 1:]).abs().max().item() < 0.025, sel
     t.select_layer = -2
     # list input (clip_encoder.py:41-46), dtype of the input kept, batch independence bit for bit
     fl = t([x[0].to(dev), x[1].to(dev).half()])
@@ -96,7 +96,7 @@ def test_clip_vit_l14_336_full_size_against_the_oracle(dev):
           f"{t.kernel_launches()} launches")
     _record("clip_vit_l14_336", {"rel_l2": rel, "max_abs": float(err.max()), "mean_abs": float(err.mean()), "ref_std": float(ref.std()),
                                  "ref_max": float(ref.abs().max()), "launches": t.kernel_launches()})
-    assert rel < 0.02 and err.max().item() < 0.05 * ref.abs().max().item() + 0.1
+    assert rel < 0.012 and err.max().item() < 0.16          # observed rel L2 0.0058, max 0.076 (ref std 2.7, max 13.1)
     # timing of one batch of 16 images (a config-3 MMU batch), device-side
     xb = _pixels(12, 16, 336).to(dev)
     t(xb)
