@@ -19,10 +19,12 @@ pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "models")), 
 
 # instances, not classes: mm_projector only exists on a w_clip_vit model (like in the reference)
 TARGETS = {"model": showo_b200.Showo(True, 58498, 50295, phi_dims=dict(hidden=128, n_layers=1, n_heads=2, ffn=256)),
-           "vq_model": showo_b200.MAGVITv2(materialize=False)}
+           "vq_model": showo_b200.MAGVITv2(materialize=False),
+           # the CLIP-ViT tower of inference_mmu.py:74,133 / train_w_clip_vit.py:216-218,531 (constructed from dims: no checkpoint offline)
+           "vision_tower": showo_b200.CLIPVisionTower(dict(image_size=336, patch_size=14, hidden=1024, n_layers=24, n_heads=16, ffn=4096))}
 FUNCS = {"get_mask_chedule": showo_b200.get_mask_chedule, "mask_or_random_replace_tokens": train_inputs.mask_or_random_replace_tokens}
 # attribute chains the scripts read (not call) on the model objects
-ATTRS = {"model": ["config", "showo", "mm_projector", "output_size"], "vq_model": []}
+ATTRS = {"model": ["config", "showo", "mm_projector", "output_size"], "vq_model": [], "vision_tower": []}
 # nn.Module / HF plumbing both sides inherit or that is exercised elsewhere: not part of the hot-path surface
 SKIP_METHODS = {"to", "eval", "train", "requires_grad_", "parameters", "named_parameters", "state_dict", "load_state_dict", "from_pretrained",
                 "module", "get", "resize_token_embeddings"}
@@ -92,3 +94,8 @@ def test_attributes_the_scripts_read_exist():
     assert hasattr(m.config, "mask_token_id") and m.config.mask_token_id == 58497          # inference_t2i.py:70
     assert callable(m.showo.model.embed_tokens)                                             # inference_mmu.py:136
     assert hasattr(train_inputs.UniversalPrompting, "t2i_prompt") and hasattr(train_inputs.UniversalPrompting, "__call__")
+    assert hasattr(train_inputs.UniversalPrompting, "t2i_gen_prompt")                        # inference_t2i.py:115,118 ('t2i_gen')
+    vt = TARGETS["vision_tower"]                                                             # models/clip_encoder.py:53-82
+    for a in ("dummy_feature", "dtype", "device", "config", "hidden_size", "num_patches_per_side", "num_patches", "image_processor", "is_loaded"):
+        assert hasattr(vt, a), a
+    assert vt.num_patches == 576 and vt.hidden_size == 1024
