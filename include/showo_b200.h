@@ -239,6 +239,13 @@ SHOWO_API int magvit_decode_code_u8(magvit_engine_t* m, const int64_t* ids_dev, 
                           void* stream);
 /* MAGVITv2.get_code(pixel_values): pixels_dev [B,3,R,R] fp32 NCHW -> ids_out_dev [B,(R/16)^2] int64 */
 SHOWO_API int magvit_get_code(magvit_engine_t* m, const float* pixels_dev, int B, int R, int64_t* ids_out_dev, void* stream);
+/* fp32 verification path ("an fp32-accumulate verification mode is needed for any stricter claim"): the same two
+ * entry points on fp32 NCHW activations and fp32 weights, CUDA cores only -- a plain second implementation used by the parity tests to
+ * show that the fast path differs from the reference only by bf16 rounding.  z_out_dev (optional) receives the quantizer's pre-sign
+ * values [B, 13, R/16, R/16].  Not a fallback: no product call routes here. */
+SHOWO_API int magvit_decode_code_fp32(magvit_engine_t* m, const int64_t* ids_dev, int B, int h, int w, float* pixels_out_dev, void* stream);
+SHOWO_API int magvit_get_code_fp32(magvit_engine_t* m, const float* pixels_dev, int B, int R, int64_t* ids_out_dev, float* z_out_dev,
+                         void* stream);
 SHOWO_API int64_t magvit_kernel_launches(magvit_engine_t* m);
 
 /* ---------------------------------------------------------------- CLIP ViT vision tower (models/clip_encoder.py:6-51)

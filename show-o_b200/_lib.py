@@ -80,6 +80,8 @@ _PROTOS = {
     "magvit_decode_code": (_I, [_P, _P, _I, _I, _I, _P, _P]),
     "magvit_decode_code_u8": (_I, [_P, _P, _I, _I, _I, _P, _P]),
     "magvit_get_code": (_I, [_P, _P, _I, _I, _P, _P]),
+    "magvit_decode_code_fp32": (_I, [_P, _P, _I, _I, _I, _P, _P]),
+    "magvit_get_code_fp32": (_I, [_P, _P, _I, _I, _P, _P, _P]),
     "magvit_kernel_launches": (_I64, [_P]),
     "clip_engine_create": (_I, [C.POINTER(ClipConfig), _I, C.POINTER(_P)]),
     "clip_engine_destroy": (_I, [_P]),

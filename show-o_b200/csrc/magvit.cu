@@ -334,6 +334,138 @@ __global__ void transpose_kernel(const bf16* __restrict__ v, int64_t ld, bf16* _
         if (t0 + threadIdx.x < n_tok) vt[(int64_t)(c0 + j) * n_tok + t0 + threadIdx.x] = tile[threadIdx.x][j];
 }
 
+
+// ================================================================================================ fp32 verification path
+// SURVEY section 7 ("an fp32-accumulate verification mode is needed for any stricter claim"): a second, deliberately plain
+// implementation of get_code / decode_code -- fp32 NCHW activations, fp32 weights in torch's own layout, CUDA cores only, no tensor
+// cores, no bf16 anywhere -- that follows models/modeling_magvitv2.py / common_modules.py operation by operation.  It exists to
+// separate "bf16 rounding of the fast path" from "a defect": against the CPU oracle it agrees to fp32 re-association level, and the
+// fast path's LFQ sign flips are shown to sit only where THIS path's pre-sign value is ~0 (tests/test_gpu_parity.py).  Not a
+// fallback: nothing on the product path calls it.
+__global__ void __launch_bounds__(256) vconv_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                                                    const float* __restrict__ resid, float* __restrict__ y, int NB, int cin, int H, int W,
+                                                    int cout, int Ho, int Wo, int k, int stride, int pad_lo) {
+    const int64_t total = (int64_t)NB * cout * Ho * Wo;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int xo = (int)(i % Wo), yo = (int)((i / Wo) % Ho), co = (int)((i / ((int64_t)Wo * Ho)) % cout), n = (int)(i / ((int64_t)Wo * Ho * cout));
+        float acc = b ? b[co] : 0.f;
+        for (int ci = 0; ci < cin; ++ci) {
+            const float* xp = x + ((int64_t)n * cin + ci) * H * W;
+            const float* wp = w + ((int64_t)co * cin + ci) * k * k;
+            for (int ky = 0; ky < k; ++ky) {
+                const int yi = yo * stride + ky - pad_lo;
+                if (yi < 0 || yi >= H) continue;
+                for (int kx = 0; kx < k; ++kx) {
+                    const int xi = xo * stride + kx - pad_lo;
+                    if (xi < 0 || xi >= W) continue;
+                    acc = fmaf(wp[ky * k + kx], xp[(int64_t)yi * W + xi], acc);
+                }
+            }
+        }
+        if (resid) acc += resid[i];
+        y[i] = acc;
+    }
+}
+// GroupNorm(32 groups, eps) (+ swish) on NCHW fp32: one CTA per (image, group), two-pass statistics
+__global__ void __launch_bounds__(256) vgn_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                  float* __restrict__ y, int C, int HW, float eps, int swish) {
+    __shared__ float red[8];
+    __shared__ float stat[2];
+    const int cpg = C / 32, g = blockIdx.x % 32, n = blockIdx.x / 32;
+    const int64_t base = ((int64_t)n * C + (int64_t)g * cpg) * HW, cnt = (int64_t)cpg * HW;
+    float s = 0.f;
+    for (int64_t i = threadIdx.x; i < cnt; i += 256) s += x[base + i];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { float t = 0.f; for (int i = 0; i < 8; ++i) t += red[i]; stat[0] = t / (float)cnt; }
+    __syncthreads();
+    const float mean = stat[0];
+    float q = 0.f;
+    for (int64_t i = threadIdx.x; i < cnt; i += 256) { const float d = x[base + i] - mean; q += d * d; }
+    q = warp_sum(q);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = q;
+    __syncthreads();
+    if (threadIdx.x == 0) { float t = 0.f; for (int i = 0; i < 8; ++i) t += red[i]; stat[1] = rsqrtf(t / (float)cnt + eps); }
+    __syncthreads();
+    const float rstd = stat[1];
+    for (int64_t i = threadIdx.x; i < cnt; i += 256) {
+        const int c = g * cpg + (int)(i / HW);
+        float t = (x[base + i] - mean) * rstd * gamma[c] + beta[c];
+        if (swish) t = t / (1.f + expf(-t));
+        y[base + i] = t;
+    }
+}
+__global__ void vupsample_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t planes, int H, int W) {
+    const int64_t total = planes * 4 * H * W;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int xo = (int)(i % (2 * W)), yo = (int)((i / (2 * W)) % (2 * H));
+        const int64_t pl = i / ((int64_t)4 * H * W);
+        y[i] = x[(pl * H + (yo >> 1)) * W + (xo >> 1)];
+    }
+}
+// AttnBlock (common_modules.py:168-211) on fused q|k|v [n, 3C, HW]: S[i][j] = sum_c q[c][i] k[c][j] * C^-0.5, softmax over j, out[c][i] = sum_j v[c][j] P[i][j]
+__global__ void vattn_scores_kernel(const float* __restrict__ qkv, float* __restrict__ S, int C, int HW, float scale) {
+    const int64_t total = (int64_t)HW * HW;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int j = (int)(t % HW), i = (int)(t / HW);
+        float acc = 0.f;
+        for (int c = 0; c < C; ++c) acc = fmaf(qkv[(int64_t)c * HW + i], qkv[(int64_t)(C + c) * HW + j], acc);
+        S[t] = acc * scale;
+    }
+}
+__global__ void __launch_bounds__(256) vsoftmax_kernel(float* __restrict__ S, int n) {
+    __shared__ float red[8];
+    float* r = S + (int64_t)blockIdx.x * n;
+    float mx = -3.0e38f;
+    for (int i = threadIdx.x; i < n; i += 256) mx = fmaxf(mx, r[i]);
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
+    __syncthreads();
+    float sum = 0.f;
+    for (int i = threadIdx.x; i < n; i += 256) { const float e = expf(r[i] - mx); r[i] = e; sum += e; }
+    sum = warp_sum(sum);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    sum = 0.f;
+    for (int i = 0; i < 8; ++i) sum += red[i];
+    const float inv = 1.f / sum;
+    for (int i = threadIdx.x; i < n; i += 256) r[i] *= inv;
+}
+__global__ void vattn_out_kernel(const float* __restrict__ qkv, const float* __restrict__ P, float* __restrict__ out, int C, int HW) {
+    const int64_t total = (int64_t)C * HW;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(t % HW), c = (int)(t / HW);
+        const float* v = qkv + (int64_t)(2 * C + c) * HW;
+        const float* p = P + (int64_t)i * HW;
+        float acc = 0.f;
+        for (int j = 0; j < HW; ++j) acc = fmaf(v[j], p[j], acc);
+        out[t] = acc;
+    }
+}
+// LFQ (modeling_magvitv2.py:186-221): code -> +-1 entries [n, 13, hw]; pre-sign values [n, 13, hw] -> code (channel 0 = MSB)
+__global__ void vlfq_entry_kernel(const int64_t* __restrict__ ids, float* __restrict__ z, int64_t n_img, int hw) {
+    const int64_t total = n_img * 13 * hw;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int p = (int)(i % hw), c = (int)((i / hw) % 13);
+        const int64_t n = i / ((int64_t)13 * hw);
+        z[i] = ((ids[n * hw + p] >> (12 - c)) & 1) ? 1.f : -1.f;
+    }
+}
+__global__ void vlfq_index_kernel(const float* __restrict__ z, int64_t* __restrict__ ids, int64_t n_img, int hw) {
+    const int64_t total = n_img * hw;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int p = (int)(i % hw);
+        const int64_t n = i / hw;
+        int64_t code = 0;
+        for (int c = 0; c < 13; ++c) code |= (int64_t)(z[(n * 13 + c) * hw + p] > 0.f ? 1 : 0) << (12 - c);
+        ids[i] = code;
+    }
+}
+
 }  // namespace showo
 
 using namespace showo;
@@ -355,6 +487,8 @@ struct magvit_engine {
     bf16* bufs[4] = {nullptr, nullptr, nullptr, nullptr}; size_t buf_cap = 0;
     float* stats = nullptr; float* partials = nullptr;
     float* scores = nullptr; size_t scores_cap = 0; bf16* probs = nullptr; bf16* vt = nullptr;
+    float* vbufs[4] = {nullptr, nullptr, nullptr, nullptr}; size_t vbuf_cap = 0;     // fp32 verification path (NCHW)
+    float* vscores = nullptr; size_t vscores_cap = 0;
     int64_t launches_last = 0;
 };
 
@@ -550,6 +684,84 @@ static int decode_impl(magvit_engine* m, const int64_t* ids, int B, int h, int w
     return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------ fp32 verification path (host side)
+static int v_ensure(magvit_engine* m, size_t elems, cudaStream_t st) {
+    if (elems <= m->vbuf_cap) return 0;
+    SHOWO_CUDA_OK(cudaStreamSynchronize(st));
+    for (int i = 0; i < 4; ++i) {
+        if (m->vbufs[i]) cudaFree(m->vbufs[i]);
+        m->vbufs[i] = nullptr;
+        SHOWO_CUDA_OK(cudaMalloc(&m->vbufs[i], elems * sizeof(float)));
+    }
+    m->vbuf_cap = elems;
+    return 0;
+}
+static int v_grid(int64_t total) { return (int)std::min<int64_t>((total + 255) / 256, 148 * 32); }
+static int v_conv(magvit_engine* m, const std::string& name, const float* x, float* y, const float* resid, int NB, int H, int W, int stride,
+                  cudaStream_t st) {
+    auto it = m->conv.find(name);
+    SHOWO_CHECK(it != m->conv.end(), "conv " + name + ": unknown");
+    const ConvW& c = it->second;
+    const int Ho = H / stride, Wo = W / stride;
+    // Downsample (common_modules.py:83-87): pad (0, 1, 0, 1) then 3x3 stride 2 = no low-side padding; 3x3 stride 1: 'same'; 1x1: none
+    const int pad_lo = (c.k == 3 && stride == 1) ? 1 : 0;
+    vconv_kernel<<<v_grid((int64_t)NB * c.cout * Ho * Wo), 256, 0, st>>>(x, c.w32, c.b, resid, y, NB, c.cin, H, W, c.cout, Ho, Wo, c.k, stride, pad_lo);
+    note_launch();
+    SHOWO_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+static int v_gn(magvit_engine* m, const std::string& name, const float* x, float* y, int NB, int C, int HW, bool swish, cudaStream_t st) {
+    auto it = m->norm.find(name);
+    SHOWO_CHECK(it != m->norm.end() && it->second.c == C, "groupnorm " + name + ": unknown or channel mismatch");
+    vgn_kernel<<<NB * 32, 256, 0, st>>>(x, it->second.g, it->second.b, y, C, HW, 1e-6f, swish ? 1 : 0);
+    note_launch();
+    SHOWO_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+static int v_res(magvit_engine* m, const std::string& p, int& X, int NB, int H, int W, int cin, int cout, cudaStream_t st) {
+    int others[3], k = 0;
+    for (int i = 0; i < 4; ++i) if (i != X) others[k++] = i;
+    const int T = others[0], U = others[1], V = others[2];
+    SHOWO_TRY(v_gn(m, p + ".norm1", m->vbufs[X], m->vbufs[T], NB, cin, H * W, true, st));
+    SHOWO_TRY(v_conv(m, p + ".conv1", m->vbufs[T], m->vbufs[U], nullptr, NB, H, W, 1, st));
+    SHOWO_TRY(v_gn(m, p + ".norm2", m->vbufs[U], m->vbufs[T], NB, cout, H * W, true, st));
+    const float* skip = m->vbufs[X];
+    if (cin != cout) {
+        SHOWO_TRY(v_conv(m, p + ".nin_shortcut", m->vbufs[X], m->vbufs[V], nullptr, NB, H, W, 1, st));
+        skip = m->vbufs[V];
+    }
+    SHOWO_TRY(v_conv(m, p + ".conv2", m->vbufs[T], m->vbufs[U], skip, NB, H, W, 1, st));
+    X = U;
+    return 0;
+}
+static int v_attn(magvit_engine* m, const std::string& p, int& X, int NB, int H, int W, int C, cudaStream_t st) {
+    int others[3], k = 0;
+    for (int i = 0; i < 4; ++i) if (i != X) others[k++] = i;
+    const int T = others[0], U = others[1], V = others[2];
+    const int HW = H * W;
+    if ((size_t)HW * HW > m->vscores_cap) {
+        SHOWO_CUDA_OK(cudaStreamSynchronize(st));
+        if (m->vscores) cudaFree(m->vscores);
+        m->vscores = nullptr;
+        SHOWO_CUDA_OK(cudaMalloc(&m->vscores, (size_t)HW * HW * 4));
+        m->vscores_cap = (size_t)HW * HW;
+    }
+    SHOWO_TRY(v_gn(m, p + ".norm", m->vbufs[X], m->vbufs[T], NB, C, HW, false, st));
+    SHOWO_TRY(v_conv(m, p + ".qkv", m->vbufs[T], m->vbufs[U], nullptr, NB, H, W, 1, st));       // [NB, 3C, HW]
+    for (int n = 0; n < NB; ++n) {
+        const float* qkv = m->vbufs[U] + (size_t)n * 3 * C * HW;
+        vattn_scores_kernel<<<v_grid((int64_t)HW * HW), 256, 0, st>>>(qkv, m->vscores, C, HW, 1.0f / sqrtf((float)C));
+        vsoftmax_kernel<<<HW, 256, 0, st>>>(m->vscores, HW);
+        vattn_out_kernel<<<v_grid((int64_t)C * HW), 256, 0, st>>>(qkv, m->vscores, m->vbufs[T] + (size_t)n * C * HW, C, HW);
+        note_launch(3);
+    }
+    SHOWO_CUDA_OK(cudaGetLastError());
+    SHOWO_TRY(v_conv(m, p + ".proj_out", m->vbufs[T], m->vbufs[V], m->vbufs[X], NB, H, W, 1, st));
+    X = V;
+    return 0;
+}
+
 extern "C" {
 
 int magvit_engine_create(int device, magvit_engine_t** out) {
@@ -604,6 +816,8 @@ int magvit_engine_destroy(magvit_engine_t* m) {
     if (m->stats) cudaFree(m->stats);
     if (m->partials) cudaFree(m->partials);
     if (m->scores) cudaFree(m->scores); if (m->probs) cudaFree(m->probs); if (m->vt) cudaFree(m->vt);
+    for (int i = 0; i < 4; ++i) if (m->vbufs[i]) cudaFree(m->vbufs[i]);
+    if (m->vscores) cudaFree(m->vscores);
     delete m;
     return 0;
 }
@@ -744,6 +958,98 @@ int magvit_get_code(magvit_engine_t* m, const float* pixels_dev, int B, int R, i
     const ConvW& qc = m->conv["encoder.quant_conv"];
     const int64_t npix = (int64_t)B * H * W;
     lfq_encode_kernel<<<(int)cdiv64(npix, 128), 128, 0, st>>>(m->bufs[U], kZ, qc.w32, qc.b, ids_out_dev, npix);
+    note_launch();
+    SHOWO_CUDA_OK(cudaGetLastError());
+    m->launches_last = launches_total() - l0;
+    return 0;
+}
+
+// MAGVITv2.decode_code on the fp32 verification path: ids_dev [B, h*w] -> pixels_out_dev [B, 3, 16h, 16w] fp32 (NCHW)
+int magvit_decode_code_fp32(magvit_engine_t* m, const int64_t* ids_dev, int B, int h, int w, float* pixels_out_dev, void* stream) {
+    SHOWO_CHECK(m && ids_dev && pixels_out_dev && B > 0 && h > 0 && w > 0, "magvit decode (fp32): bad arguments");
+    SHOWO_CUDA_OK(cudaSetDevice(m->device));
+    SHOWO_CHECK(showo_device_count() > 0, "no sm_100 CUDA device visible: libshowo_b200 has no CPU fallback");
+    SHOWO_TRY(magvit_weights_complete(m));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t l0 = launches_total();
+    SHOWO_TRY(v_ensure(m, (size_t)B * kCh * (16 * h) * (16 * w), st));
+    int H = h, W = w;
+    vlfq_entry_kernel<<<v_grid((int64_t)B * 13 * h * w), 256, 0, st>>>(ids_dev, m->vbufs[0], B, h * w);
+    note_launch();
+    SHOWO_TRY(v_conv(m, "decoder.post_quant_conv", m->vbufs[0], m->vbufs[1], nullptr, B, H, W, 1, st));
+    SHOWO_TRY(v_conv(m, "decoder.conv_in", m->vbufs[1], m->vbufs[0], nullptr, B, H, W, 1, st));
+    int X = 0;
+    int C = kCh * kDecMult[4];
+    SHOWO_TRY(v_res(m, "decoder.mid.block_1", X, B, H, W, C, C, st));
+    SHOWO_TRY(v_attn(m, "decoder.mid.attn_1", X, B, H, W, C, st));
+    SHOWO_TRY(v_res(m, "decoder.mid.block_2", X, B, H, W, C, C, st));
+    for (int lvl = 4; lvl >= 0; --lvl) {
+        const int cout = kCh * kDecMult[lvl];
+        for (int blk = 0; blk < kDecBlocks[lvl]; ++blk) {
+            SHOWO_TRY(v_res(m, "decoder.up." + std::to_string(lvl) + ".block." + std::to_string(blk), X, B, H, W, C, cout, st));
+            C = cout;
+        }
+        if (lvl != 0) {
+            const int T = (X + 1) & 3, U = (X + 2) & 3;
+            vupsample_kernel<<<v_grid((int64_t)B * C * 4 * H * W), 256, 0, st>>>(m->vbufs[X], m->vbufs[T], (int64_t)B * C, H, W);
+            note_launch();
+            H *= 2; W *= 2;
+            SHOWO_TRY(v_conv(m, "decoder.up." + std::to_string(lvl) + ".upsample.conv", m->vbufs[T], m->vbufs[U], nullptr, B, H, W, 1, st));
+            X = U;
+        }
+    }
+    const int T = (X + 1) & 3;
+    SHOWO_TRY(v_gn(m, "decoder.norm_out", m->vbufs[X], m->vbufs[T], B, C, H * W, true, st));
+    {
+        auto it = m->conv.find("decoder.conv_out");
+        const ConvW& c = it->second;
+        vconv_kernel<<<v_grid((int64_t)B * 3 * H * W), 256, 0, st>>>(m->vbufs[T], c.w32, c.b, nullptr, pixels_out_dev, B, c.cin, H, W, 3, H, W, 3, 1, 1);
+        note_launch();
+    }
+    SHOWO_CUDA_OK(cudaGetLastError());
+    m->launches_last = launches_total() - l0;
+    return 0;
+}
+
+// MAGVITv2.get_code on the fp32 verification path: pixels_dev [B, 3, R, R] -> ids_out_dev [B, (R/16)^2]; z_out_dev (optional)
+// receives the quantizer's pre-sign values [B, 13, R/16, R/16] -- what the sign of every code bit is taken from
+int magvit_get_code_fp32(magvit_engine_t* m, const float* pixels_dev, int B, int R, int64_t* ids_out_dev, float* z_out_dev, void* stream) {
+    SHOWO_CHECK(m && pixels_dev && ids_out_dev && B > 0 && R >= 16 && R % 16 == 0, "magvit get_code (fp32): bad arguments");
+    SHOWO_CUDA_OK(cudaSetDevice(m->device));
+    SHOWO_CHECK(showo_device_count() > 0, "no sm_100 CUDA device visible: libshowo_b200 has no CPU fallback");
+    SHOWO_TRY(magvit_weights_complete(m));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t l0 = launches_total();
+    SHOWO_TRY(v_ensure(m, (size_t)B * kCh * R * R, st));
+    int H = R, W = R, C = kCh;
+    {
+        const ConvW& c = m->conv["encoder.conv_in"];
+        vconv_kernel<<<v_grid((int64_t)B * C * H * W), 256, 0, st>>>(pixels_dev, c.w32, c.b, nullptr, m->vbufs[0], B, 3, H, W, C, H, W, 3, 1, 1);
+        note_launch();
+    }
+    int X = 0;
+    for (int lvl = 0; lvl < 5; ++lvl) {
+        const int cout = kCh * kEncMult[lvl];
+        for (int blk = 0; blk < kEncBlocks[lvl]; ++blk) {
+            SHOWO_TRY(v_res(m, "encoder.down." + std::to_string(lvl) + ".block." + std::to_string(blk), X, B, H, W, C, cout, st));
+            C = cout;
+        }
+        if (lvl != 4) {
+            const int U = (X + 1) & 3;
+            SHOWO_TRY(v_conv(m, "encoder.down." + std::to_string(lvl) + ".downsample.conv", m->vbufs[X], m->vbufs[U], nullptr, B, H, W, 2, st));
+            H /= 2; W /= 2;
+            X = U;
+        }
+    }
+    SHOWO_TRY(v_res(m, "encoder.mid.block_1", X, B, H, W, C, C, st));
+    SHOWO_TRY(v_attn(m, "encoder.mid.attn_1", X, B, H, W, C, st));
+    SHOWO_TRY(v_res(m, "encoder.mid.block_2", X, B, H, W, C, C, st));
+    const int T = (X + 1) & 3, U = (X + 2) & 3;
+    SHOWO_TRY(v_gn(m, "encoder.norm_out", m->vbufs[X], m->vbufs[T], B, C, H * W, true, st));
+    SHOWO_TRY(v_conv(m, "encoder.conv_out", m->vbufs[T], m->vbufs[U], nullptr, B, H, W, 1, st));       // [B, 13, h, w]
+    SHOWO_TRY(v_conv(m, "encoder.quant_conv", m->vbufs[U], m->vbufs[T], nullptr, B, H, W, 1, st));
+    if (z_out_dev) SHOWO_CUDA_OK(cudaMemcpyAsync(z_out_dev, m->vbufs[T], (size_t)B * 13 * H * W * 4, cudaMemcpyDeviceToDevice, st));
+    vlfq_index_kernel<<<v_grid((int64_t)B * H * W), 256, 0, st>>>(m->vbufs[T], ids_out_dev, B, H * W);
     note_launch();
     SHOWO_CUDA_OK(cudaGetLastError());
     m->launches_last = launches_total() - l0;

@@ -238,3 +238,34 @@ class MAGVITv2(nn.Module):
             _lib.check(lib.magvit_decode_code_u8(eng, _lib.ptr(ids), B, h, w, _lib.ptr(out),
                                                  _lib.current_stream_ptr()), "magvit_decode_code_u8")
         return out
+
+    # ------------------------------------------------------------------ fp32 verification path (parity tests only)
+    @torch.no_grad()
+    def get_code_fp32(self, pixel_values: torch.Tensor, return_z: bool = False):
+        """get_code on the engine's fp32 verification path (fp32 NCHW activations and weights, CUDA cores only): the codes, and with
+        `return_z` the quantizer's pre-sign values [B, 13, R/16, R/16] every code bit is the sign of."""
+        lib = _lib.require_gpu()
+        eng = self._sync()
+        x = pixel_values.float().contiguous()
+        B, _, R, R2 = x.shape
+        assert R == R2
+        out = torch.empty(B, (R // 16) ** 2, dtype=torch.int64, device=x.device)
+        z = torch.empty(B, 13, R // 16, R // 16, dtype=torch.float32, device=x.device) if return_z else None
+        with torch.cuda.device(x.device):
+            _lib.check(lib.magvit_get_code_fp32(eng, _lib.ptr(x), B, R, _lib.ptr(out), _lib.ptr(z), _lib.current_stream_ptr()),
+                       "magvit_get_code_fp32")
+        return (out, z) if return_z else out
+
+    @torch.no_grad()
+    def decode_code_fp32(self, codebook_indices: torch.Tensor, shape=None) -> torch.Tensor:
+        """decode_code on the fp32 verification path."""
+        lib = _lib.require_gpu()
+        eng = self._sync()
+        ids = codebook_indices.to(torch.int64).contiguous()
+        h, w = self._grid(ids, shape)
+        B = ids.shape[0]
+        out = torch.empty(B, 3, 16 * h, 16 * w, dtype=torch.float32, device=ids.device)
+        with torch.cuda.device(ids.device):
+            _lib.check(lib.magvit_decode_code_fp32(eng, _lib.ptr(ids), B, h, w, _lib.ptr(out), _lib.current_stream_ptr()),
+                       "magvit_decode_code_fp32")
+        return out

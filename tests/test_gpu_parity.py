@@ -800,3 +800,51 @@ def test_mask_descriptor_kernel_equals_host_derivation(dev):
     # strided view of a larger batch (the shim slices [:n_seq])
     big = torch.cat([dense[0], dense[0]]).to(dev)
     assert M.descriptors_from_dense(big[:3]) == M.descriptors_from_dense(dense[0])[:3]
+
+
+def test_magvit_fp32_verification_path(vq, dev):
+    """The engine's fp32 verification path (fp32 NCHW activations and weights, CUDA cores only) against the reference
+    golden / the oracle at fp32 re-association level, and the FAST path against it: the bf16 fast path's LFQ sign flips sit only where
+    the verification path's own pre-sign value is ~0, i.e. they are rounding, not defects."""
+    g = FX.load("magvit.npz")
+    codes_in, pixels = FX.magvit_inputs()
+    # ---- decode
+    with torch.no_grad():
+        ref = MO.decode_code(codes_in, MO.make_magvit_weights(1))
+    got32 = vq.decode_code_fp32(codes_in.to(dev)).cpu()
+    d32 = (got32 - ref).abs()
+    fast = vq.decode_code(codes_in.to(dev)).cpu()
+    dfast = (fast - got32).abs()
+    print(f"magvit decode, fp32 verification path vs oracle: max {d32.max():.2e} mean {d32.mean():.2e}; fast path vs verification path: "
+          f"max {dfast.max():.4f} mean {dfast.mean():.5f}")
+    _record("magvit_decode_fp32_path", {"max_abs_vs_oracle": float(d32.max()), "mean_abs_vs_oracle": float(d32.mean()),
+                                        "fast_vs_fp32_max": float(dfast.max()), "fast_vs_fp32_mean": float(dfast.mean())})
+    assert got32.shape == (1, 3, 256, 256) and d32.max().item() < 5e-4
+    assert (got32 - torch.from_numpy(g["decode"].astype(np.float32))).abs().max().item() < 2e-3        # the reference's own output (stored in half precision)
+    assert dfast.max().item() < 0.2 and dfast.mean().item() < 0.012
+    # non-square grid
+    wide = torch.randint(0, 8192, (1, 8 * 24), generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        refw = MO.decode_code(wide, MO.make_magvit_weights(1), shape=(8, 24))
+    assert (vq.decode_code_fp32(wide.to(dev), shape=(8, 24)).cpu() - refw).abs().max().item() < 5e-4
+    # ---- get_code
+    codes32, z32 = vq.get_code_fp32(pixels.to(dev), return_z=True)
+    codes32, z32 = codes32.cpu(), z32.cpu()
+    z_ref = torch.from_numpy(g["z"].astype(np.float32))
+    codes_ref = torch.from_numpy(g["codes"].astype(np.int64)).reshape(1, -1)
+    dz = (z32 - z_ref).abs()
+    print(f"magvit get_code, fp32 verification path: max |dz| vs the reference {dz.max():.2e}; codes differing {(codes32 != codes_ref).sum().item()} of 256; "
+          f"smallest |z| of the fixture {z_ref.abs().min():.2e}")
+    assert dz.max().item() < 5e-4
+    bits_ref = z_ref.reshape(1, 13, -1) > 0
+    bits32 = ((codes32[:, None, :] >> torch.arange(12, -1, -1)[None, :, None]) & 1).bool()
+    assert ((bits32 != bits_ref) <= (z_ref.reshape(1, 13, -1).abs() < 2 * dz.max())).all()            # identical unless |z| is inside the fp32 noise
+    codes_fast = vq.get_code(pixels.to(dev)).cpu()
+    bits_fast = ((codes_fast[:, None, :] >> torch.arange(12, -1, -1)[None, :, None]) & 1).bool()
+    flip = bits_fast != bits32
+    zabs = z32.reshape(1, 13, -1).abs()
+    print(f"fast path vs verification path: {int(flip.sum())} of {flip.numel()} sign bits differ, largest |z| (fp32 path) at a differing bit "
+          f"{float(zabs[flip].max()) if flip.any() else 0:.4f}")
+    _record("magvit_get_code_fp32_path", {"max_abs_dz_vs_reference": float(dz.max()), "codes_differing_vs_reference": int((codes32 != codes_ref).sum()),
+                                          "fast_path_bits_differing": int(flip.sum()), "max_abs_z_at_fast_path_flip": float(zabs[flip].max()) if flip.any() else 0.0})
+    assert (zabs[flip] < 0.025).all()
