@@ -141,6 +141,14 @@ SHOWO_API int showo_cross_entropy(const float* logits_dev, const int64_t* labels
 SHOWO_API int showo_mmu_sample(const float* logits_dev, int64_t ld, int B, int V, float temperature, int top_k,
                      const float* noise_expo_dev, uint64_t seed, uint32_t step, int64_t* out_tokens_dev, void* stream);
 
+/* fp32 verification forward ("an fp32 / TF32-accumulate verification mode is needed for any stricter claim"): the same
+ * call as showo_forward on a second, plain implementation -- fp32 activations, the fp32 master weights the engine keeps once
+ * showo_optimizer_enable has been called, CUDA cores only, six separate Linear layers per block as the reference writes them.  Used by
+ * the parity tests to pin the engine to the oracle at fp32 re-association level (token decisions bit-identical) and to measure the
+ * fast path's bf16 error.  Not a fallback: no product call routes here. */
+SHOWO_API int showo_forward_fp32(showo_engine_t* e, const int64_t* ids_dev, const float* embeds_dev, int B, int L,
+                       const showo_seq_mask_t* masks_host, float* logits_out_dev, void* stream);
+
 /* Showo.mm_projector (models/modeling_showo.py:49-54: Linear(1024, 2048) -> nn.GELU() -> Linear(2048, 2048)) on the CLIP-ViT features, as
  * inference_mmu.py:128-131 calls it: feats_dev fp32 [n, 1024] -> out_dev fp32 [n, 2048] (bf16 operands, fp32 accumulation, exact erf GELU).
  * Weights arrive through showo_load_weight under "mm_projector.0.weight" / ".0.bias" / ".2.weight" / ".2.bias" (optional set). */

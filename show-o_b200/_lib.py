@@ -47,6 +47,7 @@ _PROTOS = {
     "showo_load_weight": (_I, [_P, C.c_char_p, _P, _I64, _I]),
     "showo_weights_complete": (_I, [_P]),
     "showo_forward": (_I, [_P, _P, _P, _I, _I, C.POINTER(SeqMask), _P, _P]),
+    "showo_forward_fp32": (_I, [_P, _P, _P, _I, _I, C.POINTER(SeqMask), _P, _P]),
     "showo_t2i_logits": (_I, [_P, _P, _P, _I, _I, _I, _I, C.POINTER(SeqMask), _P, _P]),
     "showo_t2i_generate": (_I, [_P, _P, _P, _I, _I, _I, _I, C.POINTER(SeqMask), _I, _F, C.POINTER(C.c_int32),
                                 C.POINTER(C.c_float), _P, _P, C.c_uint64, _P, _P]),

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libshowo_b200.so")
-SOURCES = ["engine.cu", "gemm.cu", "gemv.cu", "decode_mega.cu", "elementwise.cu", "attention.cu", "attention_tc.cu", "attention_bwd.cu", "train.cu", "prep.cu", "sampler.cu", "magvit.cu", "clip.cu"]
+SOURCES = ["engine.cu", "gemm.cu", "gemv.cu", "decode_mega.cu", "elementwise.cu", "attention.cu", "attention_tc.cu", "attention_bwd.cu", "train.cu", "prep.cu", "sampler.cu", "magvit.cu", "clip.cu", "verify.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 

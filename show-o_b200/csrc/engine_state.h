@@ -95,5 +95,7 @@ int engine_ensure_ws(showo_engine* e, int rows, int n_seq, int L, int64_t logit_
 // optimizer is enabled); engine.cu: re-derive b2 = b_dense + b_fc2 and the image slice of the head bias after an optimizer step
 namespace showo {
 int opt_store_master(showo_engine* e, const std::string& name, const float* src_dev, int64_t numel, cudaStream_t st);
+// the fp32 master of one reference parameter inside the optimizer state: pointer + [rows, cols] with row stride ld (verify.cu)
+int opt_master_slot(showo_engine* e, const std::string& name, float** ptr, int64_t* rows, int64_t* cols, int64_t* ld);
 }
 int engine_refresh_derived(showo_engine* e, cudaStream_t st);

@@ -842,6 +842,11 @@ int opt_store_master(showo_engine* e, const std::string& name, const float* src_
     return 0;
 }
 
+int opt_master_slot(showo_engine* e, const std::string& name, float** ptr, int64_t* rows, int64_t* cols, int64_t* ld) {
+    SHOWO_CHECK(e && e->opt && e->opt->master, "no optimizer state: call showo_optimizer_enable before loading the weights");
+    return named_slot(e, e->opt->master, true, name, ptr, rows, cols, ld);
+}
+
 }  // namespace showo
 
 using namespace showo;

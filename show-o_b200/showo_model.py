@@ -380,6 +380,26 @@ class Showo(nn.Module):
             return logits, loss_t2i, loss_lm, loss_mmu
         return logits
 
+    @torch.no_grad()
+    def forward_fp32(self, input_ids=None, input_embeddings=None, attention_mask=None):
+        """Showo.forward without labels on the engine's fp32 VERIFICATION path (showo_forward_fp32: fp32 activations, the fp32 master
+        weights, CUDA cores, one Linear at a time) -- for the parity tests' stricter claims, not a product path.  Needs
+        `enable_optimizer()` (that is what makes the engine keep fp32 masters)."""
+        lib = _lib.require_gpu()
+        eng = self._sync_engine()
+        if input_embeddings is None:
+            B, L = input_ids.shape
+            ids, emb, dev = self._check_ids(input_ids, "Showo.forward_fp32"), None, input_ids.device
+        else:
+            B, L, _ = input_embeddings.shape
+            ids, emb, dev = None, input_embeddings.float().contiguous(), input_embeddings.device
+        descs = self._mask_descs(attention_mask, B)
+        logits = torch.empty(B, L, self.vocab_size, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.showo_forward_fp32(eng, _lib.ptr(ids), _lib.ptr(emb), B, L, _lib.masks_array(descs), _lib.ptr(logits),
+                                              _lib.current_stream_ptr()), "showo_forward_fp32")
+        return logits
+
     def train_forward(self, input_ids=None, input_embeddings=None, attention_mask=None, labels=None, terms=None,
                       want_logits=True):
         """The engine's training forward without autograd plumbing (used by _TrainStep and by the benchmarks): returns

@@ -848,3 +848,75 @@ def test_magvit_fp32_verification_path(vq, dev):
     _record("magvit_get_code_fp32_path", {"max_abs_dz_vs_reference": float(dz.max()), "codes_differing_vs_reference": int((codes32 != codes_ref).sum()),
                                           "fast_path_bits_differing": int(flip.sum()), "max_abs_z_at_fast_path_flip": float(zabs[flip].max()) if flip.any() else 0.0})
     assert (zabs[flip] < 0.025).all()
+
+
+def test_backbone_fp32_verification_forward(lib, dev):
+    """showo_forward_fp32 (SURVEY section 7's verification mode: fp32 activations + fp32 master weights on CUDA cores, the reference's
+    six separate Linear layers per block) pins the engine to the oracle at fp32 re-association level on every mask kind -- and with
+    logits that close the TOKEN DECISIONS are bit-identical: a whole t2i_generate run replayed step by step from the verification
+    logits (the engine's sampler kernel, the oracle's noise) reproduces the oracle's ids exactly.  The fast bf16 path is then measured
+    against it: this is the 'logit error' the tolerances of this file are multiples of."""
+    dims = O.PhiDims(**FX.TINY)
+    W = O.make_showo_weights(dims, seed=3)
+    m = showo_b200.Showo(False, dims.vocab_size, VOC.llm_vocab_size, phi_dims=FX.TINY, materialize=False)
+    m.enable_optimizer(device=dev)
+    m.load_weights(W, device=dev)
+    rows = FX.mask_rows(VOC)
+    worst = {}
+    for kind, ids, dense in (("t2i", rows["t2i"], O.create_attention_mask_predict_next(rows["t2i"])),
+                             ("mmu", rows["mmu"], O.create_attention_mask_for_mmu(rows["mmu"]))):
+        with torch.no_grad():
+            ref = O.showo_logits(W, dims, input_ids=ids, add_mask=dense)
+        descs = M.descriptors_from_dense(dense)
+        got = m.forward_fp32(ids.to(dev), attention_mask=descs).cpu()
+        fast = m(ids.to(dev), attention_mask=descs).cpu()
+        nonpad = torch.stack([torch.arange(ids.shape[1]) >= d[0] for d in descs])          # pad rows are never read by anyone (SURVEY 8a-5)
+        e32 = (got - ref).abs()[nonpad].max().item()
+        ebf = (fast - got).abs()[nonpad].max().item()
+        worst[kind] = (e32, ebf)
+        print(f"{kind}: verification path vs oracle max |dlogit| {e32:.2e}; fast bf16 path vs verification path {ebf:.4f}")
+        assert e32 < 5e-4 and ebf < TOL_TINY
+        assert torch.equal(got[nonpad].argmax(-1), ref[nonpad].argmax(-1))
+    _record("backbone_fp32_path", {k: {"fp32_vs_oracle": v[0], "bf16_vs_fp32": v[1]} for k, v in worst.items()})
+    # ---- a whole generation, decisions bit-identical
+    B, T, w = 2, 4, 3.0
+    cond, uncond = O.make_t2i_prompts(B, VOC, seed=61)
+    mask = O.create_attention_mask_predict_next(torch.cat([cond, uncond]))
+    descs = M.descriptors_from_dense(mask)
+    trace = []
+    with torch.no_grad():
+        ref_ids = O.t2i_generate(W, dims, VOC, cond.clone(), uncond.clone(), mask, guidance_scale=w, timesteps=T,
+                                 generator=torch.Generator().manual_seed(33), trace=trace)
+    floors, temps = showo_b200.step_schedule(showo_b200.cosine_schedule, T, 256, 1.0)
+    unc_d = uncond.to(dev)
+    out = torch.zeros(B, 256, dtype=torch.int64, device=dev)
+    off = VOC.image_offset
+    n_diff, on_trajectory = 0, True
+    ids_run = cond.clone().to(dev)
+    for s, tr in enumerate(trace):
+        if not torch.equal(ids_run.cpu(), tr.input_ids_in):               # a decision inside the fp32 noise moved the run: continue teacher-forced
+            on_trajectory = False
+            ids_run = tr.input_ids_in.clone().to(dev)
+        unc_step = torch.cat([unc_d[:, :129], ids_run[:, 129:]], dim=1)
+        full = m.forward_fp32(torch.cat([ids_run, unc_step]), attention_mask=descs)
+        lc = full[:B, 130:386, off:off + 8192].contiguous()
+        lu = full[B:, 130:386, off:off + 8192].contiguous()
+        err = (((1 + w) * lc - w * lu).cpu() - tr.logits).abs().max().item()
+        assert err < 5e-4 * (1 + 2 * w), (s, err)
+        ex, un = tr.expo.to(dev), tr.uniform.to(dev)
+        mk = torch.zeros(B, 256, dtype=torch.uint8, device=dev)
+        _lib.check(lib.showo_sampler_step(_lib.ptr(lc), _lib.ptr(lu), B, 256, 8192, w, _lib.ptr(ids_run), 387, 130, off, VOC.mask_token_id,
+                                          floors[s], temps[s], _lib.ptr(ex), _lib.ptr(un), 0, s, _lib.ptr(out), _lib.ptr(mk), S()))
+        diff = out.cpu() != tr.sampled_ids
+        if diff.any():                                                    # only where the oracle's own race was inside the fp32 noise
+            race = (tr.logits.reshape(-1, 8192) - torch.log(tr.expo)).topk(2, -1).values
+            margin = (race[:, 0] - race[:, 1]).view(B, 256)
+            assert (margin[diff] <= 4 * err).all(), (s, margin[diff], err)
+        n_diff += int(diff.sum()) + int((mk.cpu().bool() != tr.masking).sum())
+    _record("backbone_fp32_path_generation", {"decisions_differing": n_diff, "tokens_decided": B * 256 * T, "stayed_on_the_oracle_trajectory": on_trajectory,
+                                              "last_step_max_abs_dlogit": err})
+    assert n_diff <= 2
+    if n_diff == 0:
+        assert on_trajectory and torch.equal(out.cpu(), ref_ids)
+    print(f"t2i_generate replayed from verification logits: {n_diff} of {B * 256 * T} decisions differ from the oracle over {T} steps "
+          f"(on the oracle's trajectory throughout: {on_trajectory}; last step max |dlogit| {err:.2e})")
