@@ -281,8 +281,17 @@ def run_ours(args):
         return None
     mmu_local = mmu_decode_bench(torch, model, vq, dev, measured_peaks(), seed=5 + rank)
     mmu_agg = torch.tensor([mmu_local["ms_per_decode_step"], mmu_local["value"]], device=dev, dtype=torch.float64)
-    t512 = t2i512_bench(torch, dist, model, vq, dev, world, rank)
-    train = None if os.environ.get("SHOWO_BENCH_SKIP_TRAIN") else train_step_bench(torch, dist, model, dev, world, rank)
+
+    def guarded(name, fn):
+        """a secondary must never take the headline line down with it (same code on every rank: a failure is a failure everywhere)"""
+        try:
+            return fn()
+        except Exception as e:          # noqa: BLE001
+            import traceback
+            traceback.print_exc()
+            return {"metric": name, "error": f"{type(e).__name__}: {e}"[:400]}
+    t512 = guarded("t2i_512x512", lambda: t2i512_bench(torch, dist, model, vq, dev, world, rank))
+    train = None if os.environ.get("SHOWO_BENCH_SKIP_TRAIN") else guarded("train_step", lambda: train_step_bench(torch, dist, model, dev, world, rank))
     if world > 1:
         mx = mmu_agg.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)

@@ -647,8 +647,8 @@ static bool wgrad_mn() {
 // dW[n_out, n_in] (fp32) = dY^T X over the M tokens and dbias[n_out] = column sums of dY, with dY = [M, ld_y], X = [M, ld_x] bf16.
 // Default: the tcgen05 GEMM reads both operands as they lie (MN-major descriptors, gemm_bf16_tn) -- no transposed copies.
 static int wgrad(TrainState* t, const bf16* dY, int64_t ld_y, int n_out, const bf16* X, int64_t ld_x, int n_in, int M, int64_t Mp,
-                 float* dW, int64_t ld_w, float* dbias, cudaStream_t st) {
-    if (wgrad_mn()) {
+                 float* dW, int64_t ld_w, float* dbias, cudaStream_t st, bool force_mn = false) {
+    if (wgrad_mn() || force_mn) {
         GemmArgs g{};
         g.A = dY; g.lda = ld_y; g.B = X; g.ldb = ld_x; g.M = n_out; g.N = n_in; g.K = M; g.out = dW; g.ldc = ld_w;
         SHOWO_TRY(gemm_bf16_tn(g, st));
@@ -1181,7 +1181,6 @@ int showo_mm_projector_backward(showo_engine_t* e, const float* dy_dev, int64_t 
     cudaStream_t st = (cudaStream_t)stream;
     if (!e->train) e->train = new TrainState();
     TrainState* t = e->train;
-    SHOWO_CHECK(wgrad_mn() || n <= t->cap_M, "mm_projector_backward: SHOWO_WGRAD_MN=0 needs a training forward of at least as many rows first");
     if (!e->mmp_grads) SHOWO_TRY(dev_alloc(&e->mmp_grads, (size_t)kMmpTotal));
     if (!e->mmp_w2t) SHOWO_TRY(dev_alloc(&e->mmp_w2t, (size_t)(kMmpMid * kMmpOut)));
     if (n > e->mmp_bwd_cap) {
@@ -1200,10 +1199,11 @@ int showo_mm_projector_backward(showo_engine_t* e, const float* dy_dev, int64_t 
     const int64_t Mp = (int64_t)(M + 127) / 128 * 128;
     float* G = e->mmp_grads;
     SHOWO_TRY(f32_to_bf16(dy_dev, e->mmp_dy, n * kMmpOut, st));
-    SHOWO_TRY(wgrad(t, e->mmp_dy, kMmpOut, (int)kMmpOut, e->mmp_mid, kMmpMid, (int)kMmpMid, M, Mp, G + kMmpW2, kMmpMid, G + kMmpB2, st));
+    // (always the token-major GEMM: the SHOWO_WGRAD_MN=0 scratch belongs to the backbone's training state and is sized by its rows)
+    SHOWO_TRY(wgrad(t, e->mmp_dy, kMmpOut, (int)kMmpOut, e->mmp_mid, kMmpMid, (int)kMmpMid, M, Mp, G + kMmpW2, kMmpMid, G + kMmpB2, st, true));
     SHOWO_TRY(gemm_plain(e->mmp_dy, kMmpOut, e->mmp_w2t, kMmpOut, M, (int)kMmpMid, (int)kMmpOut, e->mmp_dmid, kMmpMid, false, st));
     SHOWO_TRY(gelu_erf_bwd_bf16(e->mmp_dmid, e->mmp_pre, n * kMmpMid, st));
-    SHOWO_TRY(wgrad(t, e->mmp_dmid, kMmpMid, (int)kMmpMid, e->mmp_in, kMmpIn, (int)kMmpIn, M, Mp, G + kMmpW0, kMmpIn, G + kMmpB0, st));
+    SHOWO_TRY(wgrad(t, e->mmp_dmid, kMmpMid, (int)kMmpMid, e->mmp_in, kMmpIn, (int)kMmpIn, M, Mp, G + kMmpW0, kMmpIn, G + kMmpB0, st, true));
     e->mmp_grads_valid = true;
     e->launches_last = launches_total() - l0;
     return 0;

@@ -49,6 +49,7 @@ def full(dev):
     W = O.make_showo_weights(dims, seed=0)
     probe = W["showo.model.layers.23.mlp.fc2.weight"][:4, :4].numpy().copy()
     m = showo_b200.Showo(False, dims.vocab_size, VOC.llm_vocab_size, materialize=False)
+    m.enable_optimizer(device=dev)          # keeps the fp32 masters the verification forward (showo_forward_fp32) reads; the fast path is unaffected
     m.load_weights(W, device=dev)
     del W
     return m, probe
@@ -189,3 +190,25 @@ def test_config3_t2i_512_geometry_single_step(full, dev):
     _record("config3", {"max_abs_dlogit": float(err.max()), "mean_abs_dlogit": float(err.mean()), "argmax_flips": int(flips.sum())})
     assert err.max() < TOL_FULL
     assert (z["margin"][flips] <= 2 * TOL_FULL).all() and flips.mean() < 0.1
+
+
+def test_full_size_fp32_verification_forward(full, dev):
+    """The engine's fp32 verification forward at FULL size against the reference's own logits (full_slice.npz): 24
+    layers deep the two agree to fp32 re-association level and every argmax of the slice is the reference's -- the stricter claim the
+    bf16 tolerance cannot make; the fast path's error against it is the number the 0.08 tolerance is a multiple of."""
+    m, _ = full
+    z = FX.load("full_slice.npz")
+    ids, mask = FX.full_row_inputs(VOC)
+    off = VOC.image_offset
+    lg = m.forward_fp32(ids.to(dev), attention_mask=mask.to(dev))[:, 130:386, off:off + 8192].cpu()
+    err = np.abs(lg[:, ::16].numpy() - z["logits_slice"])
+    flips = lg.argmax(-1).numpy() != z["argmax"]
+    fast = m.t2i_step_logits(ids.to(dev), None, mask.to(dev), guidance_scale=0.0, config=cfg_ns()).cpu()
+    bf = (fast - lg).abs()
+    print(f"full-size fp32 verification forward vs the reference: max|dlogit| {err.max():.2e} mean {err.mean():.2e}, argmax flips {int(flips.sum())} of {flips.size}; "
+          f"fast bf16 path vs verification path: max {bf.max():.4f} mean {bf.mean():.5f}")
+    _record("fp32_verification_forward", {"max_abs_dlogit_vs_reference": float(err.max()), "mean_abs_dlogit_vs_reference": float(err.mean()),
+                                          "argmax_flips": int(flips.sum()), "bf16_vs_fp32_max": float(bf.max()), "bf16_vs_fp32_mean": float(bf.mean())})
+    assert err.max() < 2e-3
+    assert (z["margin"][flips] <= 4 * err.max()).all() and flips.sum() <= 1
+    assert bf.max().item() < TOL_FULL

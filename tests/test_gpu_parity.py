@@ -819,7 +819,7 @@ def test_magvit_fp32_verification_path(vq, dev):
           f"max {dfast.max():.4f} mean {dfast.mean():.5f}")
     _record("magvit_decode_fp32_path", {"max_abs_vs_oracle": float(d32.max()), "mean_abs_vs_oracle": float(d32.mean()),
                                         "fast_vs_fp32_max": float(dfast.max()), "fast_vs_fp32_mean": float(dfast.mean())})
-    assert got32.shape == (1, 3, 256, 256) and d32.max().item() < 5e-4
+    assert got32.shape == (1, 3, 256, 256) and d32.max().item() < 2e-4          # observed 2.9e-5
     assert (got32 - torch.from_numpy(g["decode"].astype(np.float32))).abs().max().item() < 2e-3        # the reference's own output (stored in half precision)
     assert dfast.max().item() < 0.2 and dfast.mean().item() < 0.012
     # non-square grid
@@ -835,7 +835,7 @@ def test_magvit_fp32_verification_path(vq, dev):
     dz = (z32 - z_ref).abs()
     print(f"magvit get_code, fp32 verification path: max |dz| vs the reference {dz.max():.2e}; codes differing {(codes32 != codes_ref).sum().item()} of 256; "
           f"smallest |z| of the fixture {z_ref.abs().min():.2e}")
-    assert dz.max().item() < 5e-4
+    assert dz.max().item() < 5e-5          # observed 5.7e-6
     bits_ref = z_ref.reshape(1, 13, -1) > 0
     bits32 = ((codes32[:, None, :] >> torch.arange(12, -1, -1)[None, :, None]) & 1).bool()
     assert ((bits32 != bits_ref) <= (z_ref.reshape(1, 13, -1).abs() < 2 * dz.max())).all()            # identical unless |z| is inside the fp32 noise
@@ -875,7 +875,7 @@ def test_backbone_fp32_verification_forward(lib, dev):
         ebf = (fast - got).abs()[nonpad].max().item()
         worst[kind] = (e32, ebf)
         print(f"{kind}: verification path vs oracle max |dlogit| {e32:.2e}; fast bf16 path vs verification path {ebf:.4f}")
-        assert e32 < 5e-4 and ebf < TOL_TINY
+        assert e32 < 5e-5 and ebf < TOL_TINY          # observed 2e-6 / 0.0094
         assert torch.equal(got[nonpad].argmax(-1), ref[nonpad].argmax(-1))
     _record("backbone_fp32_path", {k: {"fp32_vs_oracle": v[0], "bf16_vs_fp32": v[1]} for k, v in worst.items()})
     # ---- a whole generation, decisions bit-identical
@@ -902,7 +902,7 @@ def test_backbone_fp32_verification_forward(lib, dev):
         lc = full[:B, 130:386, off:off + 8192].contiguous()
         lu = full[B:, 130:386, off:off + 8192].contiguous()
         err = (((1 + w) * lc - w * lu).cpu() - tr.logits).abs().max().item()
-        assert err < 5e-4 * (1 + 2 * w), (s, err)
+        assert err < 5e-5 * (1 + 2 * w), (s, err)
         ex, un = tr.expo.to(dev), tr.uniform.to(dev)
         mk = torch.zeros(B, 256, dtype=torch.uint8, device=dev)
         _lib.check(lib.showo_sampler_step(_lib.ptr(lc), _lib.ptr(lu), B, 256, 8192, w, _lib.ptr(ids_run), 387, 130, off, VOC.mask_token_id,
