@@ -114,6 +114,18 @@ static bool gemm_order_auto() {
     return v == 1;
 }
 
+// SHOWO_GEMM_HINT=0: no L2 eviction hints.  Default: the operand that every wave reads again is loaded evict_last when it is small enough
+// to live in the L2 next to the streaming operand (<= 64 MB)
+static void gemm_l2_hints(GemmParams& p, int64_t a_bytes, int64_t b_bytes, int tiles, int clusters) {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SHOWO_GEMM_HINT"); v = (e && atoi(e) == 0) ? 0 : 1; }
+    p.hint_a = p.hint_b = 0;
+    if (!v || tiles <= clusters) return;                       // one wave: nothing is read twice
+    const int64_t kMax = (int64_t)64 << 20;
+    if (p.n_fast) { if (b_bytes <= kMax) p.hint_b = kL2EvictLast; }
+    else if (a_bytes <= kMax) p.hint_a = kL2EvictLast;
+}
+
 // 2-D bf16 tensor map with 128B swizzle for other TMA users (attention_tc.cu): dims = {inner, rows}, row stride in bytes
 int make_tmap_2d(void* out_cutensormap, const void* ptr, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes,
                  uint32_t box_inner, uint32_t box_rows) {
@@ -213,6 +225,7 @@ static int gemm_bn(const GemmArgs& a, GemmEpi epi, cudaStream_t st) {
     }
     const int tiles = cdiv(cdiv(a.M, 128), CL) * cdiv(a.N, BN);
     p.n_fast = (gemm_order_auto() && a.M > a.N && tiles > gemm_num_sms() / CL) ? 1 : 0;
+    if constexpr (CG == 2) gemm_l2_hints(p, (int64_t)a.M * a.K * 2, (int64_t)a.N * a.K * 2, tiles, gemm_num_sms() / CL);
     if constexpr (CG == 2) {
         // stream-K for the residual GEMM when the tiles do not fill whole waves of clusters (dense|fc2: 136 tiles on 74 clusters)
         const int clusters = std::min(tiles, gemm_num_sms() / CL), num_kb = cdiv(a.K, BK);
@@ -244,6 +257,7 @@ int gemm_bf16_tn(const GemmArgs& a, cudaStream_t st) {
     p.M = a.M; p.N = a.N; p.K = a.K; p.out = a.out; p.ldc = a.ldc; p.bias = a.bias; p.gelu_from = a.N;
     const int tiles = cdiv(cdiv(a.M, 128), CL) * cdiv(a.N, BN);
     p.n_fast = (gemm_order_auto() && a.M > a.N && tiles > gemm_num_sms() / CL) ? 1 : 0;
+    gemm_l2_hints(p, (int64_t)a.M * a.K * 2, (int64_t)a.N * a.K * 2, tiles, gemm_num_sms() / CL);
     return launch<BN, EPI_BIAS_F32, A_MN, BK, CL, CG>(ma, mb, p, tiles, st);
 }
 
@@ -287,7 +301,9 @@ static int gemm_qkv_bn(const GemmArgs& a, const QkvFuse& f, cudaStream_t st) {
     p.cos_tab = f.cos_tab; p.sin_tab = f.sin_tab; p.kcache = f.kcache; p.vtcache = f.vtcache;
     p.ln_part_in = f.ln_part; p.ln_c = f.ln_c; p.ln_eps = f.ln_eps;
     if (f.ln_part != nullptr) SHOWO_CHECK(f.ln_c != nullptr && a.K % 64 == 0, "gemm_qkv: folded LayerNorm needs c_n and K % 64 == 0");
-    return launch<BN, EPI_QKV_BF16, A_PLAIN, BK, CL, CG>(ma, mb, p, cdiv(cdiv(a.M, 128), CL) * cdiv(a.N, BN), st);
+    const int tiles = cdiv(cdiv(a.M, 128), CL) * cdiv(a.N, BN);
+    if constexpr (CG == 2) gemm_l2_hints(p, (int64_t)a.M * a.K * 2, (int64_t)a.N * a.K * 2, tiles, gemm_num_sms() / CL);   // M sweeps first: A is re-read by every wave
+    return launch<BN, EPI_QKV_BF16, A_PLAIN, BK, CL, CG>(ma, mb, p, tiles, st);
 }
 
 int gemm_qkv_bf16(const GemmArgs& a, const QkvFuse& f, cudaStream_t st) {

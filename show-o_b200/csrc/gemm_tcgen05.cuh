@@ -68,6 +68,9 @@ struct GemmParams {
     // layer's second GEMM, the weight gradients of wide layers, dgrad into a narrow layer).  Measured cause: dense|fc2 at
     // 4128 x 2048 x 10240 moved 267 MB for 194 MB algorithmic in order 0 (A = 85 MB crossed DRAM once per wave).
     int n_fast;
+    // L2 eviction priority of the two operand streams (CTA-pair path): the operand every wave reads again (A when M sweeps first, B
+    // when N sweeps first) is loaded evict_last so that the streaming operand does not push it out of the L2; 0 = no preference
+    uint64_t hint_a, hint_b;
     int* sk_flags;          // [units][2] one flag per (tile, CTA rank), zero between launches
 };
 
@@ -185,6 +188,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             uint32_t phase = 0;
             GemmSegCursor cur(sk, unit0, unit_stride, num_units, num_kb);
             int unit, kb_begin, kb_end;
+            const uint64_t hint_a = p.hint_a ? p.hint_a : kL2EvictNormal, hint_b = p.hint_b ? p.hint_b : kL2EvictNormal;
+            (void)hint_a; (void)hint_b;
             while (cur.next(unit, kb_begin, kb_end)) {
                 const int tm = (p.n_fast ? unit / tiles_n : unit % tiles_mc) * CL + crank, tn = p.n_fast ? unit % tiles_n : unit / tiles_mc;
                 int img = 0, y0 = 0, x0 = 0;
@@ -206,17 +211,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             for (int h = 0; h < BK / 64; ++h)
 #pragma unroll
                                 for (int q = 0; q < 2; ++q) {
-                                    tma_load_2d_cg2(smem_a + stage * Cfg::kAB + (h * 2 + q) * 8192, &tmap_a, &full_bar[stage], tm * BM + q * 64,
-                                                    kb * BK + h * 64);
-                                    tma_load_2d_cg2(smem_b + stage * Cfg::kBB + (h * 2 + q) * 8192, &tmap_b, &full_bar[stage],
-                                                    tn * BN + crank * (BN / 2) + q * 64, kb * BK + h * 64);
+                                    tma_load_2d_cg2_hint(smem_a + stage * Cfg::kAB + (h * 2 + q) * 8192, &tmap_a, &full_bar[stage], tm * BM + q * 64,
+                                                         kb * BK + h * 64, hint_a);
+                                    tma_load_2d_cg2_hint(smem_b + stage * Cfg::kBB + (h * 2 + q) * 8192, &tmap_b, &full_bar[stage],
+                                                         tn * BN + crank * (BN / 2) + q * 64, kb * BK + h * 64, hint_b);
                                 }
                         } else {
 #pragma unroll
                         for (int h = 0; h < BK / 64; ++h) {      // a stage = BK/64 sub-tiles of 64 k (one 128B swizzle atom wide)
-                            tma_load_2d_cg2(smem_a + stage * Cfg::kAB + h * (BM * 128), &tmap_a, &full_bar[stage], kb * BK + h * 64, tm * BM);
-                            tma_load_2d_cg2(smem_b + stage * Cfg::kBB + h * ((BN / 2) * 128), &tmap_b, &full_bar[stage], kb * BK + h * 64,
-                                            tn * BN + crank * (BN / 2));
+                            tma_load_2d_cg2_hint(smem_a + stage * Cfg::kAB + h * (BM * 128), &tmap_a, &full_bar[stage], kb * BK + h * 64, tm * BM, hint_a);
+                            tma_load_2d_cg2_hint(smem_b + stage * Cfg::kBB + h * ((BN / 2) * 128), &tmap_b, &full_bar[stage], kb * BK + h * 64,
+                                                 tn * BN + crank * (BN / 2), hint_b);
                         }
                         }
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
