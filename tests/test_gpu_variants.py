@@ -20,6 +20,7 @@ VARIANTS = {
     "attention_mma_sync": ({"SHOWO_ATTN_TC": "0"}, ATTN_K),
     "gemm_streamk": ({"SHOWO_GEMM_STREAMK": "1"}, GEMM_K + " or streamk"),
     "gemm_order_m_first": ({"SHOWO_GEMM_ORDER": "0"}, GEMM_K + " or token_major"),
+    "gemm_l2_evict_last_hint": ({"SHOWO_GEMM_HINT": "1"}, GEMM_K + " or token_major"),
     "gemm_one_cta": ({"SHOWO_GEMM_CG": "1"}, GEMM_K),
     "gemm_cluster_multicast": ({"SHOWO_GEMM_CG": "1", "SHOWO_GEMM_CL": "2"}, GEMM_K),
     "gemm_bk32": ({"SHOWO_GEMM_CG": "1", "SHOWO_GEMM_BK": "32"}, GEMM_K),
