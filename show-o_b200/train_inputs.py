@@ -200,7 +200,6 @@ class UniversalPrompting:
                 t = [tk.bos_token_id]
             elif t[0] != tk.bos_token_id:
                 t = [tk.bos_token_id] + t
-            text_ids[i] = t                                   # the reference rewrites the caller's list the same way
             ids = [int(self.sptids_dict["<|t2i|>"])] + t + [tk.eos_token_id]
             if T >= len(ids):
                 n_pad = T - len(ids)

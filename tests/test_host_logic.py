@@ -306,3 +306,29 @@ def test_editing_downward_extrapolation_runs_where_the_reference_script_raises()
         gen = (torch.arange(2 * 64).reshape(2, 8, 8) * 3) % 8192
         assert torch.equal(editing.extrapolation_merge(g, gen, "up", off, 8), editing.extrapolation_merge(g.flip(1), gen.flip(1), "down", off, 8).flip(1))
         assert editing.extrapolation_merge(g, gen, "down", off, 8).shape == (2, 8 + 4 + off, 8)
+
+
+def test_clip_vision_tower_loads_a_local_checkpoint_like_the_reference(tmp_path):
+    """CLIPVisionTower(name) as inference_mmu.py:73-74 constructs it (`name` = hub id or local directory): `transformers` reads config,
+    weights and the image processor; the weights land under CLIPVisionModel.state_dict() names ready for the engine, and the oracle on
+    those weights equals the library model that wrote the checkpoint."""
+    transformers = pytest.importorskip("transformers")
+    from oracle import clip_oracle as CO
+    from showo_b200 import CLIPVisionTower
+    cfg = transformers.CLIPVisionConfig(hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2, image_size=28, patch_size=14)
+    torch.manual_seed(4)
+    ref = transformers.CLIPVisionModel(cfg).eval()
+    ref.save_pretrained(str(tmp_path))
+    transformers.CLIPImageProcessor(size={"shortest_edge": 28}, crop_size={"height": 28, "width": 28}).save_pretrained(str(tmp_path))
+    tower = CLIPVisionTower(str(tmp_path))
+    assert tower.is_loaded and tower.image_processor is not None and tower.vision_tower_name == str(tmp_path)
+    assert tower.num_patches == 4 and tower.hidden_size == 128 and tower.config.num_hidden_layers == 2
+    sd = {k: v for k, v in ref.state_dict().items() if "position_ids" not in k}
+    assert set(tower._weights) == set(sd) and all(torch.equal(tower._weights[k], sd[k]) for k in sd)
+    x = torch.randn(2, 3, 28, 28)
+    d = CO.ClipDims(image_size=28, patch_size=14, hidden=128, n_layers=2, n_heads=2, ffn=256)
+    with torch.no_grad():
+        want = ref(x, output_hidden_states=True).hidden_states[-2][:, 1:]
+        got = CO.tower_features(x, tower._weights, d)
+    assert (got - want).abs().max().item() < 1e-5
+    tower.load_model()          # "already loaded" like the reference, no reload
