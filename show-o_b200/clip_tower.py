@@ -38,7 +38,7 @@ class CLIPVisionTower(nn.Module):
         self.select_feature = "patch"     # drop the CLS token (:14)
         self._engine = None
         self._engine_device = None
-        self._anchor = nn.Parameter(torch.zeros(()), requires_grad=False)      # follows .to(device): where the engine lives
+        self.register_buffer("_anchor", torch.zeros(()), persistent=False)        # follows .to(device): where the engine lives; not in state_dict()
         self.image_processor = None
         state = None
         if isinstance(vision_tower, dict):
@@ -73,7 +73,7 @@ class CLIPVisionTower(nn.Module):
             _lib.load().clip_engine_destroy(self._engine)
             self._engine = None
         if device is not None:
-            self._anchor.data = self._anchor.data.to(device)
+            self._anchor = self._anchor.to(device)
         if self._anchor.is_cuda:
             self._sync()
         return self
