@@ -111,3 +111,55 @@ def test_clip_vit_l14_336_full_size_against_the_oracle(dev):
     flop = 16 * 23 * (577 * 2 * (4 * 1024 * 1024 + 2 * 1024 * 4096) + 4 * 577 * 577 * 1024) + 16 * 576 * 2 * 1024 * 588
     print(f"clip ViT-L/14-336, 16 images: {ms:.2f} ms = {16e3 / ms:.0f} images/s, {flop / ms / 1e9:.0f} TFLOP/s")
     _record("clip_vit_l14_336_speed", {"ms_per_16_images": ms, "tflops": flop / ms / 1e9})
+
+
+def test_inference_mmu_w_clip_vit_call_shape_end_to_end(dev):
+    """The w_clip_vit branch of inference_mmu.py:100-151 as the script writes it, every stage on the engine: `vision_tower(pixel_values[None])`
+    (CLIP ViT, 336 x 336 -> [1, 576, 1024]) -> `model.mm_projector(...)` -> `model.showo.model.embed_tokens(input_ids_llava)` -> cat around the
+    image embeddings -> `create_attention_mask_for_mmu_vit` (dense) -> `model.mmu_generate(input_embeddings=, attention_mask=, top_k=1, eot_token=)`
+    -> `torch.stack(cont_toks_list).squeeze()[None]`.  A 1-layer backbone of the real width (the projector's output is 2048 wide) and a 3-layer
+    ViT of the real width; the input embeddings and the first generated token against the oracles' fp32 flow."""
+    from oracle import showo_oracle as O
+    dims = O.PhiDims(hidden=2048, n_layers=1, n_heads=32, ffn=2048)
+    W = O.make_showo_weights(dims, seed=8, w_clip_vit=True)
+    m = showo_b200.Showo(True, dims.vocab_size, 50295, phi_dims=dict(hidden=2048, n_layers=1, n_heads=32, ffn=2048)).to(dev)
+    m.load_state_dict(W, strict=True)
+    m.eval()
+    cd = CO.ClipDims(n_layers=3)
+    CW, vision_tower = _tower(cd, dev)
+    SYS = 28
+    r = np.random.Generator(np.random.Philox(23))
+    pixel_values = _pixels(21, 1, 336)[0]
+    mmu, soi, eoi = 50301, 50296, 50297
+    sys_ids = torch.from_numpy(r.integers(0, 50257, size=(1, SYS)).astype("int64"))
+    q_ids = torch.from_numpy(r.integers(0, 50257, size=(1, 12)).astype("int64"))
+    input_ids_llava = torch.cat([torch.full((1, 1), mmu), sys_ids, torch.full((1, 1), soi), torch.full((1, 1), eoi), q_ids], dim=1).long()
+    with torch.no_grad():
+        images_embeddings = vision_tower(pixel_values[None].to(dev))
+        assert images_embeddings.shape == (1, 576, 1024)
+        images_embeddings = m.mm_projector(images_embeddings)
+        text_embeddings = m.showo.model.embed_tokens(input_ids_llava.to(dev))
+        part1, part2 = text_embeddings[:, :2 + SYS, :], text_embeddings[:, 2 + SYS:, :]
+        input_embeddings = torch.cat((part1, images_embeddings, part2), dim=1)
+        L = input_embeddings.shape[1]
+        attention_mask_llava = O.additive_from_allowed(O.mask_allowed_mmu_vit(1, L, system_prompt_len=SYS)).to(dev)      # create_attention_mask_for_mmu_vit
+        cont_toks_list = m.mmu_generate(input_embeddings=input_embeddings, attention_mask=attention_mask_llava[0].unsqueeze(0),
+                                        max_new_tokens=6, top_k=1, eot_token=50256)
+    cont = torch.stack(cont_toks_list).squeeze()[None]
+    assert 1 <= cont.numel() <= 6 and cont.dtype == torch.int64          # (a single token squeezes to [1], like in the reference)
+    # ---- the oracles' flow in fp32
+    with torch.no_grad():
+        f_ref = CO.tower_features(pixel_values[None], CW, cd)
+        h = torch.nn.functional.gelu(f_ref @ W["mm_projector.0.weight"].T + W["mm_projector.0.bias"])
+        v_ref = h @ W["mm_projector.2.weight"].T + W["mm_projector.2.bias"]
+        e_ref = W["showo.model.embed_tokens.weight"][input_ids_llava]
+        emb_ref = torch.cat((e_ref[:, :2 + SYS], v_ref, e_ref[:, 2 + SYS:]), dim=1)
+        lg = O.showo_logits(W, dims, input_embeddings=emb_ref, add_mask=attention_mask_llava.cpu())[:, -1]
+    rel = float((input_embeddings.cpu() - emb_ref).norm() / emb_ref.norm())
+    top2 = lg.topk(2)
+    first = int(cont.reshape(-1)[0])
+    print(f"inference_mmu w_clip_vit flow: input embeddings rel L2 {rel:.5f}; first token {first} (oracle {int(top2.indices[0, 0])}, margin {float(top2.values[0, 0] - top2.values[0, 1]):.4f})")
+    _record("inference_mmu_w_clip_vit_flow", {"input_embeddings_rel_l2": rel, "first_token_equal": first == int(top2.indices[0, 0])})
+    assert rel < 0.01
+    if first != int(top2.indices[0, 0]):
+        assert float(top2.values[0, 0] - top2.values[0, 1]) < 0.06 and first == int(top2.indices[0, 1])
