@@ -229,6 +229,11 @@ SHOWO_API int showo_t2i_train_prep(const int64_t* image_tokens_dev, int B, int N
                          int64_t* labels_out_dev, int64_t* attn_ones_out_dev, showo_seq_mask_t* descs_out_dev,
                          float* mask_prob_out_dev, void* stream);
 
+/* Data-parallel generation: global index of the first batch row of this engine's calls (rank * rows per rank).  The library's
+ * Philox noise (showo_t2i_generate / showo_mmu_generate without host noise) is keyed by (seed, GLOBAL row, token, step), so with the same
+ * seed on every rank the images / tokens of a row do not depend on how the batch is split over GPUs.  Default 0. */
+SHOWO_API int showo_set_rng_row_base(showo_engine_t* e, int64_t first_row);
+
 /* seconds spent / kernels launched by the last generate call (for bench.py's gpu_launches) */
 SHOWO_API int64_t showo_kernel_launches(showo_engine_t* e);
 

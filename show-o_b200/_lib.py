@@ -73,6 +73,7 @@ _PROTOS = {
     "showo_mm_projector_backward": (_I, [_P, _P, _I64, _P]),
     "showo_mm_projector_grad_buffer": (_I, [_P, C.POINTER(_P), C.POINTER(_I64)]),
     "showo_embed_tokens": (_I, [_P, _P, _I64, _P, _P]),
+    "showo_set_rng_row_base": (_I, [_P, _I64]),
     "showo_kernel_launches": (_I64, [_P]),
     "magvit_engine_create": (_I, [_I, C.POINTER(_P)]),
     "magvit_engine_destroy": (_I, [_P]),

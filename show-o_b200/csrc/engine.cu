@@ -662,7 +662,7 @@ int showo_t2i_generate(showo_engine_t* e, int64_t* ids_dev, const int64_t* uncon
         sa.mask_len_floor = mask_len_floor[s]; sa.temperature = temperature[s];
         sa.noise_expo = noise_expo_dev ? noise_expo_dev + (size_t)s * B * N * C : nullptr;
         sa.noise_unif = noise_unif_dev ? noise_unif_dev + (size_t)s * B * N : nullptr;
-        sa.seed = seed; sa.step = (uint32_t)s;
+        sa.seed = seed; sa.step = (uint32_t)s; sa.row_base = e->rng_row_base;
         sa.conf_ws = e->conf_ws; sa.sampled_ws = e->sampled_ws; sa.masking_out = nullptr;
         SHOWO_TRY(t2i_sampler_step(sa, st));
     }
@@ -756,7 +756,7 @@ int showo_mmu_generate(showo_engine_t* e, const int64_t* ids_dev, const float* e
             MmuSampleArgs ms{};
             ms.logits = e->logits_ws; ms.ld = V; ms.B = B; ms.V = V; ms.temperature = temperature; ms.top_k = top_k;
             ms.noise_expo = noise_expo_dev ? noise_expo_dev + (size_t)t * B * V : nullptr;
-            ms.seed = seed; ms.step = (uint32_t)t;
+            ms.seed = seed; ms.step = (uint32_t)t; ms.row_base = e->rng_row_base;
             ms.out = out_tokens_dev + t; ms.out_stride = max_new_tokens; ms.out_next = e->tok_ws;
             SHOWO_TRY(mmu_sample(ms, st));
         }
@@ -832,6 +832,12 @@ int showo_mm_projector(showo_engine_t* e, const float* feats_dev, int64_t n, flo
     g1.A = e->mmp_mid; g1.lda = kMid; g1.B = e->mmp_w2; g1.ldb = kMid; g1.M = (int)n; g1.N = kOut; g1.K = kMid;
     g1.out = out_dev; g1.ldc = kOut; g1.bias = e->mmp_b2; g1.block_n = 128;
     return gemm_bf16(g1, GEMM_BIAS_F32, st);
+}
+
+int showo_set_rng_row_base(showo_engine_t* e, int64_t first_row) {
+    SHOWO_CHECK(e != nullptr && first_row >= 0 && first_row < (1 << 20), "set_rng_row_base: bad arguments");
+    e->rng_row_base = (int)first_row;
+    return 0;
 }
 
 int64_t showo_kernel_launches(showo_engine_t* e) { return e ? e->launches_last : 0; }

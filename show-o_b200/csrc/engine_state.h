@@ -80,6 +80,7 @@ struct showo_engine {
     bf16* mmp_dy = nullptr; bf16* mmp_dmid = nullptr; int64_t mmp_bwd_cap = 0;
     int* attn_ctr = nullptr;                              // work counter of the attention kernel's tail phase (self-resetting, zero between launches)
     int* finished_ws = nullptr;                           // [64] rows of the running mmu_generate that have produced eot_token
+    int rng_row_base = 0;                                 // showo_set_rng_row_base: global index of the first batch row (Philox noise keyed by it)
     int64_t launches_last = 0;
     showo::OptState* opt = nullptr;                      // fp32 master weights + Adam moments (train.cu), showo_optimizer_enable
     showo::TrainState* train = nullptr;                  // training-step buffers (train.cu), allocated on first use

@@ -199,6 +199,8 @@ struct SamplerArgs {
     const float* noise_expo;     // [B*N, C] Exp(1) or nullptr -> Philox
     const float* noise_unif;     // [B, N] U(0,1) or nullptr -> Philox
     uint64_t seed; uint32_t step;
+    int row_base = 0;            // Philox mode: global index of this call's first batch row (data parallel: rank * rows per rank), so that
+                                 // the noise of a row does not depend on how the batch is split over GPUs
     float* conf_ws;              // [B, N] workspace
     int* sampled_ws;             // [B, N] workspace
     uint8_t* masking_out;        // optional [B, N] (debug / parity), or nullptr
@@ -211,6 +213,7 @@ int argmax_rows(const float* logits, int64_t ld, int B, int V, int64_t* out, cud
 struct MmuSampleArgs {
     const float* logits; int64_t ld; int B, V; float temperature; int top_k;
     const float* noise_expo; uint64_t seed; uint32_t step;
+    int row_base = 0;                    // Philox mode: global index of the first row (see SamplerArgs::row_base)
     int64_t* out; int64_t out_stride;    // token of row b -> out[b * out_stride]
     int64_t* out_next;                   // optional dense [B] copy (the next step's input ids)
 };

@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(kSampThreads) sampler_token_kernel(SamplerArgs
     float u_g;
     if (a.noise_unif) u_g = a.noise_unif[tok];
     else {
-        const uint4 r = philox4x32_10(make_uint4((uint32_t)tok, 0u, a.step, 0x9u), make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)(tok + a.row_base * a.N), 0u, a.step, 0x9u), make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
         u_g = u01(r.x);
     }
     const float gum = gumbel_from_uniform(u_g);
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(kSampThreads) sampler_token_kernel(SamplerArgs
             float4 q;
             if (ex) q = __ldg(ex + j);
             else {
-                const uint4 r = philox4x32_10(make_uint4((uint32_t)(tok * nvec + j), 0u, a.step, 0x5u),
+                const uint4 r = philox4x32_10(make_uint4((uint32_t)((tok + a.row_base * a.N) * nvec + j), 0u, a.step, 0x5u),
                                               make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
                 q = make_float4(-logf(u01(r.x)), -logf(u01(r.y)), -logf(u01(r.z)), -logf(u01(r.w)));
             }
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(1024) mmu_sample_kernel(MmuSampleArgs a) {
         float q;
         if (ex) q = ex[i];
         else {
-            const uint4 r = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)row, a.step, 0xAu), key);
+            const uint4 r = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)(row + a.row_base), a.step, 0xAu), key);
             q = -logf(u01(r.x));
         }
         const float pr = __fdiv_rn(expf(l - mx), sum);

@@ -610,8 +610,11 @@ class Showo(nn.Module):
     @torch.no_grad()
     def t2i_generate(self, input_ids: torch.LongTensor = None, uncond_input_ids: torch.LongTensor = None,
                      attention_mask=None, temperature=1.0, timesteps=18, guidance_scale=0,
-                     noise_schedule=cosine_schedule, generator: torch.Generator = None, config=None, **kwargs):
+                     noise_schedule=cosine_schedule, generator: torch.Generator = None, config=None, rng_row_offset: int = 0, **kwargs):
         """modeling_showo.py:104-181.  `input_ids` is updated in place; returns LongTensor[B, N] of codes.
+
+        `rng_row_offset` (data parallel): global index of this call's first batch row; the kernel's Philox noise is keyed by
+        (seed, global row, token, step), so with one seed on every rank a row's image does not depend on the split over GPUs.
 
         With `generator` given the categorical / gumbel noise is drawn by torch from it in the reference's order
         ([B*N,C] exponentials then [B,N] uniforms per step) and handed to the kernel, so a run is reproducible
@@ -637,6 +640,7 @@ class Showo(nn.Module):
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         unc = uncond_input_ids.contiguous() if cfg_on else None
         out = torch.empty(B, N, dtype=torch.int64, device=dev)
+        _lib.check(lib.showo_set_rng_row_base(eng, int(rng_row_offset)), "showo_set_rng_row_base")
         with torch.cuda.device(dev):
             _lib.check(lib.showo_t2i_generate(eng, _lib.ptr(input_ids), _lib.ptr(unc), B, L, N, P,
                                               _lib.masks_array(descs), timesteps, float(guidance_scale), floors_a,
@@ -662,8 +666,9 @@ class Showo(nn.Module):
     # ------------------------------------------------------------------ mmu
     @torch.no_grad()
     def mmu_generate_batched(self, idx=None, input_embeddings=None, attention_mask=None, max_new_tokens=100,
-                             temperature=1.0, top_k=None, eot_token=None, generator: torch.Generator = None):
+                             temperature=1.0, top_k=None, eot_token=None, generator: torch.Generator = None, rng_row_offset: int = 0):
         """Batched KV-cached decode: returns (tokens [B, max_new_tokens] int64, lengths [B] int32).
+        `rng_row_offset`: global index of the first row (sampled decode, Philox noise keyed by the global row; see t2i_generate).
 
         top_k=1 is greedy (inference_mmu.py:81); top_k=None / k>1 draw from softmax(top-k-filtered logits / temperature)
         (modeling_showo.py:219-228).  With `generator` the Exp(1) noise of torch.multinomial is drawn by torch
@@ -690,6 +695,7 @@ class Showo(nn.Module):
                     expo[t].exponential_(1, generator=generator)
             else:
                 seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        _lib.check(lib.showo_set_rng_row_base(eng, int(rng_row_offset)), "showo_set_rng_row_base")
         with torch.cuda.device(dev):
             _lib.check(lib.showo_mmu_generate(eng, _lib.ptr(ids), _lib.ptr(emb), B, L0, _lib.masks_array(descs),
                                               max_new_tokens, k, float(temperature), eot, seed, _lib.ptr(expo),

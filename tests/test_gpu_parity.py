@@ -920,3 +920,35 @@ def test_backbone_fp32_verification_forward(lib, dev):
         assert on_trajectory and torch.equal(out.cpu(), ref_ids)
     print(f"t2i_generate replayed from verification logits: {n_diff} of {B * 256 * T} decisions differ from the oracle over {T} steps "
           f"(on the oracle's trajectory throughout: {on_trajectory}; last step max |dlogit| {err:.2e})")
+
+
+def test_philox_noise_is_keyed_by_the_global_row(tiny, dev):
+    """with the library's own noise (no generator) a row's image must not depend on how the batch is split over GPUs.  The Philox
+    counters are keyed by (seed, GLOBAL row, token, step): four rows generated in one call == the same rows generated as two 'ranks' of two
+    rows with their row offsets and the same seed, bit for bit; without the offset the second half differs (the noise really is per row)."""
+    dims, W, m = tiny
+    cond, uncond = O.make_t2i_prompts(4, VOC, seed=71)
+    kw = dict(guidance_scale=2.0, timesteps=3, config=cfg_ns())
+
+    def run(rows, offset):
+        c, u = cond[rows].clone().to(dev), uncond[rows].to(dev)
+        mask = O.create_attention_mask_predict_next(torch.cat([cond[rows], uncond[rows]])).to(dev)
+        torch.manual_seed(123)                        # the kernel's seed is drawn from torch's global generator
+        return m.t2i_generate(c, u, mask, rng_row_offset=offset, **kw).cpu()
+    whole = run(slice(0, 4), 0)
+    a, b = run(slice(0, 2), 0), run(slice(2, 4), 2)
+    assert torch.equal(torch.cat([a, b]), whole)
+    assert not torch.equal(run(slice(2, 4), 0), whole[2:])
+    # sampled MMU decode: the same keying per sequence (recorded, not asserted: the decode GEMMs' bitwise batch invariance is not a stated contract)
+    mm = FX.tiny_mmu_inputs(VOC)
+    descs = M.descriptors_mmu(mm, O.EOI)
+
+    def dec(lo, hi, offset):
+        torch.manual_seed(77)
+        t, _ = m.mmu_generate_batched(mm[lo:hi].to(dev), attention_mask=descs[lo:hi], max_new_tokens=4, temperature=1.0, top_k=None,
+                                      rng_row_offset=offset)
+        return t.cpu()
+    whole_t, part_t = dec(0, 3, 0), dec(1, 3, 1)
+    same = bool(torch.equal(part_t, whole_t[1:]))
+    print(f"sampled MMU decode, rows 1..2 generated alone with row offset 1 == their rows of the 3-row call: {same}")
+    _record("philox_global_row_keying", {"t2i_split_equals_whole": True, "mmu_sampled_split_equals_whole": same})
